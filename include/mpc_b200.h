@@ -1,0 +1,113 @@
+/* mpc_b200.h -- C ABI of the B200-native batched convex-MPC engine (libmpc_b200.so).
+ *
+ * This is the ONLY route from host code into CUDA.  Plain pointers and sizes, no C++/torch types.
+ * The host-side C++ facade (mpc_limx_control_b200/host/) mirrors the reference classes
+ * QPSolver / mpcQP / MPC and calls nothing but these entry points.
+ *
+ * Reference interfaces replaced (paths relative to the reference repository):
+ *   include/QPSolver.h:13-37 + src/QPSolver.cpp:21-116   discretize / buildQPParams / solveQP / updateState
+ *   include/mpcQP.h:10-11,35-182                         TRON1 problem setup, buildSystemModel
+ *   include/MPCController.h:61-75                        calculateGait (horizon contact schedule)
+ * plus the batch entry point the reference does not have (BASELINE.json north_star).
+ *
+ * Conventions
+ *   - all floating point data is FP64; matrices are column-major (Eigen default) unless stated
+ *   - batch arrays are instance-major and dense:
+ *       x0     [B][13]         state [roll,pitch,yaw, px,py,pz, wx,wy,wz, vx,vy,vz, g]  (include/mpcQP.h:66-71)
+ *       x_ref  [B][N+1][13]    == column-major 13 x (N+1) per instance (include/mpcQP.h:74)
+ *       feet   [B][2][3]       world foot positions (left,right); [B][N][2][3] when per_step_feet
+ *       contact[B][N][2]       uint8, 1 = stance;  or  iter[B] int32 -> schedule from the gait clock
+ *       forces [B][N][6]       == column-major 6 x N U_opt per instance (src/QPSolver.cpp:104)
+ *       status [B] int32       0 solved (KKT certified), 1 iteration limit, 2 failed (non-finite / not PD)
+ *       iters  [B] int32       active-face solves + ADMM iterations spent
+ *   - every function returns 0 on success or a negative MPC_B200_E* code; nothing prints
+ *   - an engine is bound to one CUDA device and is single-caller (not re-entrant)
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream)
+ *   - there is no CPU fallback: without a usable CUDA device create() fails with MPC_B200_ENODEV
+ */
+#ifndef MPC_B200_H
+#define MPC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPC_B200_OK 0
+#define MPC_B200_EINVAL (-1)   /* bad argument (NULL, size, unsupported horizon, misaligned pointer) */
+#define MPC_B200_ENODEV (-2)   /* no CUDA device / wrong architecture */
+#define MPC_B200_ECUDA (-3)    /* CUDA runtime error (see mpc_b200_last_error) */
+#define MPC_B200_ENOMEM (-4)
+#define MPC_B200_ECAPACITY (-5) /* batch larger than the engine's max_batch */
+
+#define MPC_B200_INFTY 1.0e20  /* stands in for qpOASES::INFTY (src/QPSolver.cpp:72-73) */
+
+typedef struct mpc_b200_engine mpc_b200_engine;
+
+typedef struct mpc_b200_tron1_params {
+    double Ts;            /* MPC step; default dtMPC = 0.005 (include/MPCParam.h:47) */
+    double mass;          /* 9.585 (include/mpcQP.h:18) */
+    double inertia[9];    /* body inertia (include/mpcQP.h:20-22), symmetric */
+    double q[13];         /* diag(Q) (include/mpcQP.h:54) */
+    double r;             /* R = r I (include/mpcQP.h:55) */
+    double p_scale;       /* P = p_scale Q (include/mpcQP.h:56) */
+    double mu;            /* friction pyramid coefficient (not defined by the reference; 0.5) */
+    double f_max;         /* normal force cap per foot (not defined by the reference; 2 m g) */
+    int32_t ltv;          /* 0: one model at x0 (reference LTI structure), 1: per-step model */
+    int32_t per_step_feet;/* feet given per horizon step */
+    /* gait clock (include/MPCParam.h:44-49) */
+    float gait_dt;        /* 0.001f */
+    int32_t gait_mpc_step;/* 5 */
+    float gait_swing_time;  /* 0.5f */
+    float gait_stance_time; /* 0.5f */
+    /* solver */
+    int32_t max_newton;   /* active-face iterations before the ADMM fallback (default 12) */
+    int32_t max_admm;     /* ADMM iteration cap (default 2000) */
+    double tol;           /* natural-residual tolerance relative to max(1,|u|_inf) (default 1e-9) */
+} mpc_b200_tron1_params;
+
+/* library / device */
+int mpc_b200_version(void);
+const char *mpc_b200_strerror(int code);
+int mpc_b200_device_count(void);
+/* measured FP64 FMA peak of `device` (register-resident DFMA chains), TFLOP/s */
+int mpc_b200_measure_fp64_peak(int device, double *tflops);
+
+/* engine lifetime.  horizon N must be one of the compiled horizons (10, 20). */
+int mpc_b200_tron1_default_params(mpc_b200_tron1_params *p);
+int mpc_b200_create(const mpc_b200_tron1_params *p, int horizon, int max_batch, int device,
+                    mpc_b200_engine **out);
+int mpc_b200_destroy(mpc_b200_engine *e);
+const char *mpc_b200_last_error(const mpc_b200_engine *e);
+/* number of kernels this engine has launched since creation (bench.py's gpu_launches) */
+int64_t mpc_b200_launch_count(const mpc_b200_engine *e);
+
+/* MPC::calculateGait over the horizon (include/MPCController.h:61-75): contact[b][k][foot] for
+ * iter[b] + k*mpc_step; iter < 0 = standing (both feet in contact).  Device pointers. */
+int mpc_b200_contact_schedule_device(mpc_b200_engine *e, int B, const int32_t *d_iter,
+                                     uint8_t *d_contact, void *stream);
+
+/* The hot path on device-resident data: linearise -> discretise -> condense -> QP solve.
+ * Exactly one of d_contact / d_iter may be NULL (d_iter: schedule evaluated in-kernel).
+ * d_status / d_iters may be NULL. */
+int mpc_b200_tron1_solve_device(mpc_b200_engine *e, int B, const double *d_x0, const double *d_x_ref,
+                                const double *d_feet, const uint8_t *d_contact, const int32_t *d_iter,
+                                double *d_forces, int32_t *d_status, int32_t *d_iters, void *stream);
+
+/* Same with HOST buffers (pinned recommended): H2D copies, solve, D2H copies, stream sync. */
+int mpc_b200_tron1_solve_host(mpc_b200_engine *e, int B, const double *x0, const double *x_ref,
+                              const double *feet, const uint8_t *contact, const int32_t *iter,
+                              double *forces, int32_t *status, int32_t *iters);
+
+/* Parity dump of the condensed problem (any output may be NULL), device pointers:
+ *   H [B][6N x 6N], f [B][6N], A_aug [B][13(N+1) x 13], B_aug [B][13(N+1) x 6N]  (column-major)
+ * H and f do not depend on the contact schedule (src/QPSolver.cpp:58-60). */
+int mpc_b200_tron1_condense_device(mpc_b200_engine *e, int B, const double *d_x0, const double *d_x_ref,
+                                   const double *d_feet, double *d_H, double *d_f, double *d_A_aug,
+                                   double *d_B_aug, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPC_B200_H */

@@ -1,0 +1,94 @@
+"""ctypes binding of the C ABI (include/mpc_b200.h -> csrc/libmpc_b200.so).
+
+Plumbing only: torch (or any allocator) owns the buffers, this module passes raw pointers.
+There is no CPU fallback: if the shared library is missing or no CUDA device is usable the
+calls raise."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libmpc_b200.so")
+
+OK, EINVAL, ENODEV, ECUDA, ENOMEM, ECAPACITY = 0, -1, -2, -3, -4, -5
+INFTY = 1.0e20
+
+# every symbol include/mpc_b200.h declares (tests check that the library exports all of them)
+SYMBOLS = [
+    "mpc_b200_version", "mpc_b200_strerror", "mpc_b200_device_count", "mpc_b200_measure_fp64_peak",
+    "mpc_b200_tron1_default_params", "mpc_b200_create", "mpc_b200_destroy", "mpc_b200_last_error",
+    "mpc_b200_launch_count", "mpc_b200_contact_schedule_device", "mpc_b200_tron1_solve_device",
+    "mpc_b200_tron1_solve_host", "mpc_b200_tron1_condense_device",
+]
+
+
+class Tron1Params(C.Structure):
+    _fields_ = [
+        ("Ts", C.c_double), ("mass", C.c_double), ("inertia", C.c_double * 9), ("q", C.c_double * 13),
+        ("r", C.c_double), ("p_scale", C.c_double), ("mu", C.c_double), ("f_max", C.c_double),
+        ("ltv", C.c_int32), ("per_step_feet", C.c_int32),
+        ("gait_dt", C.c_float), ("gait_mpc_step", C.c_int32),
+        ("gait_swing_time", C.c_float), ("gait_stance_time", C.c_float),
+        ("max_newton", C.c_int32), ("max_admm", C.c_int32), ("tol", C.c_double),
+    ]
+
+
+class MpcB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"mpc_b200 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    """Load libmpc_b200.so (built by __graft_entry__.build()). Raises if absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FileNotFoundError(
+                f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(the engine has no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        vp, ip, dp = C.c_void_p, C.c_int, C.POINTER(C.c_double)
+        L.mpc_b200_version.restype = ip
+        L.mpc_b200_strerror.restype = C.c_char_p
+        L.mpc_b200_strerror.argtypes = [ip]
+        L.mpc_b200_device_count.restype = ip
+        L.mpc_b200_measure_fp64_peak.argtypes = [ip, dp]
+        L.mpc_b200_tron1_default_params.argtypes = [C.POINTER(Tron1Params)]
+        L.mpc_b200_create.argtypes = [C.POINTER(Tron1Params), ip, ip, ip, C.POINTER(vp)]
+        L.mpc_b200_destroy.argtypes = [vp]
+        L.mpc_b200_last_error.restype = C.c_char_p
+        L.mpc_b200_last_error.argtypes = [vp]
+        L.mpc_b200_launch_count.restype = C.c_int64
+        L.mpc_b200_launch_count.argtypes = [vp]
+        L.mpc_b200_contact_schedule_device.argtypes = [vp, ip, vp, vp, vp]
+        L.mpc_b200_tron1_solve_device.argtypes = [vp, ip, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.mpc_b200_tron1_solve_host.argtypes = [vp, ip, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.mpc_b200_tron1_condense_device.argtypes = [vp, ip, vp, vp, vp, vp, vp, vp, vp, vp]
+        _lib = L
+    return _lib
+
+
+def default_params(**overrides):
+    p = Tron1Params()
+    lib().mpc_b200_tron1_default_params(C.byref(p))
+    for k, v in overrides.items():
+        if k in ("inertia", "q"):
+            for i, x in enumerate(v):
+                getattr(p, k)[i] = float(x)
+        else:
+            setattr(p, k, v)
+    return p
+
+
+def check(code, engine=None):
+    if code != OK:
+        L = lib()
+        msg = L.mpc_b200_strerror(code).decode()
+        if engine:
+            extra = L.mpc_b200_last_error(engine).decode()
+            if extra:
+                msg += f" ({extra})"
+        raise MpcB200Error(code, msg)

@@ -1,0 +1,721 @@
+// tron1_core.cuh -- per-instance TRON1 convex-MPC algorithm (linearise -> discretise -> condense ->
+// QP solve), written once as group-cooperative code.
+//
+// A "group" is the set of threads that cooperates on ONE robot instance: a warp or a few warps
+// on the GPU (GrpCuda in mpc_b200.cu), a single serial thread in the test-only host build
+// (tests/emul/).  Every phase is a strided loop `for (w = g.tid(); w < n; w += g.size())`
+// followed by g.sync(), so the same source is valid for any group size.
+//
+// What it replaces in the reference (paths relative to /root/reference):
+//   include/mpcQP.h:121-182   buildSystemModel      -> model_step()        (intended SRBD physics)
+//   src/QPSolver.cpp:21-29    discretizeSystem      -> closed-form ZOH of the nilpotent SRBD model
+//   src/QPSolver.cpp:36-60    buildQPParams H, f    -> build_hessian(), adjoint()  (B_aug never formed)
+//   src/QPSolver.cpp:83-106   solveQP (qpOASES)     -> active-face Newton iterations on a packed
+//                                                      Cholesky + ADMM fallback, exact projection
+//   include/MPCController.h:61-75 calculateGait     -> gait_contact()
+//
+// Structure that is exploited: with x = [Theta, p, omega, v, g],
+//   A_c^3 = 0 and A_c^2 B_c = 0, so  A_d = I + Ts A_c + Ts^2/2 A_c^2,  B_d = Ts B_c + Ts^2/2 A_c B_c
+// exactly, and block (i,j) of B_aug (i > j) is
+//   Theta rows: Ts^2 S(i,j) W_j     S(i,j) = 1/2 Rz_j' + sum_{j<k<i} Rz_k'
+//   p rows    : Ts^2/m (i-j-1/2) I
+//   omega rows: Ts W_j              W_j = Iw_j^-1 [r_j]x  (per foot)
+//   v rows    : Ts/m I
+// so H = 2(B'QB + R) and f = 2B'Q(A x0 - x_ref) reduce to suffix sums over the horizon.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define MPC_HD __host__ __device__ __forceinline__
+#else
+#define MPC_HD inline
+#endif
+
+namespace mpcb200 {
+
+struct Tron1Const {
+    double Ts, inv_m;
+    double Iinv[9];   // inverse body inertia, row-major (symmetric)
+    double q[13];     // diag(Q)  (reference include/mpcQP.h:54)
+    double r;         // R = r I  (include/mpcQP.h:55)
+    double p_scale;   // P = p_scale Q (include/mpcQP.h:56)
+    double mu, f_max; // friction pyramid, normal-force cap
+    double tol;       // natural-residual tolerance (relative to max(1,|u|_inf))
+    double gamma;     // step of the natural map used for face prediction
+    double admm_alpha;
+    int ltv, per_step_feet;
+    int max_newton, max_admm;
+    float gait_dt, gait_swing, gait_stance;
+    int gait_mpc_step;
+};
+
+enum { ST_SOLVED = 0, ST_MAXITER = 1, ST_FAILED = 2 };
+
+// ------------------------------------------------------------------------------------------------
+// gait: bit-exact restatement of MPC::calculateGait (include/MPCController.h:61-75) with the float
+// members of MPCParam (include/MPCParam.h:44-49).  `iter * dt` is an int*float product rounded to
+// float, then widened; `swing + stance` is a float add.  No FMA contraction can occur (single ops).
+MPC_HD void gait_contact(const Tron1Const& P, int iter, int& left_stance, int& right_stance) {
+    if (iter < 0) { left_stance = 1; right_stance = 1; return; }   // standing
+#if defined(__CUDA_ARCH__)
+    float ct = __fmul_rn((float)iter, P.gait_dt);
+    float cy = __fadd_rn(P.gait_swing, P.gait_stance);
+#else
+    volatile float ctv = (float)iter * P.gait_dt;
+    volatile float cyv = P.gait_swing + P.gait_stance;
+    float ct = ctv, cy = cyv;
+#endif
+    double phase = fmod((double)ct, (double)cy);
+    int left_swing = phase < (double)P.gait_swing;
+    left_stance = !left_swing;
+    right_stance = left_swing;
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int N>
+struct Tron1Work {
+    static constexpr int NS = 2 * N;     // foot-steps
+    static constexpr int NV = 6 * N;     // decision variables
+    static constexpr int PKN = (NV + 1) * (NV + 2) / 2;  // packed lower triangle incl. rhs row
+    double A[PKN];          // packed reduced Hessian / Cholesky factor; row nc holds the rhs
+    double dinv[NV];        // 1 / L_kk
+    double W[N * 18];       // W[k][foot] 3x3 row-major:  Iw_k^-1 [r]x
+    double cs[N * 2];       // cos, sin of yaw_k
+    double cc[N + 1], ss[N + 1];   // prefix sums  sum_{k<i} cos / sin
+    double dc[N], ds[N];    // D_j = 1/2 Rz_j' - C_{j+1}  (cos-like / sin-like entries)
+    double SW[N * 8];       // suffix sums over i>j of w_i * {1, cc, ss, cc^2, ss^2, cc ss, i, i^2}
+    double e0[(N + 1) * 12];  // free-response tracking error  A_aug x0 - x_ref  (Theta,p,omega,v)
+    double ee[(N + 1) * 12];  // working tracking error
+    double adj[(N + 1) * 18]; // adjoint terms / suffix sums
+    double tau[(N + 1) * 6];  // per-step input effect (tau_k, phi_k) and scans
+    double f[NV], g[NV], u[NV], w[NV], z[NV], y[NV];
+    double res[NS];
+    double x0[13];
+    double feet[N * 6];
+    int8_t contact[NS], ax[NS], ay[NS], zt[NS], nax[NS], nay[NS], nzt[NS];
+    int16_t cidx[NS];
+    int nc;         // compact variable count (3 * stance foot-steps)
+    int flag;       // group-uniform scratch flag
+};
+
+#define MPC_PK(i, j) ((i) * ((i) + 1) / 2 + (j))
+
+// ---- phase: model of horizon step k  (include/mpcQP.h:121-182, intended physics) -----------------
+template <int N>
+MPC_HD void model_step(const Tron1Const& P, Tron1Work<N>& S, const double* xref, int k) {
+    const double* lin = (k == 0 || !P.ltv) ? S.x0 : (xref + 13 * k);
+    double s, c;
+    sincos(lin[2], &s, &c);
+    S.cs[2 * k] = c; S.cs[2 * k + 1] = s;
+    // Iw^-1 = Rz Ib^-1 Rz'
+    const double* I = P.Iinv;
+    double T[9];  // T = Rz * Iinv
+    for (int j = 0; j < 3; ++j) {
+        T[0 * 3 + j] = c * I[0 * 3 + j] - s * I[1 * 3 + j];
+        T[1 * 3 + j] = s * I[0 * 3 + j] + c * I[1 * 3 + j];
+        T[2 * 3 + j] = I[2 * 3 + j];
+    }
+    double Iw[9];  // Iw = T * Rz'
+    for (int i = 0; i < 3; ++i) {
+        Iw[i * 3 + 0] = T[i * 3 + 0] * c - T[i * 3 + 1] * s;
+        Iw[i * 3 + 1] = T[i * 3 + 0] * s + T[i * 3 + 1] * c;
+        Iw[i * 3 + 2] = T[i * 3 + 2];
+    }
+    const double* ft = S.feet + ((P.per_step_feet && P.ltv) ? 6 * k : 0);
+    for (int a = 0; a < 2; ++a) {
+        double rx = ft[3 * a] - lin[3], ry = ft[3 * a + 1] - lin[4], rz = ft[3 * a + 2] - lin[5];
+        double* Wk = S.W + 18 * k + 9 * a;
+        // [r]x = [[0,-rz,ry],[rz,0,-rx],[-ry,rx,0]]
+        for (int i = 0; i < 3; ++i) {
+            double i0 = Iw[i * 3], i1 = Iw[i * 3 + 1], i2 = Iw[i * 3 + 2];
+            Wk[i * 3 + 0] = i1 * rz - i2 * ry;
+            Wk[i * 3 + 1] = -i0 * rz + i2 * rx;
+            Wk[i * 3 + 2] = i0 * ry - i1 * rx;
+        }
+    }
+}
+
+// weights of prediction step i (1..N): Q for i<N, P = p_scale Q for i==N (src/QPSolver.cpp:50-56)
+template <int N>
+MPC_HD double step_weight(const Tron1Const& P, int i) { return i == N ? P.p_scale : 1.0; }
+
+// ---- phase: prefix / suffix sums that depend on the yaw sequence only ---------------------------
+template <int N, class G>
+MPC_HD void horizon_sums(const Tron1Const& P, Tron1Work<N>& S, const G& g) {
+    // prefix cc_i, ss_i (two serial scans, one per thread)
+    for (int c = g.tid(); c < 2; c += g.size()) {
+        double* out = c ? S.ss : S.cc;
+        double acc = 0.0;
+        out[0] = 0.0;
+        for (int k = 0; k < N; ++k) { acc += S.cs[2 * k + c]; out[k + 1] = acc; }
+    }
+    g.sync();
+    for (int j = g.tid(); j < N; j += g.size()) {
+        S.dc[j] = 0.5 * S.cs[2 * j] - S.cc[j + 1];
+        S.ds[j] = 0.5 * S.cs[2 * j + 1] - S.ss[j + 1];
+    }
+    // suffix sums over i = j+1..N of w_i * {1, cc_i, ss_i, cc_i^2, ss_i^2, cc_i ss_i, i, i^2}
+    for (int c = g.tid(); c < 8; c += g.size()) {
+        double acc = 0.0;
+        for (int i = N; i >= 1; --i) {
+            double w = step_weight<N>(P, i), cc = S.cc[i], ss = S.ss[i], di = (double)i;
+            double t = c == 0 ? 1.0 : c == 1 ? cc : c == 2 ? ss : c == 3 ? cc * cc : c == 4 ? ss * ss
+                     : c == 5 ? cc * ss : c == 6 ? di : di * di;
+            acc += w * t;
+            S.SW[8 * (i - 1) + c] = acc;
+        }
+    }
+    g.sync();
+}
+
+// ---- phase: free-response error  e0_i = (A_aug x0 - x_ref)_i  for i = 0..N ----------------------
+template <int N, class G>
+MPC_HD void free_response(const Tron1Const& P, Tron1Work<N>& S, const double* xref, const G& g) {
+    const double Ts = P.Ts;
+    for (int i = g.tid(); i <= N; i += g.size()) {
+        const double* x0 = S.x0;
+        const double* xr = xref + 13 * i;
+        double* e = S.e0 + 12 * i;
+        double cc = S.cc[i], ss = S.ss[i], di = (double)i;
+        double gz = x0[12];
+        e[0] = x0[0] + Ts * (cc * x0[6] + ss * x0[7]) - xr[0];
+        e[1] = x0[1] + Ts * (-ss * x0[6] + cc * x0[7]) - xr[1];
+        e[2] = x0[2] + Ts * (di * x0[8]) - xr[2];
+        e[3] = x0[3] + di * Ts * x0[9] - xr[3];
+        e[4] = x0[4] + di * Ts * x0[10] - xr[4];
+        e[5] = x0[5] + di * Ts * x0[11] + 0.5 * di * di * Ts * Ts * gz - xr[5];
+        e[6] = x0[6] - xr[6];
+        e[7] = x0[7] - xr[7];
+        e[8] = x0[8] - xr[8];
+        e[9] = x0[9] - xr[9];
+        e[10] = x0[10] - xr[10];
+        e[11] = x0[11] + di * Ts * gz - xr[11];
+    }
+    g.sync();
+}
+
+// ---- phase: input response  ee_i = (B_aug u)_i  for i = 0..N (u in full layout) -----------------
+template <int N, class G>
+MPC_HD void input_response(const Tron1Const& P, Tron1Work<N>& S, const double* u, const G& g) {
+    const double Ts = P.Ts;
+    // per step: tau_k = sum_a W_ka u_ka ; phi_k = sum_a u_ka / m
+    for (int k = g.tid(); k < N; k += g.size()) {
+        const double* W0 = S.W + 18 * k;
+        const double* uk = u + 6 * k;
+        double* t = S.tau + 6 * k;
+        for (int i = 0; i < 3; ++i) {
+            t[i] = W0[i * 3] * uk[0] + W0[i * 3 + 1] * uk[1] + W0[i * 3 + 2] * uk[2]
+                 + W0[9 + i * 3] * uk[3] + W0[9 + i * 3 + 1] * uk[4] + W0[9 + i * 3 + 2] * uk[5];
+            t[3 + i] = (uk[i] + uk[3 + i]) * P.inv_m;
+        }
+    }
+    g.sync();
+    // serial recursion per component group: thread 0 -> (omega, Theta), thread 1 -> (v, p)
+    for (int c = g.tid(); c < 2; c += g.size()) {
+        if (c == 0) {
+            double w0 = 0, w1 = 0, w2 = 0, t0 = 0, t1 = 0, t2 = 0;
+            for (int k = 0; k <= N; ++k) {
+                double* e = S.ee + 12 * k;
+                e[0] = t0; e[1] = t1; e[2] = t2; e[6] = w0; e[7] = w1; e[8] = w2;
+                if (k == N) break;
+                const double* t = S.tau + 6 * k;
+                double cz = S.cs[2 * k], sz = S.cs[2 * k + 1];
+                // Theta+ = Theta + Ts Rz'(omega + Ts/2 tau)
+                double a0 = w0 + 0.5 * Ts * t[0], a1 = w1 + 0.5 * Ts * t[1], a2 = w2 + 0.5 * Ts * t[2];
+                t0 += Ts * (cz * a0 + sz * a1);
+                t1 += Ts * (-sz * a0 + cz * a1);
+                t2 += Ts * a2;
+                w0 += Ts * t[0]; w1 += Ts * t[1]; w2 += Ts * t[2];
+            }
+        } else {
+            double v0 = 0, v1 = 0, v2 = 0, p0 = 0, p1 = 0, p2 = 0;
+            for (int k = 0; k <= N; ++k) {
+                double* e = S.ee + 12 * k;
+                e[3] = p0; e[4] = p1; e[5] = p2; e[9] = v0; e[10] = v1; e[11] = v2;
+                if (k == N) break;
+                const double* t = S.tau + 6 * k + 3;
+                p0 += Ts * (v0 + 0.5 * Ts * t[0]);
+                p1 += Ts * (v1 + 0.5 * Ts * t[1]);
+                p2 += Ts * (v2 + 0.5 * Ts * t[2]);
+                v0 += Ts * t[0]; v1 += Ts * t[1]; v2 += Ts * t[2];
+            }
+        }
+    }
+    g.sync();
+}
+
+// ---- phase: adjoint  out = 2 B_aug' Qbar e   (e: (N+1) x 12, out: full layout 6N) ----------------
+template <int N, class G>
+MPC_HD void adjoint(const Tron1Const& P, Tron1Work<N>& S, const double* e, double* out, const G& g) {
+    const double Ts = P.Ts;
+    const double* q = P.q;
+    // weighted terms of step i (row i-1 of adj holds step i, i = 1..N)
+    for (int i = 1 + g.tid(); i <= N; i += g.size()) {
+        const double* ei = e + 12 * i;
+        double w = step_weight<N>(P, i), cc = S.cc[i], ss = S.ss[i], di = (double)i;
+        double* a = S.adj + 18 * (i - 1);
+        double t0 = w * q[0] * ei[0], t1 = w * q[1] * ei[1], t2 = w * q[2] * ei[2];
+        a[0] = cc * t0 - ss * t1;   // C_i' Q e_Theta, x
+        a[1] = ss * t0 + cc * t1;   //               y
+        a[2] = di * t2;             //               z
+        a[3] = t0; a[4] = t1; a[5] = t2;
+        for (int c = 0; c < 3; ++c) {
+            a[6 + c] = w * q[6 + c] * ei[6 + c];            // omega
+            double tp = w * q[3 + c] * ei[3 + c];
+            a[9 + c] = di * tp;                             // i * Qp e_p
+            a[12 + c] = tp;                                 // Qp e_p
+            a[15 + c] = w * q[9 + c] * ei[9 + c];           // Qv e_v
+        }
+    }
+    g.sync();
+    // suffix sums over i > j, stored at row j  (row j currently holds step j+1)
+    for (int c = g.tid(); c < 18; c += g.size()) {
+        double acc = 0.0;
+        for (int j = N - 1; j >= 0; --j) { acc += S.adj[18 * j + c]; S.adj[18 * j + c] = acc; }
+    }
+    g.sync();
+    for (int s = g.tid(); s < 2 * N; s += g.size()) {
+        int j = s >> 1;
+        const double* a = S.adj + 18 * j;
+        const double* Wj = S.W + 9 * s;
+        double dc = S.dc[j], ds = S.ds[j], jh = (double)j + 0.5;
+        // sum_i S(i,j)' Q e_Theta
+        double vt0 = a[0] + dc * a[3] - ds * a[4];
+        double vt1 = a[1] + ds * a[3] + dc * a[4];
+        double vt2 = a[2] - jh * a[5];
+        double m0 = Ts * (Ts * vt0 + a[6]), m1 = Ts * (Ts * vt1 + a[7]), m2 = Ts * (Ts * vt2 + a[8]);
+        for (int c = 0; c < 3; ++c) {
+            double rot = Wj[0 * 3 + c] * m0 + Wj[1 * 3 + c] * m1 + Wj[2 * 3 + c] * m2;   // W' m
+            double lin = Ts * P.inv_m * (Ts * (a[9 + c] - jh * a[12 + c]) + a[15 + c]);
+            out[3 * s + c] = 2.0 * (rot + lin);
+        }
+    }
+    g.sync();
+}
+
+// ---- reduction basis of one foot-step face --------------------------------------------------------
+struct FaceZ { double fx, fy, fz, mx, my; };
+MPC_HD FaceZ face_basis(double mu, int ax, int ay, int zt) {
+    FaceZ z;
+    z.fz = (zt == 0) ? 1.0 : 0.0;
+    z.fx = (ax == 0 && zt != 2) ? 1.0 : 0.0;
+    z.fy = (ay == 0 && zt != 2) ? 1.0 : 0.0;
+    z.mx = (double)ax * mu;
+    z.my = (double)ay * mu;
+    return z;
+}
+
+// ---- phase: packed reduced Hessian  A = Z'(H + rho I)Z  over the stance variables ----------------
+// H = 2(B'QB + R) (src/QPSolver.cpp:58) restricted to stance foot-steps; eliminated variables get
+// a unit diagonal.  Work item = one pair of horizon steps (j >= l).
+template <int N, class G>
+MPC_HD void build_hessian(const Tron1Const& P, Tron1Work<N>& S, double rho, bool use_face, const G& g) {
+    const double Ts2 = P.Ts * P.Ts, Ts4 = Ts2 * Ts2, im2 = P.inv_m * P.inv_m;
+    const double* q = P.q;
+    for (int pr = g.tid(); pr < N * (N + 1) / 2; pr += g.size()) {
+        // unrank pr -> (j, l), j >= l
+        int j = (int)((sqrt(8.0 * pr + 1.0) - 1.0) * 0.5);
+        while (j * (j + 1) / 2 > pr) --j;
+        while ((j + 1) * (j + 2) / 2 <= pr) ++j;
+        int l = pr - j * (j + 1) / 2;
+        bool cj0 = S.contact[2 * j], cj1 = S.contact[2 * j + 1], cl0 = S.contact[2 * l], cl1 = S.contact[2 * l + 1];
+        if (!((cj0 || cj1) && (cl0 || cl1))) continue;
+        const double* sw = S.SW + 8 * j;   // suffix sums over i > j  (j >= l so i > l too)
+        double dcj = S.dc[j], dsj = S.ds[j], dcl = S.dc[l], dsl = S.ds[l];
+        double Saa = sw[3] + (dcj + dcl) * sw[1] + dcj * dcl * sw[0];
+        double Sbb = sw[4] + (dsj + dsl) * sw[2] + dsj * dsl * sw[0];
+        double Sab = sw[5] + dcj * sw[2] + dsl * sw[1] + dcj * dsl * sw[0];
+        double Sba = sw[5] + dsj * sw[1] + dcl * sw[2] + dsj * dcl * sw[0];
+        double jh = (double)j + 0.5, lh = (double)l + 0.5;
+        double Szz = sw[7] - (jh + lh) * sw[6] + jh * lh * sw[0];   // sum w (i-j-1/2)(i-l-1/2)
+        // M = Ts^4 sum S(i,j)' Q_Theta S(i,l) + Ts^2 sum Q_omega      (2x2 block + zz)
+        double M00 = Ts4 * (q[0] * Saa + q[1] * Sbb) + Ts2 * q[6] * sw[0];
+        double M01 = Ts4 * (q[0] * Sab - q[1] * Sba);
+        double M10 = Ts4 * (q[0] * Sba - q[1] * Sab);
+        double M11 = Ts4 * (q[0] * Sbb + q[1] * Saa) + Ts2 * q[7] * sw[0];
+        double M22 = Ts4 * q[2] * Szz + Ts2 * q[8] * sw[0];
+        double Dp[3];
+        for (int c = 0; c < 3; ++c) Dp[c] = im2 * (Ts4 * q[3 + c] * Szz + Ts2 * q[9 + c] * sw[0]);
+        for (int a = 0; a < 2; ++a) {
+            if (!S.contact[2 * j + a]) continue;
+            const int sa = 2 * j + a;
+            const double* Wa = S.W + 9 * sa;
+            // MW' = M' * Wa  ->  we need Wa' M Wb = (M' Wa)' Wb ; compute L = Wa' M (3x3)
+            double L[9];
+            for (int r = 0; r < 3; ++r) {   // row r of Wa' = column r of Wa
+                double w0 = Wa[0 * 3 + r], w1 = Wa[1 * 3 + r], w2 = Wa[2 * 3 + r];
+                L[r * 3 + 0] = w0 * M00 + w1 * M10;
+                L[r * 3 + 1] = w0 * M01 + w1 * M11;
+                L[r * 3 + 2] = w2 * M22;
+            }
+            FaceZ Za = use_face ? face_basis(P.mu, S.ax[sa], S.ay[sa], S.zt[sa]) : face_basis(P.mu, 0, 0, 0);
+            for (int b = 0; b < 2; ++b) {
+                if (!S.contact[2 * l + b]) continue;
+                if (j == l && b > a) continue;
+                const int sb = 2 * l + b;
+                const double* Wb = S.W + 9 * sb;
+                double T[9];
+                for (int r = 0; r < 3; ++r)
+                    for (int c = 0; c < 3; ++c)
+                        T[r * 3 + c] = L[r * 3 + 0] * Wb[0 * 3 + c] + L[r * 3 + 1] * Wb[1 * 3 + c] + L[r * 3 + 2] * Wb[2 * 3 + c];
+                for (int c = 0; c < 3; ++c) T[c * 3 + c] += Dp[c];
+                if (sa == sb) for (int c = 0; c < 3; ++c) T[c * 3 + c] += P.r + 0.5 * rho;
+                for (int i = 0; i < 9; ++i) T[i] *= 2.0;
+                if (use_face) {
+                    FaceZ Zb = face_basis(P.mu, S.ax[sb], S.ay[sb], S.zt[sb]);
+                    for (int r = 0; r < 3; ++r) {   // columns:  T <- T Zb
+                        double t0 = T[r * 3], t1 = T[r * 3 + 1], t2 = T[r * 3 + 2];
+                        T[r * 3 + 2] = Zb.fz * (Zb.mx * t0 + Zb.my * t1 + t2);
+                        T[r * 3 + 0] = Zb.fx * t0;
+                        T[r * 3 + 1] = Zb.fy * t1;
+                    }
+                    for (int c = 0; c < 3; ++c) {   // rows:  T <- Za' T
+                        double t0 = T[c], t1 = T[3 + c], t2 = T[6 + c];
+                        T[6 + c] = Za.fz * (Za.mx * t0 + Za.my * t1 + t2);
+                        T[c] = Za.fx * t0;
+                        T[3 + c] = Za.fy * t1;
+                    }
+                    if (sa == sb) {
+                        if (Za.fx == 0.0) T[0] = 1.0;
+                        if (Za.fy == 0.0) T[4] = 1.0;
+                        if (Za.fz == 0.0) T[8] = 1.0;
+                    }
+                }
+                const int ra = 3 * S.cidx[sa], cb = 3 * S.cidx[sb];
+                for (int r = 0; r < 3; ++r)
+                    for (int c = 0; c < 3; ++c) {
+                        if (sa == sb && c > r) continue;
+                        S.A[MPC_PK(ra + r, cb + c)] = T[r * 3 + c];
+                    }
+            }
+        }
+    }
+    g.sync();
+}
+
+// ---- phase: left-looking packed Cholesky of the leading nc x nc block; row nc (the rhs) is carried
+// along so that on exit A[PK(nc, k)] = (L^-1 rhs)_k.  Returns false if not positive definite.
+template <int N, class G>
+MPC_HD bool cholesky_with_rhs(Tron1Work<N>& S, const G& g) {
+    const int n = S.nc;
+    double* A = S.A;
+    if (g.tid() == 0) S.flag = 0;
+    g.sync();
+    for (int k = 0; k < n; ++k) {
+        const double* rk = A + MPC_PK(k, 0);
+        // every thread forms the pivot redundantly (row k is broadcast-read)
+        for (int i = k + 1 + g.tid(); i <= n; i += g.size()) {
+            double* ri = A + MPC_PK(i, 0);
+            double s0 = ri[k], s1 = 0.0, d0 = rk[k], d1 = 0.0;
+            int jj = 0;
+            for (; jj + 1 < k; jj += 2) {
+                double a0 = rk[jj], a1 = rk[jj + 1];
+                s0 -= ri[jj] * a0; s1 -= ri[jj + 1] * a1;
+                d0 -= a0 * a0; d1 -= a1 * a1;
+            }
+            if (jj < k) { double a0 = rk[jj]; s0 -= ri[jj] * a0; d0 -= a0 * a0; }
+            double d = d0 + d1;
+            if (!(d > 0.0)) { S.flag = 1; d = 1.0; }
+            double di = 1.0 / sqrt(d);
+            ri[k] = (s0 + s1) * di;
+            if (i == k + 1) S.dinv[k] = di;   // row k+1 <= nc always exists (the rhs row)
+        }
+        g.sync();
+    }
+    return S.flag == 0;
+}
+
+// backward solve L' x = y with y = A[row nc], result in S.w[0..nc)
+template <int N, class G>
+MPC_HD void backward_solve(Tron1Work<N>& S, const G& g) {
+    const int n = S.nc;
+    double* A = S.A;
+    for (int i = g.tid(); i < n; i += g.size()) S.w[i] = A[MPC_PK(n, i)];
+    g.sync();
+    for (int k = n - 1; k >= 0; --k) {
+        double xk = S.w[k] * S.dinv[k];
+        const double* rk = A + MPC_PK(k, 0);
+        g.sync();   // everyone has read w[k] before its owner rewrites it
+        for (int i = g.tid(); i < k; i += g.size()) S.w[i] -= rk[i] * xk;
+        if (g.tid() == 0) S.w[k] = xk;
+        g.sync();
+    }
+}
+
+// forward solve L y = b with b in S.w (used by ADMM where the factor is reused)
+template <int N, class G>
+MPC_HD void forward_solve(Tron1Work<N>& S, const G& g) {
+    const int n = S.nc;
+    double* A = S.A;
+    for (int k = 0; k < n; ++k) {
+        double yk = S.w[k] * S.dinv[k];
+        g.sync();
+        for (int i = k + 1 + g.tid(); i < n; i += g.size()) S.w[i] -= A[MPC_PK(i, k)] * yk;
+        if (g.tid() == 0) S.w[k] = yk;
+        g.sync();
+    }
+}
+
+// exact Euclidean projection onto {|x|<=mu z, |y|<=mu z, 0<=z<=fmax}; returns face codes
+MPC_HD void project_pyramid(double mu, double fmax, const double v[3], double out[3], int& ax, int& ay, int& zt) {
+    double x = v[0], y = v[1], w = v[2];
+    double fxa = fabs(x), fya = fabs(y);
+    double a = fxa > fya ? fxa : fya, b = fxa > fya ? fya : fxa, t;
+    if (mu * w >= a) t = w;
+    else {
+        t = (w + mu * a) / (1.0 + mu * mu);
+        if (mu * t < b) t = (w + mu * (a + b)) / (1.0 + 2.0 * mu * mu);
+    }
+    zt = 0;
+    if (t >= fmax) { t = fmax; zt = 1; }
+    else if (t <= 0.0) { t = 0.0; zt = 2; }
+    double lim = mu * t;
+    ax = x > lim ? 1 : (x < -lim ? -1 : 0);
+    ay = y > lim ? 1 : (y < -lim ? -1 : 0);
+    if (zt == 2) { ax = 0; ay = 0; }
+    out[0] = x > lim ? lim : (x < -lim ? -lim : x);
+    out[1] = y > lim ? lim : (y < -lim ? -lim : y);
+    out[2] = t;
+}
+
+// ---- gradient g = H u + f  at u (full layout) -----------------------------------------------------
+template <int N, class G>
+MPC_HD void gradient(const Tron1Const& P, Tron1Work<N>& S, const G& g) {
+    input_response<N>(P, S, S.u, g);
+    adjoint<N>(P, S, S.ee, S.g, g);
+    for (int i = g.tid(); i < 6 * N; i += g.size()) S.g[i] += S.f[i] + 2.0 * P.r * S.u[i];
+    g.sync();
+}
+
+// ---- one active-face solve: u = argmin q on the affine hull of the current face -------------------
+// returns false when the reduced Hessian is not positive definite (never for valid inputs)
+template <int N, class G>
+MPC_HD bool face_solve(const Tron1Const& P, Tron1Work<N>& S, const G& g) {
+    // fixed part: z = fmax on zt==1 foot-steps
+    bool any_fixed = false;
+    for (int s = 0; s < 2 * N; ++s) any_fixed |= (S.contact[s] && S.zt[s] == 1);
+    for (int s = g.tid(); s < 2 * N; s += g.size()) {
+        double fz = (S.contact[s] && S.zt[s] == 1) ? P.f_max : 0.0;
+        S.u[3 * s] = (double)S.ax[s] * P.mu * fz;
+        S.u[3 * s + 1] = (double)S.ay[s] * P.mu * fz;
+        S.u[3 * s + 2] = fz;
+    }
+    g.sync();
+    if (any_fixed) gradient<N>(P, S, g);   // g0 = f + H u_fix
+    build_hessian<N>(P, S, 0.0, true, g);
+    const int n = S.nc;
+    for (int s = g.tid(); s < 2 * N; s += g.size()) {
+        if (!S.contact[s]) continue;
+        FaceZ Z = face_basis(P.mu, S.ax[s], S.ay[s], S.zt[s]);
+        const double* g0 = any_fixed ? S.g + 3 * s : S.f + 3 * s;
+        double* rhs = S.A + MPC_PK(n, 3 * S.cidx[s]);
+        rhs[0] = -Z.fx * g0[0];
+        rhs[1] = -Z.fy * g0[1];
+        rhs[2] = -Z.fz * (Z.mx * g0[0] + Z.my * g0[1] + g0[2]);
+    }
+    if (g.tid() == 0) S.A[MPC_PK(n, n)] = 1.0;
+    g.sync();
+    bool ok = cholesky_with_rhs<N>(S, g);
+    backward_solve<N>(S, g);
+    for (int s = g.tid(); s < 2 * N; s += g.size()) {
+        if (!S.contact[s]) continue;
+        const double* w = S.w + 3 * S.cidx[s];
+        int zt = S.zt[s];
+        double fz = zt == 0 ? w[2] : (zt == 1 ? P.f_max : 0.0);
+        S.u[3 * s + 2] = fz;
+        S.u[3 * s] = S.ax[s] != 0 ? (double)S.ax[s] * P.mu * fz : (zt == 2 ? 0.0 : w[0]);
+        S.u[3 * s + 1] = S.ay[s] != 0 ? (double)S.ay[s] * P.mu * fz : (zt == 2 ? 0.0 : w[1]);
+    }
+    g.sync();
+    return ok;
+}
+
+// ---- optimality check of S.u: natural residual |u - P_C(u - gamma g)|_inf, predicts the next face --
+// returns true if converged; `changed` tells whether the predicted face differs from the current one
+template <int N, class G>
+MPC_HD bool check_optimality(const Tron1Const& P, Tron1Work<N>& S, const G& g, bool& changed, double& resid) {
+    gradient<N>(P, S, g);
+    for (int s = g.tid(); s < 2 * N; s += g.size()) {
+        double r = 0.0, um = 0.0;
+        if (S.contact[s]) {
+            double v[3], o[3];
+            int ax, ay, zt;
+            for (int c = 0; c < 3; ++c) v[c] = S.u[3 * s + c] - P.gamma * S.g[3 * s + c];
+            project_pyramid(P.mu, P.f_max, v, o, ax, ay, zt);
+            for (int c = 0; c < 3; ++c) {
+                double d = fabs(S.u[3 * s + c] - o[c]);
+                r = d > r ? d : r;
+                double a = fabs(S.u[3 * s + c]);
+                um = a > um ? a : um;
+            }
+            S.nax[s] = (int8_t)ax; S.nay[s] = (int8_t)ay; S.nzt[s] = (int8_t)zt;
+        }
+        S.res[s] = r;
+        S.tau[s] = um;   // scratch: per foot-step |u|_inf
+    }
+    g.sync();
+    double r = 0.0, um = 1.0;
+    bool ch = false;
+    for (int s = 0; s < 2 * N; ++s) {
+        r = S.res[s] > r ? S.res[s] : r;
+        um = S.tau[s] > um ? S.tau[s] : um;
+        if (S.contact[s]) ch |= (S.nax[s] != S.ax[s]) || (S.nay[s] != S.ay[s]) || (S.nzt[s] != S.zt[s]);
+    }
+    g.sync();
+    changed = ch;
+    resid = r;
+    return r <= P.tol * um;
+}
+
+template <int N, class G>
+MPC_HD void adopt_predicted_face(Tron1Work<N>& S, const G& g) {
+    for (int s = g.tid(); s < 2 * N; s += g.size()) { S.ax[s] = S.nax[s]; S.ay[s] = S.nay[s]; S.zt[s] = S.nzt[s]; }
+    g.sync();
+}
+
+// ---- setup shared by solve and dump: inputs must already be in S.x0 / S.feet / S.contact ---------
+template <int N, class G>
+MPC_HD void setup_instance(const Tron1Const& P, Tron1Work<N>& S, const double* xref, const G& g) {
+    if (g.tid() == 0) {
+        int c = 0;
+        for (int s = 0; s < 2 * N; ++s) { S.cidx[s] = (int16_t)c; c += S.contact[s] ? 1 : 0; }
+        S.nc = 3 * c;
+    }
+    for (int s = g.tid(); s < 2 * N; s += g.size()) { S.ax[s] = 0; S.ay[s] = 0; S.zt[s] = 0; }
+    for (int k = g.tid(); k < N; k += g.size()) model_step<N>(P, S, xref, k);
+    g.sync();
+    horizon_sums<N>(P, S, g);
+    free_response<N>(P, S, xref, g);
+    adjoint<N>(P, S, S.e0, S.f, g);   // f = 2 B' Q (A x0 - x_ref)   (src/QPSolver.cpp:59-60)
+}
+
+// ---- full QP solve of one instance.  On exit S.u holds the forces (full layout). -----------------
+// iters = face solves + ADMM iterations.
+template <int N, class G>
+MPC_HD int solve_instance(const Tron1Const& P, Tron1Work<N>& S, const double* xref, const G& g, int& iters) {
+    setup_instance<N>(P, S, xref, g);
+    iters = 0;
+    if (S.nc == 0) {
+        for (int i = g.tid(); i < 6 * N; i += g.size()) S.u[i] = 0.0;
+        g.sync();
+        return ST_SOLVED;
+    }
+    bool changed;
+    double resid;
+    // phase A: active-face (semismooth Newton) iterations, cold start from the interior face
+    for (int it = 0; it < P.max_newton; ++it) {
+        ++iters;
+        if (!face_solve<N>(P, S, g)) return ST_FAILED;
+        if (check_optimality<N>(P, S, g, changed, resid)) return ST_SOLVED;
+        if (!changed) break;   // same face predicted but not optimal: numerical stall -> ADMM
+        adopt_predicted_face<N>(S, g);
+    }
+    // phase B: ADMM on  min q(u) + I_C(z), u = z  with periodic active-face polish
+    const int n = S.nc;
+    double hmax = 0.0;
+    build_hessian<N>(P, S, 0.0, false, g);
+    for (int i = 0; i < n; ++i) hmax = S.A[MPC_PK(i, i)] > hmax ? S.A[MPC_PK(i, i)] : hmax;
+    g.sync();
+    const double rho = sqrt(2.0 * P.r * hmax * 4.0);
+    // start from the projection of the last face solution
+    for (int s = g.tid(); s < 2 * N; s += g.size()) {
+        if (!S.contact[s]) continue;
+        double o[3];
+        int ax, ay, zt;
+        project_pyramid(P.mu, P.f_max, S.u + 3 * s, o, ax, ay, zt);
+        for (int c = 0; c < 3; ++c) { S.z[3 * S.cidx[s] + c] = o[c]; S.y[3 * S.cidx[s] + c] = 0.0; }
+    }
+    g.sync();
+    bool have_factor = false;
+    int stable = 0, since_polish = 0;
+    for (int it = 0; it < P.max_admm; ++it) {
+        ++iters;
+        if (!have_factor) {
+            build_hessian<N>(P, S, rho, false, g);
+            for (int i = g.tid(); i <= n; i += g.size()) S.A[MPC_PK(n, i)] = (i == n) ? 1.0 : 0.0;
+            g.sync();
+            if (!cholesky_with_rhs<N>(S, g)) return ST_FAILED;
+            have_factor = true;
+        }
+        for (int s = g.tid(); s < 2 * N; s += g.size()) {
+            if (!S.contact[s]) continue;
+            int b = 3 * S.cidx[s];
+            for (int c = 0; c < 3; ++c) S.w[b + c] = rho * (S.z[b + c] - S.y[b + c]) - S.f[3 * s + c];
+        }
+        g.sync();
+        forward_solve<N>(S, g);
+        for (int i = g.tid(); i < n; i += g.size()) S.A[MPC_PK(n, i)] = S.w[i];
+        g.sync();
+        backward_solve<N>(S, g);
+        if (g.tid() == 0) S.flag = 0;
+        g.sync();
+        for (int s = g.tid(); s < 2 * N; s += g.size()) {
+            if (!S.contact[s]) continue;
+            int b = 3 * S.cidx[s];
+            double v[3], o[3], uh[3];
+            int ax, ay, zt;
+            for (int c = 0; c < 3; ++c) {
+                uh[c] = P.admm_alpha * S.w[b + c] + (1.0 - P.admm_alpha) * S.z[b + c];
+                v[c] = uh[c] + S.y[b + c];
+            }
+            project_pyramid(P.mu, P.f_max, v, o, ax, ay, zt);
+            for (int c = 0; c < 3; ++c) { S.y[b + c] += uh[c] - o[c]; S.z[b + c] = o[c]; }
+            if (ax != S.ax[s] || ay != S.ay[s] || zt != S.zt[s]) S.flag = 1;
+            S.ax[s] = (int8_t)ax; S.ay[s] = (int8_t)ay; S.zt[s] = (int8_t)zt;
+        }
+        g.sync();
+        stable = S.flag ? 0 : stable + 1;
+        ++since_polish;
+        g.sync();
+        if ((stable >= 3 && since_polish >= 8) || since_polish >= 40) {
+            since_polish = 0;
+            have_factor = false;
+            if (!face_solve<N>(P, S, g)) return ST_FAILED;
+            if (check_optimality<N>(P, S, g, changed, resid)) return ST_SOLVED;
+        }
+    }
+    // not certified: return the last ADMM iterate (feasible by construction)
+    for (int s = g.tid(); s < 2 * N; s += g.size())
+        for (int c = 0; c < 3; ++c) S.u[3 * s + c] = S.contact[s] ? S.z[3 * S.cidx[s] + c] : 0.0;
+    g.sync();
+    return ST_MAXITER;
+}
+
+// ---- parity dump helpers (closed-form prediction matrices, column-major like Eigen) --------------
+// A_aug: 13(N+1) x 13, block i = A_{i-1}...A_0   (src/QPSolver.cpp:36-40)
+template <int N>
+MPC_HD double a_aug_entry(const Tron1Const& P, const Tron1Work<N>& S, int i, int r, int c) {
+    double v = (r == c) ? 1.0 : 0.0;
+    double di = (double)i, Ts = P.Ts;
+    if (r < 3 && c >= 6 && c < 9) {   // Theta <- omega : Ts C_i
+        int rr = r, cc = c - 6;
+        double C[9] = {S.cc[i], S.ss[i], 0, -S.ss[i], S.cc[i], 0, 0, 0, di};
+        v += Ts * C[rr * 3 + cc];
+    }
+    if (r >= 3 && r < 6 && c == r + 6) v += di * Ts;              // p <- v
+    if (r == 11 && c == 12) v += di * Ts;                         // v_z <- g
+    if (r == 5 && c == 12) v += 0.5 * di * di * Ts * Ts;          // p_z <- g
+    return v;
+}
+// B_aug block (i,j), i > j: 13 x 6 (src/QPSolver.cpp:42-47 generalised to the per-step model)
+template <int N>
+MPC_HD double b_aug_entry(const Tron1Const& P, const Tron1Work<N>& S, int i, int j, int r, int c) {
+    if (i <= j) return 0.0;
+    const double Ts = P.Ts;
+    const int a = c / 3, cc = c % 3;
+    const double* W = S.W + 18 * j + 9 * a;
+    if (r < 3) {
+        double sa = S.cc[i] + S.dc[j], sb = S.ss[i] + S.ds[j], sz = (double)(i - j) - 0.5;
+        double Sm[9] = {sa, sb, 0, -sb, sa, 0, 0, 0, sz};
+        double v = 0.0;
+        for (int k = 0; k < 3; ++k) v += Sm[r * 3 + k] * W[k * 3 + cc];
+        return Ts * Ts * v;
+    }
+    if (r < 6) return (r - 3 == cc) ? Ts * Ts * P.inv_m * ((double)(i - j) - 0.5) : 0.0;
+    if (r < 9) return Ts * W[(r - 6) * 3 + cc];
+    if (r < 12) return (r - 9 == cc) ? Ts * P.inv_m : 0.0;
+    return 0.0;
+}
+
+}  // namespace mpcb200

@@ -1,0 +1,101 @@
+// emul_tron1.cpp -- TEST INFRASTRUCTURE ONLY.
+// Compiles the product's group-cooperative device source (mpc_limx_control_b200/csrc/tron1_core.cuh)
+// for the host with a one-thread "group", so the kernel mathematics can be checked against the
+// oracle in the CPU test tier (no GPU in the build container).  It is NOT a CPU fallback: nothing
+// under mpc_limx_control_b200/ or include/ links or loads this file, and the product library fails
+// loudly without CUDA.
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "../../mpc_limx_control_b200/csrc/tron1_core.cuh"
+#include "../../mpc_limx_control_b200/csrc/tron1_params.h"
+
+using namespace mpcb200;
+
+struct GrpSerial {
+    int tid() const { return 0; }
+    int size() const { return 1; }
+    void sync() const {}
+};
+
+template <int N>
+static int run_solve(const Tron1Const& P, const double* x0, const double* xref, const double* feet,
+                     const uint8_t* contact, double* forces, int* iters) {
+    auto* S = new Tron1Work<N>();
+    std::memcpy(S->x0, x0, sizeof(double) * 13);
+    std::memcpy(S->feet, feet, sizeof(double) * ((P.per_step_feet && P.ltv) ? 6 * N : 6));
+    for (int s = 0; s < 2 * N; ++s) S->contact[s] = contact[s] ? 1 : 0;
+    GrpSerial g;
+    int it = 0;
+    int st = solve_instance<N>(P, *S, xref, g, it);
+    std::memcpy(forces, S->u, sizeof(double) * 6 * N);
+    if (iters) *iters = it;
+    delete S;
+    return st;
+}
+
+template <int N>
+static void run_dump(const Tron1Const& P, const double* x0, const double* xref, const double* feet,
+                     double* H, double* f, double* A_aug, double* B_aug) {
+    auto* S = new Tron1Work<N>();
+    std::memcpy(S->x0, x0, sizeof(double) * 13);
+    std::memcpy(S->feet, feet, sizeof(double) * ((P.per_step_feet && P.ltv) ? 6 * N : 6));
+    for (int s = 0; s < 2 * N; ++s) S->contact[s] = 1;
+    GrpSerial g;
+    setup_instance<N>(P, *S, xref, g);
+    build_hessian<N>(P, *S, 0.0, false, g);
+    const int n = 6 * N, p = 13 * (N + 1);
+    if (H)
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j <= i; ++j) { H[i + n * j] = S->A[MPC_PK(i, j)]; H[j + n * i] = S->A[MPC_PK(i, j)]; }
+    if (f) std::memcpy(f, S->f, sizeof(double) * n);
+    if (A_aug)
+        for (int i = 0; i <= N; ++i)
+            for (int r = 0; r < 13; ++r)
+                for (int c = 0; c < 13; ++c) A_aug[(13 * i + r) + p * c] = a_aug_entry<N>(P, *S, i, r, c);
+    if (B_aug)
+        for (int i = 0; i <= N; ++i)
+            for (int j = 0; j < N; ++j)
+                for (int r = 0; r < 13; ++r)
+                    for (int c = 0; c < 6; ++c) B_aug[(13 * i + r) + p * (6 * j + c)] = b_aug_entry<N>(P, *S, i, j, r, c);
+    delete S;
+}
+
+extern "C" {
+
+int emul_tron1_solve(const mpc_b200_tron1_params* prm, int N, const double* x0, const double* xref,
+                     const double* feet, const uint8_t* contact, double* forces, int* iters) {
+    Tron1Const P;
+    if (make_tron1_const(*prm, P)) return -1;
+    switch (N) {
+        case 4: return run_solve<4>(P, x0, xref, feet, contact, forces, iters);
+        case 10: return run_solve<10>(P, x0, xref, feet, contact, forces, iters);
+        case 20: return run_solve<20>(P, x0, xref, feet, contact, forces, iters);
+        default: return -2;
+    }
+}
+
+int emul_tron1_dump(const mpc_b200_tron1_params* prm, int N, const double* x0, const double* xref,
+                    const double* feet, double* H, double* f, double* A_aug, double* B_aug) {
+    Tron1Const P;
+    if (make_tron1_const(*prm, P)) return -1;
+    switch (N) {
+        case 4: run_dump<4>(P, x0, xref, feet, H, f, A_aug, B_aug); return 0;
+        case 10: run_dump<10>(P, x0, xref, feet, H, f, A_aug, B_aug); return 0;
+        case 20: run_dump<20>(P, x0, xref, feet, H, f, A_aug, B_aug); return 0;
+        default: return -2;
+    }
+}
+
+void emul_gait_contact(const mpc_b200_tron1_params* prm, int iter, int N, uint8_t* contact) {
+    Tron1Const P;
+    make_tron1_const(*prm, P);
+    for (int k = 0; k < N; ++k) {
+        int l, r;
+        gait_contact(P, iter < 0 ? iter : iter + k * P.gait_mpc_step, l, r);
+        contact[2 * k] = (uint8_t)l;
+        contact[2 * k + 1] = (uint8_t)r;
+    }
+}
+}
