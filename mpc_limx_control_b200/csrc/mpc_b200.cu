@@ -1,0 +1,454 @@
+// mpc_b200.cu -- sm_100a kernels and the C ABI (include/mpc_b200.h) of the batched convex-MPC engine.
+//
+// Kernel map:
+//   tron1_solve_kernel<N,WPI,IPC>   the hot path: one thread group (WPI warps) per robot instance,
+//                                   IPC instances per CTA; inputs staged into shared memory with
+//                                   1-D TMA bulk copies (cp.async.bulk + mbarrier), everything else
+//                                   (model, condensing, packed Cholesky, active-face iterations,
+//                                   ADMM fallback) lives in shared memory / registers; only the
+//                                   forces, status and iteration count go back to HBM.
+//   tron1_condense_kernel<N>        parity dump of H, f, A_aug, B_aug (tests only use it)
+//   contact_schedule_kernel         MPC::calculateGait over the horizon, bit-exact
+//   fp64_peak_kernel                DFMA-chain microbenchmark: the FP64 roofline denominator
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/mpc_b200.h"
+#include "tron1_core.cuh"
+#include "tron1_params.h"
+
+using namespace mpcb200;
+
+// ------------------------------------------------------------------------------------------------
+// thread group = WPI warps cooperating on one instance
+template <int WPI>
+struct GrpCuda {
+    int t, gid;
+    __device__ __forceinline__ int tid() const { return t; }
+    __device__ __forceinline__ int size() const { return 32 * WPI; }
+    __device__ __forceinline__ void sync() const {
+        if (WPI == 1) __syncwarp();
+        else asm volatile("bar.sync %0, %1;" ::"r"(gid + 1), "n"(32 * WPI) : "memory");
+    }
+};
+
+// ---- 1-D TMA bulk copy global -> shared, completion on an mbarrier --------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    }
+}
+
+template <int N, int IPC>
+struct CtaStage {
+    static constexpr int XR = 13 * (N + 1);
+    alignas(16) double xr[IPC * XR];
+    alignas(16) double x0[IPC * 13 + 1];
+    alignas(16) double feet[IPC * 6 * N];   // sized for per-step feet
+    alignas(8) uint64_t bar;
+};
+
+template <int N, int WPI, int IPC>
+__global__ void __launch_bounds__(32 * WPI * IPC)
+tron1_solve_kernel(const __grid_constant__ Tron1Const P, int B, const double* __restrict__ x0,
+                   const double* __restrict__ xref, const double* __restrict__ feet,
+                   const uint8_t* __restrict__ contact, const int32_t* __restrict__ iter,
+                   double* __restrict__ forces, int32_t* __restrict__ status, int32_t* __restrict__ iters) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    using Stage = CtaStage<N, IPC>;
+    using Work = Tron1Work<N>;
+    Stage& st = *reinterpret_cast<Stage*>(smem_raw);
+    constexpr size_t stage_bytes = (sizeof(Stage) + 15) & ~size_t(15);
+    Work* works = reinterpret_cast<Work*>(smem_raw + stage_bytes);
+
+    const int first = blockIdx.x * IPC;
+    const int valid = min(IPC, B - first);
+    const int fstride = (P.per_step_feet && P.ltv) ? 6 * N : 6;
+    constexpr int XR = Stage::XR;
+
+    // ---- stage this CTA's inputs: TMA bulk copies when the CTA's slice is 16-byte aligned ----------
+    const double* gx = xref + (size_t)first * XR;
+    const double* g0 = x0 + (size_t)first * 13;
+    const double* gf = feet + (size_t)first * fstride;
+    const uint32_t bx = (uint32_t)(valid * XR * sizeof(double));
+    const uint32_t b0 = (uint32_t)(valid * 13 * sizeof(double));
+    const uint32_t bf = (uint32_t)(valid * fstride * sizeof(double));
+    const bool bulk = (((uintptr_t)gx | (uintptr_t)g0 | (uintptr_t)gf | bx | b0 | bf) & 15) == 0;
+    if (bulk) {
+        if (threadIdx.x == 0) {
+            mbar_init(&st.bar, 1);
+            mbar_expect_tx(&st.bar, bx + b0 + bf);
+            bulk_g2s(st.xr, gx, bx, &st.bar);
+            bulk_g2s(st.x0, g0, b0, &st.bar);
+            bulk_g2s(st.feet, gf, bf, &st.bar);
+        }
+        __syncthreads();   // barrier init visible before anyone waits
+        mbar_wait(&st.bar, 0);
+    } else {
+        for (int i = threadIdx.x; i < valid * XR; i += blockDim.x) st.xr[i] = gx[i];
+        for (int i = threadIdx.x; i < valid * 13; i += blockDim.x) st.x0[i] = g0[i];
+        for (int i = threadIdx.x; i < valid * fstride; i += blockDim.x) st.feet[i] = gf[i];
+        __syncthreads();
+    }
+
+    GrpCuda<WPI> g;
+    g.t = threadIdx.x % (32 * WPI);
+    g.gid = threadIdx.x / (32 * WPI);
+    if (g.gid >= valid) return;
+    const int b = first + g.gid;
+    Work& S = works[g.gid];
+
+    for (int i = g.t; i < 13; i += g.size()) S.x0[i] = st.x0[g.gid * 13 + i];
+    for (int i = g.t; i < fstride; i += g.size()) S.feet[i] = st.feet[g.gid * fstride + i];
+    if (contact) {
+        for (int s = g.t; s < 2 * N; s += g.size()) S.contact[s] = contact[(size_t)b * 2 * N + s] ? 1 : 0;
+    } else {
+        const int it0 = iter[b];
+        for (int k = g.t; k < N; k += g.size()) {
+            int l, r;
+            gait_contact(P, it0 < 0 ? it0 : it0 + k * P.gait_mpc_step, l, r);
+            S.contact[2 * k] = (int8_t)l;
+            S.contact[2 * k + 1] = (int8_t)r;
+        }
+    }
+    g.sync();
+
+    int its = 0;
+    int code = solve_instance<N>(P, S, st.xr + g.gid * XR, g, its);
+
+    double* out = forces + (size_t)b * 6 * N;
+    for (int i = g.t; i < 6 * N; i += g.size()) out[i] = S.u[i];
+    if (g.t == 0) {
+        if (status) status[b] = code;
+        if (iters) iters[b] = its;
+    }
+}
+
+// ---- parity dump: one warp per instance -------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(32)
+tron1_condense_kernel(const __grid_constant__ Tron1Const P, int B, const double* __restrict__ x0,
+                      const double* __restrict__ xref, const double* __restrict__ feet,
+                      double* __restrict__ H, double* __restrict__ f, double* __restrict__ A_aug,
+                      double* __restrict__ B_aug) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    using Work = Tron1Work<N>;
+    Work& S = *reinterpret_cast<Work*>(smem_raw);
+    const int b = blockIdx.x;
+    if (b >= B) return;
+    GrpCuda<1> g;
+    g.t = threadIdx.x;
+    g.gid = 0;
+    const int fstride = (P.per_step_feet && P.ltv) ? 6 * N : 6;
+    const double* xr = xref + (size_t)b * 13 * (N + 1);
+    for (int i = g.t; i < 13; i += 32) S.x0[i] = x0[(size_t)b * 13 + i];
+    for (int i = g.t; i < fstride; i += 32) S.feet[i] = feet[(size_t)b * fstride + i];
+    for (int s = g.t; s < 2 * N; s += 32) S.contact[s] = 1;
+    g.sync();
+    setup_instance<N>(P, S, xr, g);
+    build_hessian<N>(P, S, 0.0, false, g);
+    constexpr int n = 6 * N, p = 13 * (N + 1);
+    if (H) {
+        double* Hb = H + (size_t)b * n * n;
+        for (int idx = g.t; idx < n * n; idx += 32) {
+            int i = idx % n, j = idx / n;
+            Hb[idx] = i >= j ? S.A[MPC_PK(i, j)] : S.A[MPC_PK(j, i)];
+        }
+    }
+    if (f) for (int i = g.t; i < n; i += 32) f[(size_t)b * n + i] = S.f[i];
+    if (A_aug) {
+        double* Ab = A_aug + (size_t)b * p * 13;
+        for (int idx = g.t; idx < p * 13; idx += 32) {
+            int row = idx % p, c = idx / p;
+            Ab[idx] = a_aug_entry<N>(P, S, row / 13, row % 13, c);
+        }
+    }
+    if (B_aug) {
+        double* Bb = B_aug + (size_t)b * p * n;
+        for (int idx = g.t; idx < p * n; idx += 32) {
+            int row = idx % p, c = idx / p;
+            Bb[idx] = b_aug_entry<N>(P, S, row / 13, c / 6, row % 13, c % 6);
+        }
+    }
+}
+
+__global__ void contact_schedule_kernel(const __grid_constant__ Tron1Const P, int B, int N,
+                                        const int32_t* __restrict__ iter, uint8_t* __restrict__ contact) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * N) return;
+    int b = idx / N, k = idx % N;
+    int it0 = iter[b], l, r;
+    gait_contact(P, it0 < 0 ? it0 : it0 + k * P.gait_mpc_step, l, r);
+    contact[2 * (size_t)idx] = (uint8_t)l;
+    contact[2 * (size_t)idx + 1] = (uint8_t)r;
+}
+
+// ---- FP64 peak: 8 independent DFMA chains per thread, register resident -------------------------------
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int reps, double a, double b) {
+    double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int r = 0; r < reps; ++r) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+struct mpc_b200_engine {
+    int device = 0, N = 0, max_batch = 0;
+    mpc_b200_tron1_params params;
+    Tron1Const C;
+    cudaStream_t stream = nullptr;   // used by the host-buffer entry point
+    // device staging for the host-buffer entry point
+    double *d_x0 = nullptr, *d_xref = nullptr, *d_feet = nullptr, *d_forces = nullptr;
+    uint8_t* d_contact = nullptr;
+    int32_t *d_iter = nullptr, *d_status = nullptr, *d_iters = nullptr;
+    int64_t launches = 0;
+    std::string err;
+};
+
+static int set_err(mpc_b200_engine* e, int code, const char* what, cudaError_t ce = cudaSuccess) {
+    if (e) {
+        e->err = what;
+        if (ce != cudaSuccess) { e->err += ": "; e->err += cudaGetErrorString(ce); }
+    }
+    return code;
+}
+#define CU(e, call)                                                        \
+    do {                                                                   \
+        cudaError_t ce_ = (call);                                          \
+        if (ce_ != cudaSuccess) return set_err((e), MPC_B200_ECUDA, #call, ce_); \
+    } while (0)
+
+template <int N, int WPI, int IPC>
+static size_t solve_smem_bytes() {
+    return ((sizeof(CtaStage<N, IPC>) + 15) & ~size_t(15)) + sizeof(Tron1Work<N>) * IPC;
+}
+
+template <int N, int WPI, int IPC>
+static int launch_solve(mpc_b200_engine* e, int B, const double* x0, const double* xref, const double* feet,
+                        const uint8_t* contact, const int32_t* iter, double* forces, int32_t* status,
+                        int32_t* iters, cudaStream_t s) {
+    auto kern = tron1_solve_kernel<N, WPI, IPC>;
+    const size_t smem = solve_smem_bytes<N, WPI, IPC>();
+    static bool configured[64] = {};
+    if (!configured[e->device & 63]) {
+        CU(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[e->device & 63] = true;
+    }
+    const int grid = (B + IPC - 1) / IPC;
+    kern<<<grid, 32 * WPI * IPC, smem, s>>>(e->C, B, x0, xref, feet, contact, iter, forces, status, iters);
+    CU(e, cudaGetLastError());
+    e->launches++;
+    return MPC_B200_OK;
+}
+
+// compiled configurations: (horizon, warps per instance, instances per CTA)
+static int dispatch_solve(mpc_b200_engine* e, int B, const double* x0, const double* xref, const double* feet,
+                          const uint8_t* contact, const int32_t* iter, double* forces, int32_t* status,
+                          int32_t* iters, cudaStream_t s) {
+    switch (e->N) {
+        case 10: return launch_solve<10, 1, 4>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s);
+        case 20: return launch_solve<20, 2, 2>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s);
+        default: return set_err(e, MPC_B200_EINVAL, "unsupported horizon");
+    }
+}
+
+extern "C" {
+
+int mpc_b200_version(void) { return 100; }
+
+const char* mpc_b200_strerror(int code) {
+    switch (code) {
+        case MPC_B200_OK: return "ok";
+        case MPC_B200_EINVAL: return "invalid argument";
+        case MPC_B200_ENODEV: return "no usable CUDA device (sm_100a required; there is no CPU fallback)";
+        case MPC_B200_ECUDA: return "CUDA runtime error";
+        case MPC_B200_ENOMEM: return "out of memory";
+        case MPC_B200_ECAPACITY: return "batch exceeds engine capacity";
+        default: return "unknown error";
+    }
+}
+
+int mpc_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int mpc_b200_tron1_default_params(mpc_b200_tron1_params* p) {
+    if (!p) return MPC_B200_EINVAL;
+    tron1_default_params(*p);
+    return MPC_B200_OK;
+}
+
+int mpc_b200_create(const mpc_b200_tron1_params* p, int horizon, int max_batch, int device, mpc_b200_engine** out) {
+    if (!p || !out || max_batch < 1) return MPC_B200_EINVAL;
+    if (horizon != 10 && horizon != 20) return MPC_B200_EINVAL;
+    *out = nullptr;
+    int ndev = mpc_b200_device_count();
+    if (device < 0 || device >= ndev) return MPC_B200_ENODEV;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) return MPC_B200_ENODEV;
+    Tron1Const C;
+    if (make_tron1_const(*p, C)) return MPC_B200_EINVAL;
+    if (C.per_step_feet && !C.ltv) return MPC_B200_EINVAL;
+    mpc_b200_engine* e = new (std::nothrow) mpc_b200_engine();
+    if (!e) return MPC_B200_ENOMEM;
+    e->device = device; e->N = horizon; e->max_batch = max_batch; e->params = *p; e->C = C;
+    const int N = horizon;
+    const size_t fstride = (C.per_step_feet && C.ltv) ? 6 * (size_t)N : 6;
+    bool ok = cudaSetDevice(device) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaMalloc(&e->d_x0, sizeof(double) * 13 * max_batch) == cudaSuccess &&
+              cudaMalloc(&e->d_xref, sizeof(double) * 13 * (N + 1) * (size_t)max_batch) == cudaSuccess &&
+              cudaMalloc(&e->d_feet, sizeof(double) * fstride * max_batch) == cudaSuccess &&
+              cudaMalloc(&e->d_forces, sizeof(double) * 6 * N * (size_t)max_batch) == cudaSuccess &&
+              cudaMalloc(&e->d_contact, (size_t)2 * N * max_batch) == cudaSuccess &&
+              cudaMalloc(&e->d_iter, sizeof(int32_t) * max_batch) == cudaSuccess &&
+              cudaMalloc(&e->d_status, sizeof(int32_t) * max_batch) == cudaSuccess &&
+              cudaMalloc(&e->d_iters, sizeof(int32_t) * max_batch) == cudaSuccess;
+    if (!ok) {
+        cudaGetLastError();
+        mpc_b200_destroy(e);
+        return MPC_B200_ENOMEM;
+    }
+    *out = e;
+    return MPC_B200_OK;
+}
+
+int mpc_b200_destroy(mpc_b200_engine* e) {
+    if (!e) return MPC_B200_EINVAL;
+    cudaSetDevice(e->device);
+    if (e->stream) { cudaStreamSynchronize(e->stream); cudaStreamDestroy(e->stream); }
+    cudaFree(e->d_x0); cudaFree(e->d_xref); cudaFree(e->d_feet); cudaFree(e->d_forces);
+    cudaFree(e->d_contact); cudaFree(e->d_iter); cudaFree(e->d_status); cudaFree(e->d_iters);
+    delete e;
+    return MPC_B200_OK;
+}
+
+const char* mpc_b200_last_error(const mpc_b200_engine* e) { return e ? e->err.c_str() : ""; }
+int64_t mpc_b200_launch_count(const mpc_b200_engine* e) { return e ? e->launches : 0; }
+
+int mpc_b200_contact_schedule_device(mpc_b200_engine* e, int B, const int32_t* d_iter, uint8_t* d_contact, void* stream) {
+    if (!e || !d_iter || !d_contact || B < 1) return set_err(e, MPC_B200_EINVAL, "contact_schedule: bad argument");
+    CU(e, cudaSetDevice(e->device));
+    const int total = B * e->N;
+    contact_schedule_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(e->C, B, e->N, d_iter, d_contact);
+    CU(e, cudaGetLastError());
+    e->launches++;
+    return MPC_B200_OK;
+}
+
+int mpc_b200_tron1_solve_device(mpc_b200_engine* e, int B, const double* d_x0, const double* d_x_ref,
+                                const double* d_feet, const uint8_t* d_contact, const int32_t* d_iter,
+                                double* d_forces, int32_t* d_status, int32_t* d_iters, void* stream) {
+    if (!e || !d_x0 || !d_x_ref || !d_feet || !d_forces || B < 1) return set_err(e, MPC_B200_EINVAL, "solve: bad argument");
+    if ((d_contact == nullptr) == (d_iter == nullptr)) return set_err(e, MPC_B200_EINVAL, "solve: pass exactly one of contact / iter");
+    if (((uintptr_t)d_x0 | (uintptr_t)d_x_ref | (uintptr_t)d_feet | (uintptr_t)d_forces) & 7)
+        return set_err(e, MPC_B200_EINVAL, "solve: pointers must be 8-byte aligned");
+    CU(e, cudaSetDevice(e->device));
+    return dispatch_solve(e, B, d_x0, d_x_ref, d_feet, d_contact, d_iter, d_forces, d_status, d_iters, (cudaStream_t)stream);
+}
+
+int mpc_b200_tron1_solve_host(mpc_b200_engine* e, int B, const double* x0, const double* x_ref, const double* feet,
+                              const uint8_t* contact, const int32_t* iter, double* forces, int32_t* status, int32_t* iters) {
+    if (!e || !x0 || !x_ref || !feet || !forces || B < 1) return set_err(e, MPC_B200_EINVAL, "solve_host: bad argument");
+    if ((contact == nullptr) == (iter == nullptr)) return set_err(e, MPC_B200_EINVAL, "solve_host: pass exactly one of contact / iter");
+    if (B > e->max_batch) return set_err(e, MPC_B200_ECAPACITY, "solve_host: B > max_batch");
+    CU(e, cudaSetDevice(e->device));
+    const int N = e->N;
+    const size_t fstride = (e->C.per_step_feet && e->C.ltv) ? 6 * (size_t)N : 6;
+    cudaStream_t s = e->stream;
+    CU(e, cudaMemcpyAsync(e->d_x0, x0, sizeof(double) * 13 * B, cudaMemcpyHostToDevice, s));
+    CU(e, cudaMemcpyAsync(e->d_xref, x_ref, sizeof(double) * 13 * (N + 1) * (size_t)B, cudaMemcpyHostToDevice, s));
+    CU(e, cudaMemcpyAsync(e->d_feet, feet, sizeof(double) * fstride * B, cudaMemcpyHostToDevice, s));
+    if (contact) CU(e, cudaMemcpyAsync(e->d_contact, contact, (size_t)2 * N * B, cudaMemcpyHostToDevice, s));
+    else CU(e, cudaMemcpyAsync(e->d_iter, iter, sizeof(int32_t) * B, cudaMemcpyHostToDevice, s));
+    int rc = dispatch_solve(e, B, e->d_x0, e->d_xref, e->d_feet, contact ? e->d_contact : nullptr,
+                            contact ? nullptr : e->d_iter, e->d_forces, e->d_status, e->d_iters, s);
+    if (rc) return rc;
+    CU(e, cudaMemcpyAsync(forces, e->d_forces, sizeof(double) * 6 * N * (size_t)B, cudaMemcpyDeviceToHost, s));
+    if (status) CU(e, cudaMemcpyAsync(status, e->d_status, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, s));
+    if (iters) CU(e, cudaMemcpyAsync(iters, e->d_iters, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, s));
+    CU(e, cudaStreamSynchronize(s));
+    return MPC_B200_OK;
+}
+
+int mpc_b200_tron1_condense_device(mpc_b200_engine* e, int B, const double* d_x0, const double* d_x_ref,
+                                   const double* d_feet, double* d_H, double* d_f, double* d_A_aug,
+                                   double* d_B_aug, void* stream) {
+    if (!e || !d_x0 || !d_x_ref || !d_feet || B < 1) return set_err(e, MPC_B200_EINVAL, "condense: bad argument");
+    CU(e, cudaSetDevice(e->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (e->N == 10) {
+        auto k = tron1_condense_kernel<10>;
+        size_t smem = sizeof(Tron1Work<10>);
+        CU(e, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<B, 32, smem, s>>>(e->C, B, d_x0, d_x_ref, d_feet, d_H, d_f, d_A_aug, d_B_aug);
+    } else if (e->N == 20) {
+        auto k = tron1_condense_kernel<20>;
+        size_t smem = sizeof(Tron1Work<20>);
+        CU(e, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<B, 32, smem, s>>>(e->C, B, d_x0, d_x_ref, d_feet, d_H, d_f, d_A_aug, d_B_aug);
+    } else return set_err(e, MPC_B200_EINVAL, "unsupported horizon");
+    CU(e, cudaGetLastError());
+    e->launches++;
+    return MPC_B200_OK;
+}
+
+int mpc_b200_measure_fp64_peak(int device, double* tflops) {
+    if (!tflops) return MPC_B200_EINVAL;
+    if (device < 0 || device >= mpc_b200_device_count()) return MPC_B200_ENODEV;
+    if (cudaSetDevice(device) != cudaSuccess) return MPC_B200_ECUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return MPC_B200_ECUDA;
+    double* d = nullptr;
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, reps = 2000;
+    if (cudaMalloc(&d, sizeof(double) * blocks * threads) != cudaSuccess) return MPC_B200_ENOMEM;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    double best = 0.0;
+    for (int trial = 0; trial < 5; ++trial) {
+        cudaEventRecord(a);
+        fp64_peak_kernel<<<blocks, threads>>>(d, reps, 0.999999, 1e-9);
+        cudaEventRecord(b);
+        if (cudaEventSynchronize(b) != cudaSuccess) { cudaFree(d); return MPC_B200_ECUDA; }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        double flops = 2.0 * 8 * 16 * (double)reps * blocks * threads;
+        double tf = flops / (ms * 1e-3) / 1e12;
+        if (trial > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(d);
+    *tflops = best;
+    return MPC_B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,144 @@
+"""Host-side plumbing over the C ABI: torch owns device/pinned memory and streams, the engine
+computes.  Mirrors the batch entry point of BASELINE.json's north_star (set state, reference,
+gait/contact schedule and foot positions; get optimal ground-reaction forces).
+
+No CPU fallback: constructing an Engine without the built CUDA library or without a B200-class
+device raises."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _capi
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr())
+
+
+class Engine:
+    """One engine per GPU (single caller).  horizon in {10, 20}."""
+
+    def __init__(self, horizon=10, max_batch=4096, device=0, **param_overrides):
+        self.lib = _capi.lib()
+        self.N = int(horizon)
+        self.max_batch = int(max_batch)
+        self.device = int(device)
+        self.params = _capi.default_params(**param_overrides)
+        self.per_step_feet = bool(self.params.per_step_feet and self.params.ltv)
+        h = C.c_void_p()
+        rc = self.lib.mpc_b200_create(C.byref(self.params), self.N, self.max_batch, self.device, C.byref(h))
+        _capi.check(rc)
+        self.h = h
+        self.tdev = torch.device("cuda", self.device)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mpc_b200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- helpers ---------------------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.tdev).cuda_stream)
+
+    def _check_dev(self, t, dtype, numel, name):
+        if t.device != self.tdev or t.dtype != dtype or not t.is_contiguous() or t.numel() != numel:
+            raise ValueError(f"{name}: expected contiguous {dtype} tensor of {numel} elements on {self.tdev}")
+
+    def launch_count(self):
+        return int(self.lib.mpc_b200_launch_count(self.h))
+
+    # -- device-resident entry points ------------------------------------------------------------
+    def contact_schedule(self, it):
+        """it: int32 [B] on device -> uint8 [B,N,2] (MPC::calculateGait over the horizon)."""
+        B = it.numel()
+        self._check_dev(it, torch.int32, B, "iter")
+        out = torch.empty((B, self.N, 2), dtype=torch.uint8, device=self.tdev)
+        _capi.check(self.lib.mpc_b200_contact_schedule_device(self.h, B, _ptr(it), _ptr(out), self._stream()), self.h)
+        return out
+
+    def solve(self, x0, x_ref, feet, contact=None, it=None, forces=None, status=None, iters=None):
+        """Device tensors in, device tensors out (launched on torch's current stream).
+        x0 [B,13], x_ref [B,N+1,13], feet [B,2,3] (or [B,N,2,3]), contact uint8 [B,N,2] or it int32 [B]."""
+        B, N = x0.shape[0], self.N
+        self._check_dev(x0, torch.float64, B * 13, "x0")
+        self._check_dev(x_ref, torch.float64, B * 13 * (N + 1), "x_ref")
+        self._check_dev(feet, torch.float64, B * (6 * N if self.per_step_feet else 6), "feet")
+        if contact is not None:
+            self._check_dev(contact, torch.uint8, B * 2 * N, "contact")
+        if it is not None:
+            self._check_dev(it, torch.int32, B, "iter")
+        if forces is None:
+            forces = torch.empty((B, N, 6), dtype=torch.float64, device=self.tdev)
+        if status is None:
+            status = torch.empty((B,), dtype=torch.int32, device=self.tdev)
+        if iters is None:
+            iters = torch.empty((B,), dtype=torch.int32, device=self.tdev)
+        rc = self.lib.mpc_b200_tron1_solve_device(self.h, B, _ptr(x0), _ptr(x_ref), _ptr(feet), _ptr(contact), _ptr(it),
+                                                  _ptr(forces), _ptr(status), _ptr(iters), self._stream())
+        _capi.check(rc, self.h)
+        return forces, status, iters
+
+    def condense(self, x0, x_ref, feet, want_pred=True):
+        """Parity dump: H [B,n,n], f [B,n], A_aug [B,13(N+1),13], B_aug [B,13(N+1),n] as numpy,
+        column-major per instance (returned arrays are indexed [b][row][col])."""
+        B, N = x0.shape[0], self.N
+        n, p = 6 * N, 13 * (N + 1)
+        H = torch.empty((B, n, n), dtype=torch.float64, device=self.tdev)
+        f = torch.empty((B, n), dtype=torch.float64, device=self.tdev)
+        A = torch.empty((B, 13, p), dtype=torch.float64, device=self.tdev) if want_pred else None
+        Bm = torch.empty((B, n, p), dtype=torch.float64, device=self.tdev) if want_pred else None
+        rc = self.lib.mpc_b200_tron1_condense_device(self.h, B, _ptr(x0), _ptr(x_ref), _ptr(feet), _ptr(H), _ptr(f),
+                                                     _ptr(A), _ptr(Bm), self._stream())
+        _capi.check(rc, self.h)
+        torch.cuda.synchronize(self.tdev)
+        out = dict(H=H.cpu().numpy().transpose(0, 2, 1), f=f.cpu().numpy())
+        if want_pred:
+            out["A_aug"] = A.cpu().numpy().transpose(0, 2, 1)
+            out["B_aug"] = Bm.cpu().numpy().transpose(0, 2, 1)
+        return out
+
+    # -- host-buffer entry point (the reference-facing call: H2D + solve + D2H inside) -------------
+    def solve_host(self, x0, x_ref, feet, contact=None, it=None, forces=None, status=None, iters=None):
+        """numpy arrays or CPU torch tensors (pinned recommended) in and out."""
+        def as_np(a, dt):
+            if a is None:
+                return None
+            if isinstance(a, torch.Tensor):
+                a = a.numpy()
+            a = np.ascontiguousarray(a, dtype=dt)
+            return a
+        x0 = as_np(x0, np.float64); x_ref = as_np(x_ref, np.float64); feet = as_np(feet, np.float64)
+        contact = as_np(contact, np.uint8); it = as_np(it, np.int32)
+        B, N = x0.shape[0], self.N
+        if forces is None:
+            forces = np.empty((B, N, 6))
+        if status is None:
+            status = np.empty(B, np.int32)
+        if iters is None:
+            iters = np.empty(B, np.int32)
+        fo, so, io = as_np_out(forces), as_np_out(status), as_np_out(iters)
+        p = lambda a: None if a is None else C.c_void_p(a.ctypes.data)
+        rc = self.lib.mpc_b200_tron1_solve_host(self.h, B, p(x0), p(x_ref), p(feet), p(contact), p(it), p(fo), p(so), p(io))
+        _capi.check(rc, self.h)
+        return forces, status, iters
+
+
+def as_np_out(a):
+    if isinstance(a, torch.Tensor):
+        return a.numpy()
+    return a
+
+
+def measure_fp64_peak(device=0):
+    v = C.c_double(0.0)
+    _capi.check(_capi.lib().mpc_b200_measure_fp64_peak(int(device), C.byref(v)))
+    return v.value

@@ -542,6 +542,10 @@ int orc_qp_solve(int n, const double *H, const double *f, int mA, const double *
         for (int i = 0; i < n; ++i) if (fabs(x[i]) > scale) scale = fabs(x[i]);
     }
 done:
+    /* fixed variables (lb == ub) are returned exactly at their bound, as qpOASES reports them */
+    if (status == 0 && lb && ub)
+        for (int i = 0; i < n; ++i)
+            if (lb[i] > -BIG && ub[i] < BIG && ub[i] - lb[i] <= 0.0) x[i] = lb[i];
     if (y_bnd) memset(y_bnd, 0, sizeof(double) * n);
     if (y_row && mA) memset(y_row, 0, sizeof(double) * mA);
     for (int k = 0; k < q; ++k) {

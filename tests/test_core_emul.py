@@ -1,0 +1,103 @@
+"""CPU tier: the product's device source (csrc/tron1_core.cuh) compiled for the host with a
+one-thread group (tests/emul) against the oracle and the golden fixtures.  Checks the kernel
+MATHEMATICS without a GPU; the -m gpu tier re-runs the same comparisons through the C ABI."""
+import numpy as np
+import pytest
+
+import emul_lib as E
+import oracle_lib as O
+from mpc_limx_control_b200 import synth
+
+
+def rel(a, b):
+    return np.abs(np.asarray(a) - np.asarray(b)).max() / max(1e-300, np.abs(np.asarray(b)).max())
+
+
+def test_golden_cases(golden):
+    for key in golden["tron1_cases"]:
+        N = int(golden[f"{key}_N"]); Ts = float(golden[f"{key}_Ts"]); ltv = int(golden[f"{key}_ltv"])
+        p = E.default_params(Ts=Ts, ltv=ltv)
+        x0 = golden[f"{key}_x0"]; xr = golden[f"{key}_xref"].T.copy(); feet = golden[f"{key}_feet"]
+        c = E.dump(p, N, x0, xr, feet)
+        for k in ("H", "f", "A_aug", "B_aug"):
+            assert rel(c[k], golden[f"{key}_{k}"]) < 1e-9, (key, k)      # north_star: 1e-9 relative, FP64
+        contact = golden[f"{key}_contact"]
+        F, st, it = E.solve(p, N, x0, xr, feet, contact)
+        assert st == 0, key
+        assert np.abs(F.reshape(-1) - golden[f"{key}_U"]).max() / max(1.0, np.abs(F).max()) < 1e-5, key
+        assert np.all(F.reshape(N, 2, 3)[contact == 0] == 0.0)
+
+
+@pytest.mark.parametrize("N,Ts,ltv,standing,scale,mu", [
+    (10, 0.005, 0, False, 1, 0.5), (10, 0.005, 1, False, 1, 0.5), (20, 0.005, 1, True, 1, 0.5),
+    (10, 0.05, 1, False, 3, 0.5), (10, 0.001, 1, False, 1, 0.5), (10, 0.02, 1, True, 8, 0.2),
+    (20, 0.05, 1, True, 6, 0.3), (4, 0.01, 1, True, 3, 0.5)])
+def test_random_vs_oracle(N, Ts, ltv, standing, scale, mu):
+    B = 10
+    d = synth.tron1_batch(31, B, N, Ts, standing=standing)
+    po = O.tron1_defaults(Ts=Ts, ltv=ltv, mu=mu); pe = E.default_params(Ts=Ts, ltv=ltv, mu=mu)
+    for b in range(B):
+        x0 = d["x0"][b].copy(); x0[[0, 1, 6, 7, 8, 9, 10, 11]] *= scale
+        xr = d["x_ref"][b]; feet = d["feet"][b]
+        c = O.tron1_condense(po, N, x0, xr, feet); c2 = E.dump(pe, N, x0, xr, feet)
+        for k in ("H", "f", "A_aug", "B_aug"):
+            assert rel(c2[k], c[k]) < 1e-9, k
+        contact = O.contact_schedule(int(d["iter"][b]), N)
+        assert np.array_equal(contact, E.gait_contact(pe, int(d["iter"][b]), N))     # bit-exact mode indices
+        A, lbA, ubA, lb, ub = O.tron1_constraints(po, N, contact)
+        u, info = O.qp_solve(c["H"], c["f"], A, lbA, ubA, lb, ub)
+        F, st, it = E.solve(pe, N, x0, xr, feet, contact)
+        assert st == 0 and info["status"] == 0
+        assert np.abs(F.reshape(-1) - u).max() / max(1.0, np.abs(u).max()) < 1e-4   # north_star tolerance
+        assert O.tron1_natural_residual(po, N, c["H"], c["f"], contact, F) < 1e-6   # KKT residual bound
+
+
+def test_admm_fallback_path():
+    """max_newton=1 forces every instance whose first face guess is wrong through ADMM + polish."""
+    N, Ts, B = 10, 0.02, 12
+    d = synth.tron1_batch(9, B, N, Ts, standing=True)
+    po = O.tron1_defaults(Ts=Ts); pe = E.default_params(Ts=Ts, max_newton=1)
+    used_admm = 0
+    for b in range(B):
+        x0 = d["x0"][b].copy(); x0[[0, 1, 6, 7, 8, 9, 10, 11]] *= 5
+        contact = np.ones((N, 2), np.uint8)
+        c = O.tron1_condense(po, N, x0, d["x_ref"][b], d["feet"][b], want_pred=False)
+        A, lbA, ubA, lb, ub = O.tron1_constraints(po, N, contact)
+        u, info = O.qp_solve(c["H"], c["f"], A, lbA, ubA, lb, ub)
+        F, st, it = E.solve(pe, N, x0, d["x_ref"][b], d["feet"][b], contact)
+        used_admm += it > 1
+        assert st == 0
+        assert np.abs(F.reshape(-1) - u).max() / max(1.0, np.abs(u).max()) < 1e-6
+    assert used_admm > 0
+
+
+def test_iteration_cap_reports_status():
+    N, Ts = 10, 0.02
+    d = synth.tron1_batch(9, 6, N, Ts, standing=True)
+    pe = E.default_params(Ts=Ts, max_newton=1, max_admm=2)
+    sts = []
+    for b in range(6):
+        x0 = d["x0"][b].copy(); x0[[0, 1, 6, 7, 8, 9, 10, 11]] *= 5
+        F, st, it = E.solve(pe, N, x0, d["x_ref"][b], d["feet"][b], np.ones((N, 2), np.uint8))
+        sts.append(st)
+        assert np.isfinite(F).all()
+        # the returned iterate is always feasible
+        F3 = F.reshape(N, 2, 3)
+        assert (np.abs(F3[..., 0]) <= 0.5 * F3[..., 2] + 1e-9).all() and (F3[..., 2] >= -1e-12).all()
+    assert 1 in sts   # ST_MAXITER surfaced, never silently "solved"
+
+
+def test_all_swing_gives_zero():
+    N = 10
+    pe = E.default_params()
+    d = synth.tron1_batch(1, 1, N, 0.005)
+    F, st, it = E.solve(pe, N, d["x0"][0], d["x_ref"][0], d["feet"][0], np.zeros((N, 2), np.uint8))
+    assert st == 0 and np.all(F == 0.0)
+
+
+def test_gait_matches_golden(golden):
+    pe = E.default_params()
+    for it, l, r in zip(golden["gait_iter"][::7], golden["gait_left"][::7], golden["gait_right"][::7]):
+        c = E.gait_contact(pe, int(it), 1)
+        assert c[0, 0] == 1 - l and c[0, 1] == 1 - r
+    assert np.all(E.gait_contact(pe, -1, 5) == 1)   # standing

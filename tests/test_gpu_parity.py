@@ -1,0 +1,229 @@
+"""GPU tier (-m gpu): the CUDA path through the C ABI against the oracle on the same seeded inputs,
+against the committed golden fixtures, and -- at BASELINE.json's full batch sizes -- through
+size-independent properties.  Tolerances (BASELINE.json north_star): H, f, prediction matrices
+1e-9 relative in FP64; forces 1e-4 relative with KKT (natural) residual <= 1e-6; contact/mode
+indices bit-exact."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from mpc_limx_control_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return np.abs(np.asarray(a) - np.asarray(b)).max() / max(1e-300, np.abs(np.asarray(b)).max())
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "GPU tier needs a CUDA device"
+    return torch
+
+
+def make_engine(N, B, **kw):
+    from mpc_limx_control_b200.engine import Engine
+    return Engine(horizon=N, max_batch=B, device=0, **kw)
+
+
+def to_dev(torch, d, keys=("x0", "x_ref", "feet", "iter")):
+    return {k: torch.from_numpy(np.ascontiguousarray(d[k])).cuda() for k in keys}
+
+
+def test_library_loaded_and_device(torch_cuda):
+    from mpc_limx_control_b200 import _capi
+    assert _capi.lib().mpc_b200_device_count() >= 1
+
+
+def test_golden_cases(torch_cuda, golden):
+    torch = torch_cuda
+    for key in golden["tron1_cases"]:
+        N = int(golden[f"{key}_N"]); Ts = float(golden[f"{key}_Ts"]); ltv = int(golden[f"{key}_ltv"])
+        eng = make_engine(N, 4, Ts=Ts, ltv=ltv)
+        x0 = torch.from_numpy(golden[f"{key}_x0"][None].copy()).cuda()
+        xr = torch.from_numpy(golden[f"{key}_xref"].T[None].copy()).cuda()
+        feet = torch.from_numpy(golden[f"{key}_feet"][None].copy()).cuda()
+        contact = torch.from_numpy(golden[f"{key}_contact"][None].copy()).cuda()
+        c = eng.condense(x0, xr, feet)
+        for k in ("H", "f", "A_aug", "B_aug"):
+            assert rel(c[k][0], golden[f"{key}_{k}"]) < 1e-9, (key, k)
+        F, st, it = eng.solve(x0, xr, feet, contact=contact)
+        torch.cuda.synchronize()
+        assert int(st[0]) == 0, key
+        Fn = F.cpu().numpy()[0]
+        assert np.abs(Fn.reshape(-1) - golden[f"{key}_U"]).max() / max(1.0, np.abs(Fn).max()) < 1e-5, key
+        eng.close()
+
+
+@pytest.mark.parametrize("N,Ts,ltv,standing,scale,mu,B", [
+    (10, 0.005, 1, False, 1, 0.5, 67),     # config-2 distribution, odd batch (tail CTA, non-bulk path)
+    (10, 0.005, 0, False, 1, 0.5, 32),     # LTI (reference QPSolver structure)
+    (10, 0.005, 1, True, 1, 0.5, 32),      # standing, n = 60 free variables
+    (10, 0.05, 1, False, 3, 0.5, 32),      # ill-conditioned
+    (10, 0.001, 1, False, 1, 0.5, 32),     # mpcQP.h Ts, fz >= 0 active
+    (10, 0.02, 1, True, 8, 0.2, 48),       # friction pyramid heavily active
+    (20, 0.005, 1, False, 1, 0.5, 21),     # config-3 horizon
+    (20, 0.05, 1, True, 6, 0.3, 16),       # N=20 stress
+])
+def test_batch_vs_oracle(torch_cuda, N, Ts, ltv, standing, scale, mu, B):
+    torch = torch_cuda
+    d = synth.tron1_batch(77, B, N, Ts, standing=standing)
+    d["x0"][:, [0, 1, 6, 7, 8, 9, 10, 11]] *= scale
+    eng = make_engine(N, B, Ts=Ts, ltv=ltv, mu=mu)
+    t = to_dev(torch, d)
+    contact = eng.contact_schedule(t["iter"])
+    c_ref = np.stack([O.contact_schedule(int(i), N) for i in d["iter"]])
+    assert np.array_equal(contact.cpu().numpy(), c_ref)                       # bit-exact
+    po = O.tron1_defaults(Ts=Ts, ltv=ltv, mu=mu)
+    dump = eng.condense(t["x0"], t["x_ref"], t["feet"])
+    F, st, it = eng.solve(t["x0"], t["x_ref"], t["feet"], contact=contact)
+    F2, st2, it2 = eng.solve(t["x0"], t["x_ref"], t["feet"], it=t["iter"])    # in-kernel gait schedule
+    torch.cuda.synchronize()
+    F = F.cpu().numpy(); st = st.cpu().numpy()
+    assert np.array_equal(F, F2.cpu().numpy()) and np.array_equal(st, st2.cpu().numpy())
+    assert (st == 0).all(), st
+    Fo, so, _ = O.tron1_solve_batch(po, N, d["x0"], d["x_ref"], d["feet"], c_ref, nthreads=8)
+    assert (so == 0).all()
+    for b in range(B):
+        c = O.tron1_condense(po, N, d["x0"][b], d["x_ref"][b], d["feet"][b], want_pred=(b < 4))
+        assert rel(dump["H"][b], c["H"]) < 1e-9 and rel(dump["f"][b], c["f"]) < 1e-9
+        if b < 4:
+            assert rel(dump["A_aug"][b], c["A_aug"]) < 1e-9 and rel(dump["B_aug"][b], c["B_aug"]) < 1e-9
+        assert np.abs(F[b] - Fo[b]).max() / max(1.0, np.abs(Fo[b]).max()) < 1e-4
+        assert O.tron1_natural_residual(po, N, c["H"], c["f"], c_ref[b], F[b]) < 1e-6
+        assert np.all(F[b].reshape(N, 2, 3)[c_ref[b] == 0] == 0.0)
+    eng.close()
+
+
+def test_host_entry_point_matches_device(torch_cuda):
+    torch = torch_cuda
+    N, B, Ts = 10, 130, 0.005
+    d = synth.tron1_batch(5, B, N, Ts)
+    eng = make_engine(N, B, Ts=Ts)
+    t = to_dev(torch, d)
+    F, st, it = eng.solve(t["x0"], t["x_ref"], t["feet"], it=t["iter"])
+    torch.cuda.synchronize()
+    pin = {k: torch.from_numpy(np.ascontiguousarray(d[k])).pin_memory() for k in ("x0", "x_ref", "feet", "iter")}
+    Fh = torch.empty((B, N, 6), dtype=torch.float64).pin_memory()
+    sh = torch.empty(B, dtype=torch.int32).pin_memory(); ih = torch.empty(B, dtype=torch.int32).pin_memory()
+    eng.solve_host(pin["x0"], pin["x_ref"], pin["feet"], it=pin["iter"], forces=Fh, status=sh, iters=ih)
+    assert np.array_equal(Fh.numpy(), F.cpu().numpy()) and np.array_equal(sh.numpy(), st.cpu().numpy())
+    # pageable numpy buffers and an explicit contact schedule
+    contact = np.stack([O.contact_schedule(int(i), N) for i in d["iter"]])
+    F3, s3, i3 = eng.solve_host(d["x0"], d["x_ref"], d["feet"], contact=contact)
+    assert np.array_equal(F3, F.cpu().numpy())
+    eng.close()
+
+
+def test_per_step_feet(torch_cuda):
+    torch = torch_cuda
+    N, B, Ts = 10, 24, 0.005
+    d = synth.tron1_batch(8, B, N, Ts, per_step_feet=True)
+    rng = np.random.default_rng(0)
+    d["feet"] = d["feet"] + rng.uniform(-0.02, 0.02, d["feet"].shape) * np.array([1, 1, 0.0])
+    eng = make_engine(N, B, Ts=Ts, per_step_feet=1)
+    t = to_dev(torch, d)
+    F, st, it = eng.solve(t["x0"], t["x_ref"], t["feet"], it=t["iter"])
+    torch.cuda.synchronize()
+    po = O.tron1_defaults(Ts=Ts, per_step_feet=1)
+    c_ref = np.stack([O.contact_schedule(int(i), N) for i in d["iter"]])
+    Fo, so, _ = O.tron1_solve_batch(po, N, d["x0"], d["x_ref"], d["feet"], c_ref, nthreads=8)
+    assert (st.cpu().numpy() == 0).all() and (so == 0).all()
+    assert np.abs(F.cpu().numpy() - Fo).max() / max(1.0, np.abs(Fo).max()) < 1e-4
+    eng.close()
+
+
+def test_edge_batches(torch_cuda):
+    """B = 1, 2, 3, 5 (ragged CTAs) and an all-swing instance."""
+    torch = torch_cuda
+    N, Ts = 10, 0.005
+    eng = make_engine(N, 8, Ts=Ts)
+    po = O.tron1_defaults(Ts=Ts)
+    for B in (1, 2, 3, 5):
+        d = synth.tron1_batch(100 + B, B, N, Ts)
+        t = to_dev(torch, d)
+        c_ref = np.stack([O.contact_schedule(int(i), N) for i in d["iter"]])
+        F, st, it = eng.solve(t["x0"], t["x_ref"], t["feet"], it=t["iter"])
+        torch.cuda.synchronize()
+        Fo, so, _ = O.tron1_solve_batch(po, N, d["x0"], d["x_ref"], d["feet"], c_ref)
+        assert (st.cpu().numpy() == 0).all()
+        assert np.abs(F.cpu().numpy() - Fo).max() / max(1.0, np.abs(Fo).max()) < 1e-4
+    d = synth.tron1_batch(3, 2, N, Ts)
+    t = to_dev(torch, d)
+    zero = torch.zeros((2, N, 2), dtype=torch.uint8, device="cuda")
+    F, st, it = eng.solve(t["x0"], t["x_ref"], t["feet"], contact=zero)
+    torch.cuda.synchronize()
+    assert (st.cpu().numpy() == 0).all() and float(F.abs().max()) == 0.0
+    eng.close()
+
+
+def test_iteration_cap_status(torch_cuda):
+    torch = torch_cuda
+    N, Ts, B = 10, 0.02, 16
+    d = synth.tron1_batch(9, B, N, Ts, standing=True)
+    d["x0"][:, [0, 1, 6, 7, 8, 9, 10, 11]] *= 5
+    eng = make_engine(N, B, Ts=Ts, max_newton=1, max_admm=2)
+    t = to_dev(torch, d)
+    F, st, it = eng.solve(t["x0"], t["x_ref"], t["feet"], it=t["iter"])
+    torch.cuda.synchronize()
+    st = st.cpu().numpy(); F = F.cpu().numpy()
+    assert (st == 1).any() and np.isfinite(F).all()
+    F3 = F.reshape(B, N, 2, 3)
+    assert (np.abs(F3[..., 0]) <= 0.5 * F3[..., 2] + 1e-9).all()
+    eng.close()
+
+
+def test_capacity_and_argument_errors(torch_cuda):
+    torch = torch_cuda
+    from mpc_limx_control_b200 import _capi
+    eng = make_engine(10, 4)
+    d = synth.tron1_batch(1, 8, 10, 0.005)
+    with pytest.raises(_capi.MpcB200Error) as ei:
+        eng.solve_host(d["x0"], d["x_ref"], d["feet"], it=d["iter"])
+    assert ei.value.code == _capi.ECAPACITY
+    t = to_dev(torch, d)
+    with pytest.raises(_capi.MpcB200Error):
+        eng.solve(t["x0"], t["x_ref"], t["feet"])            # neither contact nor iter
+    eng.close()
+
+
+def test_full_size_properties_config2(torch_cuda):
+    """BASELINE config 2 (B=4096, N=10, seed 1001): size-independent properties at full size and
+    oracle parity on a strided sample."""
+    torch = torch_cuda
+    N, B, Ts = 10, 4096, 0.005
+    d = synth.tron1_batch(1001, B, N, Ts)
+    eng = make_engine(N, B, Ts=Ts)
+    t = to_dev(torch, d)
+    F, st, it = eng.solve(t["x0"], t["x_ref"], t["feet"], it=t["iter"])
+    Fb, stb, _ = eng.solve(t["x0"], t["x_ref"], t["feet"], it=t["iter"])
+    torch.cuda.synchronize()
+    F = F.cpu().numpy(); st = st.cpu().numpy()
+    assert np.array_equal(F, Fb.cpu().numpy())                    # deterministic / idempotent
+    assert (st == 0).all()
+    c_ref = np.stack([O.contact_schedule(int(i), N) for i in d["iter"]])
+    F4 = F.reshape(B, N, 2, 3)
+    assert np.all(F4[c_ref == 0] == 0.0)                          # swing feet: exactly zero force
+    assert (np.abs(F4[..., 0]) <= 0.5 * F4[..., 2] + 1e-9).all()  # friction pyramid
+    assert (np.abs(F4[..., 1]) <= 0.5 * F4[..., 2] + 1e-9).all()
+    assert (F4[..., 2] >= -1e-12).all() and (F4[..., 2] <= 2 * 9.585 * 9.8 + 1e-9).all()
+    # permutation equivariance: solving a shuffled batch gives the shuffled forces
+    perm = np.random.default_rng(0).permutation(B)
+    tp = {k: t[k][torch.from_numpy(perm).cuda()].contiguous() for k in t}
+    Fp, _, _ = eng.solve(tp["x0"], tp["x_ref"], tp["feet"], it=tp["iter"])
+    torch.cuda.synchronize()
+    assert np.array_equal(Fp.cpu().numpy(), F[perm])
+    po = O.tron1_defaults(Ts=Ts)
+    idx = np.arange(0, B, 64)
+    Fo, so, _ = O.tron1_solve_batch(po, N, d["x0"][idx], d["x_ref"][idx], d["feet"][idx], c_ref[idx], nthreads=8)
+    assert (so == 0).all()
+    assert np.abs(F[idx] - Fo).max() / max(1.0, np.abs(Fo).max()) < 1e-4
+    eng.close()
+
+
+def test_fp64_peak_measurement(torch_cuda):
+    from mpc_limx_control_b200.engine import measure_fp64_peak
+    tf = measure_fp64_peak(0)
+    assert 5.0 < tf < 80.0, tf
