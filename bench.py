@@ -224,7 +224,7 @@ def run_gpu(args):
         eng.solve_host(a[0], a[1], a[2], it=a[3], forces=a[4], status=a[5], iters=a[6])
         if j >= 200:
             lat.append(time.perf_counter() - t0)
-    lat = np.array(lat) * 1e6
+    lat = np.array(lat if lat else [float("nan")]) * 1e6
 
     # ---- roofline of the dominant (only) kernel of the step --------------------------------------------
     peaks = load_peaks()

@@ -1,0 +1,64 @@
+"""Summarise an ncu report + launch list into profiles/ (tracked evidence).
+usage: python tools/ncu_summary.py <tag> [gpurun_out/prof.ncu-rep] [gpurun_out/launches.csv]"""
+import csv
+import json
+import os
+import subprocess
+import sys
+from collections import defaultdict
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag = sys.argv[1]
+rep = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "gpurun_out", "prof.ncu-rep")
+lst = sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, "gpurun_out", "launches.csv")
+out = os.path.join(ROOT, "profiles")
+
+KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__occupancy_limit_shared_mem",
+        "launch__occupancy_limit_registers", "launch__occupancy_limit_warps", "launch__waves_per_multiprocessor", "launch__grid_size",
+        "launch__block_size", "launch__shared_mem_per_block_dynamic", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "smsp__inst_executed.sum", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+        "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum", "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum",
+        "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "smsp__cycles_active.avg", "sm__cycles_elapsed.max", "sm__cycles_active.avg",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__inst_executed_op_shared_ld.sum", "smsp__inst_executed_op_shared_st.sum"]
+
+summary = {"tag": tag}
+if os.path.exists(rep):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    H = rows[0]
+    kcol = H.index("Kernel Name")
+    kernels = []
+    for r in rows[2:]:
+        k = {"kernel": r[kcol]}
+        for i, h in enumerate(H):
+            if h in KEEP or "warp_issue_stalled" in h and h.endswith("_per_warp_active.pct"):
+                k[h] = r[i] + (" " + rows[1][i] if rows[1][i] else "")
+        kernels.append(k)
+    summary["kernels"] = kernels
+    if kernels:
+        def num(s):
+            return float(s.split()[0].replace(",", ""))
+        k0 = kernels[-1]
+        unit_r = k0["dram__bytes_read.sum"].split()[1]
+        mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        traffic = num(k0["dram__bytes_read.sum"]) * mult[unit_r] + num(k0["dram__bytes_write.sum"]) * mult[k0["dram__bytes_write.sum"].split()[1]]
+        summary["dram_bytes_per_launch"] = traffic
+        json.dump({"dram_bytes_per_launch": traffic, "source": f"profiles/{tag}_solve_kernel.json (ncu --set full)"},
+                  open(os.path.join(out, "traffic.json"), "w"))
+if os.path.exists(lst):
+    rows = [r for r in csv.reader(open(lst)) if len(r) > 5]
+    h = [i for i, r in enumerate(rows) if r[0] == "ID"][0]
+    H, data = rows[h], rows[h + 1:]
+    ki, vi = H.index("Kernel Name"), H.index("Metric Value")
+    agg = defaultdict(list)
+    for r in data:
+        agg[r[ki].split("(")[0][:70]].append(float(r[vi].replace(",", "")))
+    tot = sum(sum(v) for v in agg.values())
+    summary["launch_list"] = [{"kernel": k, "launches": len(v), "mean_us": sum(v) / len(v) / 1e3, "share": sum(v) / tot} for k, v in agg.items()]
+    with open(os.path.join(out, f"{tag}_launches.csv"), "w") as f:
+        f.write(open(lst).read())
+json.dump(summary, open(os.path.join(out, f"{tag}_solve_kernel.json"), "w"), indent=1)
+print(json.dumps(summary, indent=1)[:3000])
