@@ -107,6 +107,46 @@ int mpc_b200_tron1_condense_device(mpc_b200_engine *e, int B, const double *d_x0
                                    const double *d_feet, double *d_H, double *d_f, double *d_A_aug,
                                    double *d_B_aug, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Generic condensed-MPC path: the reference class QPSolver (include/QPSolver.h:13-37), any NX/NU/N.
+ * HOST pointers, column-major (Eigen layout), B independent instances per call (B = 1 for the
+ * facade).  Copies in, runs one CTA per instance on the device, copies out, synchronises. */
+typedef struct mpc_b200_lti mpc_b200_lti;
+int mpc_b200_lti_create(int device, mpc_b200_lti **out);
+int mpc_b200_lti_destroy(mpc_b200_lti *c);
+const char *mpc_b200_lti_last_error(const mpc_b200_lti *c);
+int64_t mpc_b200_lti_launch_count(const mpc_b200_lti *c);
+
+/* QPSolver::discretizeSystem (src/QPSolver.cpp:21-29): Ad, Bd = blocks of exp([[Ac,Bc],[0,0]] Ts).
+ * Ac [B][NX x NX], Bc [B][NX x NU]. */
+int mpc_b200_lti_discretize(mpc_b200_lti *c, int B, int NX, int NU, double Ts, const double *Ac,
+                            const double *Bc, double *Ad, double *Bd);
+
+/* QPSolver::buildQPParams (src/QPSolver.cpp:31-81).  One system (Ad, Bd, Q, R, P, x_min, x_max,
+ * u_min, u_max), B initial states xi0 [B][NX] and references xi_ref [B][NX x (N+1)].
+ * Outputs per instance (any may be NULL): H [n x n], f [n], A_eq [NX N x n], b_eq [NX N], lb/ub [n],
+ * A_ineq [2 NX N x n], lbA/ubA [2 NX N], A_aug [NX(N+1) x NX], B_aug [NX(N+1) x n], n = NU N.
+ * A_eq/b_eq reproduce the reference block as written; it is spurious and the
+ * facade does not pass it on to the solver. */
+int mpc_b200_lti_build_qp(mpc_b200_lti *c, int B, int NX, int NU, int N, const double *Ad,
+                          const double *Bd, const double *Q, const double *R, const double *P,
+                          const double *x_min, const double *x_max, double u_min, double u_max,
+                          const double *xi0, const double *xi_ref, double *H, double *f, double *A_eq,
+                          double *b_eq, double *lb, double *ub, double *A_ineq, double *lbA, double *ubA,
+                          double *A_aug, double *B_aug);
+
+/* QPSolver::solveQP (src/QPSolver.cpp:83-106): min 1/2 u'Hu + f'u, lb <= u <= ub, lbA <= A u <= ubA.
+ * H [B][n x n] symmetric positive definite, A [B][m x n] (m may be 0), bounds beyond
+ * +-MPC_B200_INFTY/2 are infinite, all-zero rows of A are ignored.  status/iters may be NULL.
+ * Unlike the reference (which ignores qpOASES' return value) the status is reported. */
+int mpc_b200_qp_solve_dense(mpc_b200_lti *c, int B, int n, int m, const double *H, const double *f,
+                            const double *A, const double *lb, const double *ub, const double *lbA,
+                            const double *ubA, double *U, int32_t *status, int32_t *iters);
+
+/* QPSolver::updateState (src/QPSolver.cpp:108-111): xi <- Ad xi + Bd u, xi [B][NX] in place. */
+int mpc_b200_lti_update_state(mpc_b200_lti *c, int B, int NX, int NU, const double *Ad,
+                              const double *Bd, double *xi, const double *u);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,6 +18,8 @@ SYMBOLS = [
     "mpc_b200_tron1_default_params", "mpc_b200_create", "mpc_b200_destroy", "mpc_b200_last_error",
     "mpc_b200_launch_count", "mpc_b200_contact_schedule_device", "mpc_b200_tron1_solve_device",
     "mpc_b200_tron1_solve_host", "mpc_b200_tron1_condense_device",
+    "mpc_b200_lti_create", "mpc_b200_lti_destroy", "mpc_b200_lti_last_error", "mpc_b200_lti_launch_count",
+    "mpc_b200_lti_discretize", "mpc_b200_lti_build_qp", "mpc_b200_qp_solve_dense", "mpc_b200_lti_update_state",
 ]
 
 
@@ -67,6 +69,17 @@ def lib():
         L.mpc_b200_tron1_solve_device.argtypes = [vp, ip, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         L.mpc_b200_tron1_solve_host.argtypes = [vp, ip, vp, vp, vp, vp, vp, vp, vp, vp]
         L.mpc_b200_tron1_condense_device.argtypes = [vp, ip, vp, vp, vp, vp, vp, vp, vp, vp]
+        dd = C.c_double
+        L.mpc_b200_lti_create.argtypes = [ip, C.POINTER(vp)]
+        L.mpc_b200_lti_destroy.argtypes = [vp]
+        L.mpc_b200_lti_last_error.restype = C.c_char_p
+        L.mpc_b200_lti_last_error.argtypes = [vp]
+        L.mpc_b200_lti_launch_count.restype = C.c_int64
+        L.mpc_b200_lti_launch_count.argtypes = [vp]
+        L.mpc_b200_lti_discretize.argtypes = [vp, ip, ip, ip, dd, vp, vp, vp, vp]
+        L.mpc_b200_lti_build_qp.argtypes = [vp, ip, ip, ip, ip] + [vp] * 7 + [dd, dd] + [vp] * 13
+        L.mpc_b200_qp_solve_dense.argtypes = [vp, ip, ip, ip] + [vp] * 10
+        L.mpc_b200_lti_update_state.argtypes = [vp, ip, ip, ip, vp, vp, vp, vp]
         _lib = L
     return _lib
 

@@ -1,0 +1,42 @@
+// tron1_single.cpp -- BASELINE config 1b through the controller shim: one TRON1 instance, standing
+// (iter < 0), nominal feet, hold reference; prints the first-step ground-reaction forces and the
+// p50/p99 latency of MPC::run (host call -> forces on host).
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <vector>
+
+#include "../MPCController.h"
+
+using namespace mpcb200::host;
+
+int main(int argc, char** argv) {
+    const int calls = argc > 1 ? atoi(argv[1]) : 2000;
+    try {
+        RobotOdomState s;
+        s.pos[2] = 0.81181;
+        MPC mpc([&] { return s; });
+        mpc.desieredV_pos(0) = 0.0;
+        limxsdk::RobotState st; limxsdk::ImuData imu; limxsdk::RobotCmd cmd;
+        mpc.run(st, imu, cmd, -1);
+        auto f = mpc.supportFootForce();
+        printf("forces %.17g %.17g %.17g %.17g %.17g %.17g certified %d\n", f[0], f[1], f[2], f[3], f[4], f[5],
+               (int)mpc.lastSolveCertified());
+        mpc.run(st, imu, cmd, 250);   // left swing / right stance per calculateGait
+        f = mpc.supportFootForce();
+        printf("gait250 left_state %d right_state %d forces %.17g %.17g %.17g %.17g %.17g %.17g\n", mpc.leftLegState(),
+               mpc.rightLegState(), f[0], f[1], f[2], f[3], f[4], f[5]);
+        std::vector<double> us;
+        for (int i = 0; i < calls + 100; ++i) {
+            auto t0 = std::chrono::steady_clock::now();
+            mpc.run(st, imu, cmd, -1);
+            if (i >= 100) us.push_back(std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count());
+        }
+        std::sort(us.begin(), us.end());
+        if (!us.empty()) printf("latency_us p50 %.2f p99 %.2f calls %zu\n", us[us.size() / 2], us[(size_t)(us.size() * 0.99)], us.size());
+        return 0;
+    } catch (const DeviceError& e) {
+        fprintf(stderr, "tron1_single: %s\n", e.what());
+        return 1;
+    }
+}

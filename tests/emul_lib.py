@@ -71,3 +71,60 @@ def gait_contact(p, it, N):
     c = np.zeros((N, 2), np.uint8)
     lib().emul_gait_contact(C.byref(p), int(it), N, c.ctypes.data_as(_u8))
     return c
+
+
+# ---- generic LTI path (csrc/lti_core.cuh) -----------------------------------------------------------
+_lti = None
+
+
+def lti():
+    global _lti
+    if _lti is None:
+        lib()
+        _lti = C.CDLL(os.path.join(_ROOT, "tests", "emul", "libemul_lti.so"))
+    return _lti
+
+
+def _F(a):
+    return np.asfortranarray(np.asarray(a, dtype=np.float64))
+
+
+def _pp(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def lti_discretize(Ac, Bc, Ts):
+    Ac, Bc = _F(Ac), _F(Bc); NX, NU = Bc.shape
+    Ad = np.zeros((NX, NX), order="F"); Bd = np.zeros((NX, NU), order="F")
+    lti().emul_lti_discretize(NX, NU, C.c_double(Ts), _pp(Ac), _pp(Bc), _pp(Ad), _pp(Bd))
+    return Ad, Bd
+
+
+def lti_build(Ad, Bd, Q, R, P, x_min, x_max, u_min, u_max, N, xi0, xi_ref):
+    Ad, Bd, Q, R, P = _F(Ad), _F(Bd), _F(Q), _F(R), _F(P); NX, NU = Bd.shape; p = NX * (N + 1); n = NU * N
+    x_min, x_max, xi0, xi_ref = _F(x_min), _F(x_max), _F(xi0), _F(xi_ref)
+    o = dict(H=np.zeros((n, n), order="F"), f=np.zeros(n), A_eq=np.zeros((NX * N, n), order="F"), b_eq=np.zeros(NX * N),
+             lb=np.zeros(n), ub=np.zeros(n), A_ineq=np.zeros((2 * NX * N, n), order="F"), lbA_ineq=np.zeros(2 * NX * N),
+             ubA_ineq=np.zeros(2 * NX * N), A_aug=np.zeros((p, NX), order="F"), B_aug=np.zeros((p, n), order="F"))
+    lti().emul_lti_build(NX, NU, N, _pp(Ad), _pp(Bd), _pp(Q), _pp(R), _pp(P), _pp(x_min), _pp(x_max), C.c_double(u_min),
+                         C.c_double(u_max), _pp(xi0), _pp(xi_ref), _pp(o["H"]), _pp(o["f"]), _pp(o["A_eq"]), _pp(o["b_eq"]),
+                         _pp(o["lb"]), _pp(o["ub"]), _pp(o["A_ineq"]), _pp(o["lbA_ineq"]), _pp(o["ubA_ineq"]),
+                         _pp(o["A_aug"]), _pp(o["B_aug"]))
+    return o
+
+
+def qp_dense(H, f, A, lbA, ubA, lb, ub, max_newton=30, max_admm=4000):
+    H = _F(H); n = H.shape[0]; f = _F(f); lb = _F(lb); ub = _F(ub)
+    m = 0 if A is None else A.shape[0]
+    A_ = _F(A) if m else None; lbA_ = _F(lbA) if m else None; ubA_ = _F(ubA) if m else None
+    U = np.zeros(n); it = C.c_int(0)
+    st = lti().emul_qp_dense(n, m, _pp(H), _pp(f), _pp(A_), _pp(lb), _pp(ub), _pp(lbA_), _pp(ubA_), _pp(U), C.byref(it),
+                             int(max_newton), int(max_admm))
+    return U, st, it.value
+
+
+def lti_update(Ad, Bd, xi, u):
+    Ad, Bd = _F(Ad), _F(Bd); NX, NU = Bd.shape
+    xi = np.array(xi, dtype=np.float64); u = np.array(u, dtype=np.float64)
+    lti().emul_lti_update(NX, NU, _pp(Ad), _pp(Bd), _pp(xi), _pp(u))
+    return xi

@@ -1,0 +1,114 @@
+"""GPU tier: the generic QPSolver path through the C ABI (ctypes) and through the C++ facade
+binaries, against the golden demo vectors (reference src/qpSolver_test.cpp scenario) and the oracle."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import npref as R
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EX = os.path.join(ROOT, "mpc_limx_control_b200", "host", "examples")
+
+
+def rel(a, b):
+    return np.abs(np.asarray(a) - np.asarray(b)).max() / max(1e-300, np.abs(np.asarray(b)).max())
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from mpc_limx_control_b200.lti import LtiContext
+    c = LtiContext(0)
+    yield c
+    c.close()
+
+
+def test_discretize_build_golden(ctx, golden):
+    d = R.demo_system()
+    Ad, Bd = ctx.discretize(d["Ac"], d["Bc"], d["Ts"])
+    assert rel(Ad, golden["demo_Ad"]) < 1e-9 and rel(Bd, golden["demo_Bd"]) < 1e-9
+    q = ctx.build_qp(Ad, Bd, d["Q"], d["R"], d["P"], d["x_min"], d["x_max"], d["u_min"], d["u_max"], d["N"],
+                     np.array([2.0, 0, 0, 0]), R.demo_reference(0, d["Ts"], d["N"]))
+    for k, gk in [("A_aug", "demo_A_aug"), ("B_aug", "demo_B_aug"), ("H", "demo_H"), ("f", "demo_f"),
+                  ("A_ineq", "demo_A_ineq"), ("lbA_ineq", "demo_lbA"), ("ubA_ineq", "demo_ubA")]:
+        assert rel(q[k], golden[gk]) < 1e-9, k
+    assert np.all(q["lb"] == -8.0) and np.all(q["ub"] == 8.0)
+
+
+def test_build_batch_and_literal_model(ctx):
+    p = O.tron1_defaults()
+    Ac, Bc = O.tron1_model_literal(p, np.array([0.1, 0.2, 0.8]), np.array([0.05, 0.1, 0.0]))
+    Ad, Bd = ctx.discretize(Ac, Bc, 0.001)
+    Ad2, Bd2 = O.discretize(Ac, Bc, 0.001)
+    assert rel(Ad, Ad2) < 1e-9 and rel(Bd, Bd2) < 1e-9
+    Q = np.diag(p.q[:]); Rm = 0.1 * np.eye(3); P = 20 * Q
+    big = np.full(13, 1e3)
+    rng = np.random.default_rng(1)
+    x0s = np.array([[0.01, 0.02, 0.3, 0.1, 0.2, 0.8, 0.0, 0.1, 0.0, 0.3, 0.0, 0.0, -9.8] + 0 * rng.random(13) for _ in range(3)])
+    x0s[:, :12] += rng.uniform(-0.1, 0.1, (3, 12))
+    xrs = np.stack([O.tron1_reference(x, 20, 0.001) for x in x0s])
+    q = ctx.build_qp(Ad, Bd, Q, Rm, P, -big, big, -8.0, 8.0, 20, x0s, xrs)
+    for b in range(3):
+        o = O.build_qp_params(Ad2, Bd2, Q, Rm, P, -big, big, -8.0, 8.0, 20, x0s[b], xrs[b])
+        for k in ("H", "f", "A_aug", "B_aug", "A_ineq", "lbA_ineq", "ubA_ineq", "A_eq", "b_eq"):
+            assert rel(q[k][b], o[k]) < 1e-9, (b, k)
+
+
+def test_dense_qp_vs_oracle(ctx, golden):
+    U, st, it = ctx.qp_solve(golden["democ_H"], golden["democ_f"], golden["democ_A"], golden["democ_lbA"],
+                             golden["democ_ubA"], golden["democ_lb"], golden["democ_ub"])
+    assert st == 0 and np.abs(U - golden["democ_U"]).max() < 1e-6
+    rng = np.random.default_rng(3)
+    solved = 0
+    for _ in range(15):
+        n = int(rng.integers(3, 25)); m = int(rng.integers(0, 30))
+        M = rng.standard_normal((n, n)); H = M @ M.T + 0.1 * np.eye(n); f = rng.standard_normal(n) * 3
+        A = rng.standard_normal((m, n)); xf = rng.standard_normal(n)
+        lbA = A @ xf - rng.random(m); ubA = A @ xf + rng.random(m); lb = xf - rng.random(n); ub = xf + rng.random(n)
+        ubA[rng.random(m) < 0.3] = O.INFTY; lb[rng.random(n) < 0.3] = -O.INFTY
+        u, info = O.qp_solve(H, f, A, lbA, ubA, lb, ub)
+        U, st, it = ctx.qp_solve(H, f, A if m else None, lbA, ubA, lb, ub)
+        assert st in (0, 1)
+        if st == 0:
+            solved += 1
+            assert np.abs(U - u).max() / max(1.0, np.abs(u).max()) < 1e-4
+            res = np.zeros(4)
+    assert solved >= 12
+
+
+def test_update_state(ctx, golden):
+    x = ctx.update_state(golden["demo_Ad"], golden["demo_Bd"], [2.0, 0, 0, 0], golden["demo_us"][0])
+    assert np.abs(x - golden["demo_xs"][1]).max() < 1e-12
+
+
+def test_facade_qp_test_binary(golden):
+    """the reference's qp_test program through the C++ QPSolver facade: 500 closed-loop steps"""
+    exe = os.path.join(EX, "qp_test")
+    assert os.path.exists(exe), "run __graft_entry__.build()"
+    r = subprocess.run([exe, "500"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    rows = np.array([[float(x) for x in l.split()] for l in r.stdout.strip().splitlines()])
+    assert rows.shape == (500, 8)
+    assert np.abs(rows[:, 1:3] - golden["demo_us"]).max() < 1e-6
+    assert np.abs(rows[:, 3:7] - golden["demo_xs"][1:]).max() < 1e-6
+    assert rows[-1, 7] < 0.05
+
+
+def test_facade_tron1_single_binary(golden):
+    """config 1b through MPC::run (controller shim): forces match the golden standing solution"""
+    exe = os.path.join(EX, "tron1_single")
+    r = subprocess.run([exe, "300"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.strip().splitlines()
+    vals = lines[0].split()
+    f = np.array([float(x) for x in vals[1:7]])
+    assert vals[-1] == "1"
+    assert np.abs(f - golden["t1b0_U"][:6]).max() < 1e-6
+    g = lines[1].split()
+    assert g[2] == "1" and g[4] == "0"           # iter 250: left swing, right stance (calculateGait)
+    fg = np.array([float(x) for x in g[6:12]])
+    assert np.all(fg[:3] == 0.0) and fg[5] > 0.0  # swing foot carries no force
+    assert lines[2].startswith("latency_us")
