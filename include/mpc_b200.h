@@ -21,7 +21,8 @@
  *       status [B] int32       0 solved (KKT certified), 1 iteration limit, 2 failed (non-finite / not PD)
  *       iters  [B] int32       active-face solves + ADMM iterations spent
  *   - every function returns 0 on success or a negative MPC_B200_E* code; nothing prints
- *   - an engine is bound to one CUDA device and is single-caller (not re-entrant)
+ *   - an engine is bound to one CUDA device and is single-caller (not re-entrant); its calls must not
+ *     overlap on the device (issue them in one stream, or synchronise between streams)
  *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream)
  *   - there is no CPU fallback: without a usable CUDA device create() fails with MPC_B200_ENODEV
  */

@@ -27,6 +27,7 @@ using namespace mpcb200;
 // thread group = WPI warps cooperating on one instance
 template <int WPI>
 struct GrpCuda {
+    static constexpr int kThreads = 32 * WPI;
     int t, gid;
     __device__ __forceinline__ int tid() const { return t; }
     __device__ __forceinline__ int size() const { return 32 * WPI; }
@@ -61,6 +62,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+#if defined(MPC_PHASE_TIMING)
+__device__ unsigned long long g_phase_cycles[16];
+extern "C" int mpc_b200_debug_phase_cycles(unsigned long long* out, int reset) {
+    if (out && cudaMemcpyFromSymbol(out, g_phase_cycles, sizeof(unsigned long long) * 16) != cudaSuccess) return -3;
+    if (reset) {
+        unsigned long long z[16] = {};
+        if (cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z)) != cudaSuccess) return -3;
+    }
+    return 0;
+}
+#endif
+
 template <int N, int IPC>
 struct CtaStage {
     static constexpr int XR = 13 * (N + 1);
@@ -70,79 +83,132 @@ struct CtaStage {
     alignas(8) uint64_t bar;
 };
 
-template <int N, int WPI, int IPC>
-__global__ void __launch_bounds__(32 * WPI * IPC)
+// Capacity routing: NC = 3N (one stance foot per step, the reference's alternating gait) keeps the
+// per-instance workspace small enough for 12-16 resident instances per SM; instances that need more
+// (double support) are appended to an overflow list and solved by the NC = 6N instantiation, which
+// runs INDIRECT (list-driven, grid-stride, plain loads) right after.  No host synchronisation.
+template <int N, int NC, int WPI, int IPC, int MINB, bool INDIRECT>
+__global__ void __launch_bounds__(32 * WPI * IPC, MINB)
 tron1_solve_kernel(const __grid_constant__ Tron1Const P, int B, const double* __restrict__ x0,
                    const double* __restrict__ xref, const double* __restrict__ feet,
                    const uint8_t* __restrict__ contact, const int32_t* __restrict__ iter,
-                   double* __restrict__ forces, int32_t* __restrict__ status, int32_t* __restrict__ iters) {
+                   double* __restrict__ forces, int32_t* __restrict__ status, int32_t* __restrict__ iters,
+                   int32_t* __restrict__ ovf_list, int32_t* __restrict__ ovf_count) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using Stage = CtaStage<N, IPC>;
-    using Work = Tron1Work<N>;
+    using Work = Tron1Work<N, NC>;
     Stage& st = *reinterpret_cast<Stage*>(smem_raw);
     constexpr size_t stage_bytes = (sizeof(Stage) + 15) & ~size_t(15);
     Work* works = reinterpret_cast<Work*>(smem_raw + stage_bytes);
-
-    const int first = blockIdx.x * IPC;
-    const int valid = min(IPC, B - first);
     const int fstride = (P.per_step_feet && P.ltv) ? 6 * N : 6;
     constexpr int XR = Stage::XR;
-
-    // ---- stage this CTA's inputs: TMA bulk copies when the CTA's slice is 16-byte aligned ----------
-    const double* gx = xref + (size_t)first * XR;
-    const double* g0 = x0 + (size_t)first * 13;
-    const double* gf = feet + (size_t)first * fstride;
-    const uint32_t bx = (uint32_t)(valid * XR * sizeof(double));
-    const uint32_t b0 = (uint32_t)(valid * 13 * sizeof(double));
-    const uint32_t bf = (uint32_t)(valid * fstride * sizeof(double));
-    const bool bulk = (((uintptr_t)gx | (uintptr_t)g0 | (uintptr_t)gf | bx | b0 | bf) & 15) == 0;
-    if (bulk) {
-        if (threadIdx.x == 0) {
-            mbar_init(&st.bar, 1);
-            mbar_expect_tx(&st.bar, bx + b0 + bf);
-            bulk_g2s(st.xr, gx, bx, &st.bar);
-            bulk_g2s(st.x0, g0, b0, &st.bar);
-            bulk_g2s(st.feet, gf, bf, &st.bar);
-        }
-        __syncthreads();   // barrier init visible before anyone waits
-        mbar_wait(&st.bar, 0);
-    } else {
-        for (int i = threadIdx.x; i < valid * XR; i += blockDim.x) st.xr[i] = gx[i];
-        for (int i = threadIdx.x; i < valid * 13; i += blockDim.x) st.x0[i] = g0[i];
-        for (int i = threadIdx.x; i < valid * fstride; i += blockDim.x) st.feet[i] = gf[i];
-        __syncthreads();
-    }
 
     GrpCuda<WPI> g;
     g.t = threadIdx.x % (32 * WPI);
     g.gid = threadIdx.x / (32 * WPI);
-    if (g.gid >= valid) return;
-    const int b = first + g.gid;
     Work& S = works[g.gid];
+    S.x0 = st.x0 + g.gid * 13;
+    S.feet = st.feet + g.gid * fstride;
+    const double* xr_s = st.xr + g.gid * XR;
 
-    for (int i = g.t; i < 13; i += g.size()) S.x0[i] = st.x0[g.gid * 13 + i];
-    for (int i = g.t; i < fstride; i += g.size()) S.feet[i] = st.feet[g.gid * fstride + i];
-    if (contact) {
-        for (int s = g.t; s < 2 * N; s += g.size()) S.contact[s] = contact[(size_t)b * 2 * N + s] ? 1 : 0;
-    } else {
-        const int it0 = iter[b];
-        for (int k = g.t; k < N; k += g.size()) {
-            int l, r;
-            gait_contact(P, it0 < 0 ? it0 : it0 + k * P.gait_mpc_step, l, r);
-            S.contact[2 * k] = (int8_t)l;
-            S.contact[2 * k + 1] = (int8_t)r;
+    auto load_contact = [&](int b) {   // fills S.contact, returns the compact size 3 * stance foot-steps
+        if (contact) {
+            for (int s = g.t; s < 2 * N; s += g.size()) S.contact[s] = contact[(size_t)b * 2 * N + s] ? 1 : 0;
+        } else {
+            const int it0 = iter[b];
+            for (int k = g.t; k < N; k += g.size()) {
+                int l, r;
+                gait_contact(P, it0 < 0 ? it0 : it0 + k * P.gait_mpc_step, l, r);
+                S.contact[2 * k] = (int8_t)l;
+                S.contact[2 * k + 1] = (int8_t)r;
+            }
         }
-    }
-    g.sync();
+        g.sync();
+        int c = 0;
+        for (int s = 0; s < 2 * N; ++s) c += S.contact[s];
+        return 3 * c;
+    };
+    auto finish = [&](int b) {
+        int its = 0;
+#if defined(MPC_PHASE_TIMING)
+        if (g.t == 0) { for (int i = 0; i < 16; ++i) S.prof[i] = 0; S.t_last = clock64(); }
+        g.sync();
+#endif
+        int code = solve_instance<Work>(P, S, xr_s, g, its);
+#if defined(MPC_PHASE_TIMING)
+        MPC_TICK(S, g, 13);
+        if (g.t == 0) for (int i = 0; i < 16; ++i) atomicAdd(&g_phase_cycles[i], (unsigned long long)S.prof[i]);
+#endif
+        double* out = forces + (size_t)b * 6 * N;
+        for (int i = g.t; i < 6 * N; i += g.size()) out[i] = S.u[i];
+        if (g.t == 0) {
+            if (status) status[b] = code;
+            if (iters) iters[b] = its;
+        }
+    };
 
-    int its = 0;
-    int code = solve_instance<N>(P, S, st.xr + g.gid * XR, g, its);
-
-    double* out = forces + (size_t)b * 6 * N;
-    for (int i = g.t; i < 6 * N; i += g.size()) out[i] = S.u[i];
-    if (g.t == 0) {
-        if (status) status[b] = code;
-        if (iters) iters[b] = its;
+    if (!INDIRECT) {
+        const int first = blockIdx.x * IPC;
+        const int valid = min(IPC, B - first);
+        // ---- stage this CTA's inputs: TMA bulk copies when the CTA's slice is 16-byte aligned ----------
+        const double* gx = xref + (size_t)first * XR;
+        const double* g0 = x0 + (size_t)first * 13;
+        const double* gf = feet + (size_t)first * fstride;
+        const uint32_t bx = (uint32_t)(valid * XR * sizeof(double));
+        const uint32_t b0 = (uint32_t)(valid * 13 * sizeof(double));
+        const uint32_t bf = (uint32_t)(valid * fstride * sizeof(double));
+        const bool bulk = (((uintptr_t)gx | (uintptr_t)g0 | (uintptr_t)gf | bx | b0 | bf) & 15) == 0;
+        if (bulk) {
+            if (threadIdx.x == 0) {
+                mbar_init(&st.bar, 1);
+                mbar_expect_tx(&st.bar, bx + b0 + bf);
+                bulk_g2s(st.xr, gx, bx, &st.bar);
+                bulk_g2s(st.x0, g0, b0, &st.bar);
+                bulk_g2s(st.feet, gf, bf, &st.bar);
+            }
+        } else {
+            for (int i = threadIdx.x; i < valid * XR; i += blockDim.x) st.xr[i] = gx[i];
+            for (int i = threadIdx.x; i < valid * 13; i += blockDim.x) st.x0[i] = g0[i];
+            for (int i = threadIdx.x; i < valid * fstride; i += blockDim.x) st.feet[i] = gf[i];
+        }
+        // the contact schedule is evaluated while the copies are in flight
+        const bool mine = g.gid < valid;
+        const int b = first + g.gid;
+        int nc = 0;
+        if (mine) nc = load_contact(b);
+        __syncthreads();   // barrier init / plain stores visible
+        if (bulk) mbar_wait(&st.bar, 0);
+        if (!mine) return;
+        if (nc > NC) {     // does not fit this capacity class: hand over to the large instantiation
+            if (g.t == 0) {
+                if (ovf_list) ovf_list[atomicAdd(ovf_count, 1)] = b;
+                else if (status) status[b] = ST_FAILED;
+            }
+            return;
+        }
+        finish(b);
+    } else {
+        // ovf_count[0] = list length, ovf_count[1] = CTAs that have read it; the last reader clears both
+        // so the next call starts from zero without a memset (calls of one engine never overlap)
+        __shared__ int s_count;
+        if (threadIdx.x == 0) {
+            s_count = ovf_count[0];
+            if (atomicAdd(&ovf_count[1], 1) == (int)gridDim.x - 1) { ovf_count[0] = 0; ovf_count[1] = 0; }
+        }
+        __syncthreads();
+        const int count = s_count;
+        for (int slot = blockIdx.x * IPC + g.gid; slot < count; slot += gridDim.x * IPC) {
+            const int b = ovf_list[slot];
+            double* sx = st.xr + g.gid * XR;
+            double* s0 = st.x0 + g.gid * 13;
+            double* sf = st.feet + g.gid * fstride;
+            for (int i = g.t; i < XR; i += g.size()) sx[i] = xref[(size_t)b * XR + i];
+            for (int i = g.t; i < 13; i += g.size()) s0[i] = x0[(size_t)b * 13 + i];
+            for (int i = g.t; i < fstride; i += g.size()) sf[i] = feet[(size_t)b * fstride + i];
+            load_contact(b);
+            finish(b);
+            g.sync();
+        }
     }
 }
 
@@ -154,7 +220,7 @@ tron1_condense_kernel(const __grid_constant__ Tron1Const P, int B, const double*
                       double* __restrict__ H, double* __restrict__ f, double* __restrict__ A_aug,
                       double* __restrict__ B_aug) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    using Work = Tron1Work<N>;
+    using Work = Tron1Work<N, 6 * N>;
     Work& S = *reinterpret_cast<Work*>(smem_raw);
     const int b = blockIdx.x;
     if (b >= B) return;
@@ -163,12 +229,12 @@ tron1_condense_kernel(const __grid_constant__ Tron1Const P, int B, const double*
     g.gid = 0;
     const int fstride = (P.per_step_feet && P.ltv) ? 6 * N : 6;
     const double* xr = xref + (size_t)b * 13 * (N + 1);
-    for (int i = g.t; i < 13; i += 32) S.x0[i] = x0[(size_t)b * 13 + i];
-    for (int i = g.t; i < fstride; i += 32) S.feet[i] = feet[(size_t)b * fstride + i];
+    S.x0 = x0 + (size_t)b * 13;
+    S.feet = feet + (size_t)b * fstride;
     for (int s = g.t; s < 2 * N; s += 32) S.contact[s] = 1;
     g.sync();
-    setup_instance<N>(P, S, xr, g);
-    build_hessian<N>(P, S, 0.0, false, g);
+    setup_instance<Work>(P, S, xr, g);
+    build_hessian<Work>(P, S, 0.0, false, g);
     constexpr int n = 6 * N, p = 13 * (N + 1);
     if (H) {
         double* Hb = H + (size_t)b * n * n;
@@ -182,14 +248,14 @@ tron1_condense_kernel(const __grid_constant__ Tron1Const P, int B, const double*
         double* Ab = A_aug + (size_t)b * p * 13;
         for (int idx = g.t; idx < p * 13; idx += 32) {
             int row = idx % p, c = idx / p;
-            Ab[idx] = a_aug_entry<N>(P, S, row / 13, row % 13, c);
+            Ab[idx] = a_aug_entry<Work>(P, S, row / 13, row % 13, c);
         }
     }
     if (B_aug) {
         double* Bb = B_aug + (size_t)b * p * n;
         for (int idx = g.t; idx < p * n; idx += 32) {
             int row = idx % p, c = idx / p;
-            Bb[idx] = b_aug_entry<N>(P, S, row / 13, c / 6, row % 13, c % 6);
+            Bb[idx] = b_aug_entry<Work>(P, S, row / 13, c / 6, row % 13, c % 6);
         }
     }
 }
@@ -229,6 +295,8 @@ struct mpc_b200_engine {
     double *d_x0 = nullptr, *d_xref = nullptr, *d_feet = nullptr, *d_forces = nullptr;
     uint8_t* d_contact = nullptr;
     int32_t *d_iter = nullptr, *d_status = nullptr, *d_iters = nullptr;
+    int32_t *d_ovf_list = nullptr, *d_ovf_count = nullptr;   // capacity-overflow routing: list, {length, readers}
+    int num_sms = 148;
     int64_t launches = 0;
     std::string err;
 };
@@ -246,36 +314,46 @@ static int set_err(mpc_b200_engine* e, int code, const char* what, cudaError_t c
         if (ce_ != cudaSuccess) return set_err((e), MPC_B200_ECUDA, #call, ce_); \
     } while (0)
 
-template <int N, int WPI, int IPC>
+template <int N, int NC, int IPC>
 static size_t solve_smem_bytes() {
-    return ((sizeof(CtaStage<N, IPC>) + 15) & ~size_t(15)) + sizeof(Tron1Work<N>) * IPC;
+    return ((sizeof(CtaStage<N, IPC>) + 15) & ~size_t(15)) + sizeof(Tron1Work<N, NC>) * IPC;
 }
 
-template <int N, int WPI, int IPC>
+// small class (direct, TMA-staged) followed by the large class (indirect, overflow list)
+template <int N, int WPI_S, int IPC_S, int MINB_S, int WPI_L, int IPC_L>
 static int launch_solve(mpc_b200_engine* e, int B, const double* x0, const double* xref, const double* feet,
                         const uint8_t* contact, const int32_t* iter, double* forces, int32_t* status,
                         int32_t* iters, cudaStream_t s) {
-    auto kern = tron1_solve_kernel<N, WPI, IPC>;
-    const size_t smem = solve_smem_bytes<N, WPI, IPC>();
+    auto ks = tron1_solve_kernel<N, 3 * N, WPI_S, IPC_S, MINB_S, false>;
+    auto kl = tron1_solve_kernel<N, 6 * N, WPI_L, IPC_L, 1, true>;
+    const size_t smem_s = solve_smem_bytes<N, 3 * N, IPC_S>();
+    const size_t smem_l = solve_smem_bytes<N, 6 * N, IPC_L>();
     static bool configured[64] = {};
     if (!configured[e->device & 63]) {
-        CU(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(e, cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+        CU(e, cudaFuncSetAttribute(kl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l));
         configured[e->device & 63] = true;
     }
-    const int grid = (B + IPC - 1) / IPC;
-    kern<<<grid, 32 * WPI * IPC, smem, s>>>(e->C, B, x0, xref, feet, contact, iter, forces, status, iters);
+    ks<<<(B + IPC_S - 1) / IPC_S, 32 * WPI_S * IPC_S, smem_s, s>>>(e->C, B, x0, xref, feet, contact, iter, forces, status,
+                                                                 iters, e->d_ovf_list, e->d_ovf_count);
     CU(e, cudaGetLastError());
-    e->launches++;
+    int grid_l = (B + IPC_L - 1) / IPC_L;
+    if (grid_l > e->num_sms * 2) grid_l = e->num_sms * 2;
+    kl<<<grid_l, 32 * WPI_L * IPC_L, smem_l, s>>>(e->C, B, x0, xref, feet, contact, iter, forces, status, iters,
+                                                  e->d_ovf_list, e->d_ovf_count);
+    CU(e, cudaGetLastError());
+    e->launches += 2;
     return MPC_B200_OK;
 }
 
-// compiled configurations: (horizon, warps per instance, instances per CTA)
+// compiled configurations per horizon
 static int dispatch_solve(mpc_b200_engine* e, int B, const double* x0, const double* xref, const double* feet,
                           const uint8_t* contact, const int32_t* iter, double* forces, int32_t* status,
                           int32_t* iters, cudaStream_t s) {
+    if (B > e->max_batch) return set_err(e, MPC_B200_ECAPACITY, "solve: B > max_batch");
     switch (e->N) {
-        case 10: return launch_solve<10, 1, 4>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s);
-        case 20: return launch_solve<20, 2, 2>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s);
+        case 10: return launch_solve<10, 1, 4, 4, 1, 4>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s);
+        case 20: return launch_solve<20, 2, 2, 2, 2, 2>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s);
         default: return set_err(e, MPC_B200_EINVAL, "unsupported horizon");
     }
 }
@@ -333,7 +411,11 @@ int mpc_b200_create(const mpc_b200_tron1_params* p, int horizon, int max_batch, 
               cudaMalloc(&e->d_contact, (size_t)2 * N * max_batch) == cudaSuccess &&
               cudaMalloc(&e->d_iter, sizeof(int32_t) * max_batch) == cudaSuccess &&
               cudaMalloc(&e->d_status, sizeof(int32_t) * max_batch) == cudaSuccess &&
-              cudaMalloc(&e->d_iters, sizeof(int32_t) * max_batch) == cudaSuccess;
+              cudaMalloc(&e->d_iters, sizeof(int32_t) * max_batch) == cudaSuccess &&
+              cudaMalloc(&e->d_ovf_list, sizeof(int32_t) * max_batch) == cudaSuccess &&
+              cudaMalloc(&e->d_ovf_count, 2 * sizeof(int32_t)) == cudaSuccess &&
+              cudaMemset(e->d_ovf_count, 0, 2 * sizeof(int32_t)) == cudaSuccess;
+    e->num_sms = prop.multiProcessorCount;
     if (!ok) {
         cudaGetLastError();
         mpc_b200_destroy(e);
@@ -349,6 +431,7 @@ int mpc_b200_destroy(mpc_b200_engine* e) {
     if (e->stream) { cudaStreamSynchronize(e->stream); cudaStreamDestroy(e->stream); }
     cudaFree(e->d_x0); cudaFree(e->d_xref); cudaFree(e->d_feet); cudaFree(e->d_forces);
     cudaFree(e->d_contact); cudaFree(e->d_iter); cudaFree(e->d_status); cudaFree(e->d_iters);
+    cudaFree(e->d_ovf_list); cudaFree(e->d_ovf_count);
     delete e;
     return MPC_B200_OK;
 }
@@ -409,12 +492,12 @@ int mpc_b200_tron1_condense_device(mpc_b200_engine* e, int B, const double* d_x0
     cudaStream_t s = (cudaStream_t)stream;
     if (e->N == 10) {
         auto k = tron1_condense_kernel<10>;
-        size_t smem = sizeof(Tron1Work<10>);
+        size_t smem = sizeof(Tron1Work<10, 60>);
         CU(e, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k<<<B, 32, smem, s>>>(e->C, B, d_x0, d_x_ref, d_feet, d_H, d_f, d_A_aug, d_B_aug);
     } else if (e->N == 20) {
         auto k = tron1_condense_kernel<20>;
-        size_t smem = sizeof(Tron1Work<20>);
+        size_t smem = sizeof(Tron1Work<20, 120>);
         CU(e, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k<<<B, 32, smem, s>>>(e->C, B, d_x0, d_x_ref, d_feet, d_H, d_f, d_A_aug, d_B_aug);
     } else return set_err(e, MPC_B200_EINVAL, "unsupported horizon");

@@ -73,37 +73,58 @@ MPC_HD void gait_contact(const Tron1Const& P, int iter, int& left_stance, int& r
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int N>
+// N_ = horizon, NC_ = capacity in compact decision variables (3 per stance foot-step).
+// NC_ = 3N serves gaits with one stance foot per step (the reference's alternating gait),
+// NC_ = 6N serves double support; the kernel wrapper routes instances by their actual size.
+template <int N_, int NC_>
 struct Tron1Work {
+    static constexpr int N = N_;
+    static constexpr int NC = NC_;
     static constexpr int NS = 2 * N;     // foot-steps
-    static constexpr int NV = 6 * N;     // decision variables
-    static constexpr int PKN = (NV + 1) * (NV + 2) / 2;  // packed lower triangle incl. rhs row
+    static constexpr int NV = 6 * N;     // decision variables (full layout)
+    static constexpr int PKN = (NC + 1) * (NC + 2) / 2;  // packed lower triangle incl. rhs row
     double A[PKN];          // packed reduced Hessian / Cholesky factor; row nc holds the rhs
-    double dinv[NV];        // 1 / L_kk
+    double dinv[NC];        // 1 / L_kk
+    double w[NC], z[NC], y[NC];   // compact solve vector, ADMM iterates
     double W[N * 18];       // W[k][foot] 3x3 row-major:  Iw_k^-1 [r]x
     double cs[N * 2];       // cos, sin of yaw_k
     double cc[N + 1], ss[N + 1];   // prefix sums  sum_{k<i} cos / sin
     double dc[N], ds[N];    // D_j = 1/2 Rz_j' - C_{j+1}  (cos-like / sin-like entries)
     double SW[N * 8];       // suffix sums over i>j of w_i * {1, cc, ss, cc^2, ss^2, cc ss, i, i^2}
-    double e0[(N + 1) * 12];  // free-response tracking error  A_aug x0 - x_ref  (Theta,p,omega,v)
-    double ee[(N + 1) * 12];  // working tracking error
-    double adj[(N + 1) * 18]; // adjoint terms / suffix sums
-    double tau[(N + 1) * 6];  // per-step input effect (tau_k, phi_k) and scans
-    double f[NV], g[NV], u[NV], w[NV], z[NV], y[NV];
+    double ee[(N + 1) * 12];  // tracking error: free response during setup, input response later
+    double adj[(N + 1) * 18]; // adjoint terms / suffix sums; first 6(N+1) doubles double as `tau`
+    double f[NV], g[NV], u[NV];   // full layout: linear term, gradient, solution
     double res[NS];
-    double x0[13];
-    double feet[N * 6];
+    const double* x0;       // 13 doubles (staged by the caller)
+    const double* feet;     // 6 or 6N doubles
     int8_t contact[NS], ax[NS], ay[NS], zt[NS], nax[NS], nay[NS], nzt[NS];
     int16_t cidx[NS];
     int nc;         // compact variable count (3 * stance foot-steps)
     int flag;       // group-uniform scratch flag
+#if defined(MPC_PHASE_TIMING)
+    long long prof[16];
+    long long t_last;
+#endif
+    MPC_HD double* tau() { return adj; }
 };
 
 #define MPC_PK(i, j) ((i) * ((i) + 1) / 2 + (j))
 
+// optional per-phase cycle accounting (profiling build only: -DMPC_PHASE_TIMING, tools/phase_timing.py)
+#if defined(MPC_PHASE_TIMING) && defined(__CUDA_ARCH__)
+#define MPC_TICK(S, g, id)                                         \
+    do {                                                           \
+        long long t_ = clock64();                                  \
+        if ((g).tid() == 0) { (S).prof[id] += t_ - (S).t_last; (S).t_last = t_; } \
+    } while (0)
+#else
+#define MPC_TICK(S, g, id) do { } while (0)
+#endif
+
 // ---- phase: model of horizon step k  (include/mpcQP.h:121-182, intended physics) -----------------
-template <int N>
-MPC_HD void model_step(const Tron1Const& P, Tron1Work<N>& S, const double* xref, int k) {
+template <class WK>
+MPC_HD void model_step(const Tron1Const& P, WK& S, const double* xref, int k) {
+    [[maybe_unused]] constexpr int N = WK::N;
     const double* lin = (k == 0 || !P.ltv) ? S.x0 : (xref + 13 * k);
     double s, c;
     sincos(lin[2], &s, &c);
@@ -141,8 +162,9 @@ template <int N>
 MPC_HD double step_weight(const Tron1Const& P, int i) { return i == N ? P.p_scale : 1.0; }
 
 // ---- phase: prefix / suffix sums that depend on the yaw sequence only ---------------------------
-template <int N, class G>
-MPC_HD void horizon_sums(const Tron1Const& P, Tron1Work<N>& S, const G& g) {
+template <class WK, class G>
+MPC_HD void horizon_sums(const Tron1Const& P, WK& S, const G& g) {
+    [[maybe_unused]] constexpr int N = WK::N;
     // prefix cc_i, ss_i (two serial scans, one per thread)
     for (int c = g.tid(); c < 2; c += g.size()) {
         double* out = c ? S.ss : S.cc;
@@ -155,28 +177,31 @@ MPC_HD void horizon_sums(const Tron1Const& P, Tron1Work<N>& S, const G& g) {
         S.dc[j] = 0.5 * S.cs[2 * j] - S.cc[j + 1];
         S.ds[j] = 0.5 * S.cs[2 * j + 1] - S.ss[j + 1];
     }
-    // suffix sums over i = j+1..N of w_i * {1, cc_i, ss_i, cc_i^2, ss_i^2, cc_i ss_i, i, i^2}
+    // per-step terms w_i * {1, cc_i, ss_i, cc_i^2, ss_i^2, cc_i ss_i, i, i^2} (parallel over i = 1..N) ...
+    for (int i = 1 + g.tid(); i <= N; i += g.size()) {
+        double w = step_weight<N>(P, i), cc = S.cc[i], ss = S.ss[i], di = (double)i;
+        double* t = S.SW + 8 * (i - 1);
+        t[0] = w; t[1] = w * cc; t[2] = w * ss; t[3] = w * cc * cc; t[4] = w * ss * ss; t[5] = w * cc * ss;
+        t[6] = w * di; t[7] = w * di * di;
+    }
+    g.sync();
+    // ... then suffix sums over i > j, one component per thread (uniform code, no divergence)
     for (int c = g.tid(); c < 8; c += g.size()) {
         double acc = 0.0;
-        for (int i = N; i >= 1; --i) {
-            double w = step_weight<N>(P, i), cc = S.cc[i], ss = S.ss[i], di = (double)i;
-            double t = c == 0 ? 1.0 : c == 1 ? cc : c == 2 ? ss : c == 3 ? cc * cc : c == 4 ? ss * ss
-                     : c == 5 ? cc * ss : c == 6 ? di : di * di;
-            acc += w * t;
-            S.SW[8 * (i - 1) + c] = acc;
-        }
+        for (int j = N - 1; j >= 0; --j) { acc += S.SW[8 * j + c]; S.SW[8 * j + c] = acc; }
     }
     g.sync();
 }
 
 // ---- phase: free-response error  e0_i = (A_aug x0 - x_ref)_i  for i = 0..N ----------------------
-template <int N, class G>
-MPC_HD void free_response(const Tron1Const& P, Tron1Work<N>& S, const double* xref, const G& g) {
+template <class WK, class G>
+MPC_HD void free_response(const Tron1Const& P, WK& S, const double* xref, const G& g) {
+    [[maybe_unused]] constexpr int N = WK::N;
     const double Ts = P.Ts;
     for (int i = g.tid(); i <= N; i += g.size()) {
         const double* x0 = S.x0;
         const double* xr = xref + 13 * i;
-        double* e = S.e0 + 12 * i;
+        double* e = S.ee + 12 * i;
         double cc = S.cc[i], ss = S.ss[i], di = (double)i;
         double gz = x0[12];
         e[0] = x0[0] + Ts * (cc * x0[6] + ss * x0[7]) - xr[0];
@@ -196,14 +221,15 @@ MPC_HD void free_response(const Tron1Const& P, Tron1Work<N>& S, const double* xr
 }
 
 // ---- phase: input response  ee_i = (B_aug u)_i  for i = 0..N (u in full layout) -----------------
-template <int N, class G>
-MPC_HD void input_response(const Tron1Const& P, Tron1Work<N>& S, const double* u, const G& g) {
+template <class WK, class G>
+MPC_HD void input_response(const Tron1Const& P, WK& S, const double* u, const G& g) {
+    [[maybe_unused]] constexpr int N = WK::N;
     const double Ts = P.Ts;
     // per step: tau_k = sum_a W_ka u_ka ; phi_k = sum_a u_ka / m
     for (int k = g.tid(); k < N; k += g.size()) {
         const double* W0 = S.W + 18 * k;
         const double* uk = u + 6 * k;
-        double* t = S.tau + 6 * k;
+        double* t = S.tau() + 6 * k;
         for (int i = 0; i < 3; ++i) {
             t[i] = W0[i * 3] * uk[0] + W0[i * 3 + 1] * uk[1] + W0[i * 3 + 2] * uk[2]
                  + W0[9 + i * 3] * uk[3] + W0[9 + i * 3 + 1] * uk[4] + W0[9 + i * 3 + 2] * uk[5];
@@ -211,43 +237,45 @@ MPC_HD void input_response(const Tron1Const& P, Tron1Work<N>& S, const double* u
         }
     }
     g.sync();
-    // serial recursion per component group: thread 0 -> (omega, Theta), thread 1 -> (v, p)
-    for (int c = g.tid(); c < 2; c += g.size()) {
-        if (c == 0) {
-            double w0 = 0, w1 = 0, w2 = 0, t0 = 0, t1 = 0, t2 = 0;
-            for (int k = 0; k <= N; ++k) {
-                double* e = S.ee + 12 * k;
-                e[0] = t0; e[1] = t1; e[2] = t2; e[6] = w0; e[7] = w1; e[8] = w2;
-                if (k == N) break;
-                const double* t = S.tau + 6 * k;
-                double cz = S.cs[2 * k], sz = S.cs[2 * k + 1];
-                // Theta+ = Theta + Ts Rz'(omega + Ts/2 tau)
-                double a0 = w0 + 0.5 * Ts * t[0], a1 = w1 + 0.5 * Ts * t[1], a2 = w2 + 0.5 * Ts * t[2];
-                t0 += Ts * (cz * a0 + sz * a1);
-                t1 += Ts * (-sz * a0 + cz * a1);
-                t2 += Ts * a2;
-                w0 += Ts * t[0]; w1 += Ts * t[1]; w2 += Ts * t[2];
-            }
-        } else {
-            double v0 = 0, v1 = 0, v2 = 0, p0 = 0, p1 = 0, p2 = 0;
-            for (int k = 0; k <= N; ++k) {
-                double* e = S.ee + 12 * k;
-                e[3] = p0; e[4] = p1; e[5] = p2; e[9] = v0; e[10] = v1; e[11] = v2;
-                if (k == N) break;
-                const double* t = S.tau + 6 * k + 3;
-                p0 += Ts * (v0 + 0.5 * Ts * t[0]);
-                p1 += Ts * (v1 + 0.5 * Ts * t[1]);
-                p2 += Ts * (v2 + 0.5 * Ts * t[2]);
-                v0 += Ts * t[0]; v1 += Ts * t[1]; v2 += Ts * t[2];
-            }
+    // level 1: omega_k = Ts sum_{m<k} tau_m, v_k = Ts sum_{m<k} phi_m  (one component per thread, uniform code)
+    for (int c = g.tid(); c < 6; c += g.size()) {
+        double acc = 0.0;
+        double* dst = S.ee + 6 + c;                      // omega -> 6..8, v -> 9..11
+        for (int k = 0; k <= N; ++k) {
+            dst[12 * k] = acc;
+            if (k < N) acc += Ts * S.tau()[6 * k + c];
+        }
+    }
+    g.sync();
+    // level 2: per-step increments  dTheta_k = Ts Rz_k'(omega_k + Ts/2 tau_k),  dp_k = Ts (v_k + Ts/2 phi_k)
+    for (int k = g.tid(); k < N; k += g.size()) {
+        double* t = S.tau() + 6 * k;
+        const double* e = S.ee + 12 * k;
+        double cz = S.cs[2 * k], sz = S.cs[2 * k + 1];
+        double a0 = e[6] + 0.5 * Ts * t[0], a1 = e[7] + 0.5 * Ts * t[1], a2 = e[8] + 0.5 * Ts * t[2];
+        double b0 = e[9] + 0.5 * Ts * t[3], b1 = e[10] + 0.5 * Ts * t[4], b2 = e[11] + 0.5 * Ts * t[5];
+        t[0] = Ts * (cz * a0 + sz * a1);
+        t[1] = Ts * (-sz * a0 + cz * a1);
+        t[2] = Ts * a2;
+        t[3] = Ts * b0; t[4] = Ts * b1; t[5] = Ts * b2;
+    }
+    g.sync();
+    // level 3: Theta_k, p_k = prefix sums of the increments
+    for (int c = g.tid(); c < 6; c += g.size()) {
+        double acc = 0.0;
+        double* dst = S.ee + c;                          // Theta -> 0..2, p -> 3..5
+        for (int k = 0; k <= N; ++k) {
+            dst[12 * k] = acc;
+            if (k < N) acc += S.tau()[6 * k + c];
         }
     }
     g.sync();
 }
 
 // ---- phase: adjoint  out = 2 B_aug' Qbar e   (e: (N+1) x 12, out: full layout 6N) ----------------
-template <int N, class G>
-MPC_HD void adjoint(const Tron1Const& P, Tron1Work<N>& S, const double* e, double* out, const G& g) {
+template <class WK, class G>
+MPC_HD void adjoint(const Tron1Const& P, WK& S, const double* e, double* out, const G& g) {
+    [[maybe_unused]] constexpr int N = WK::N;
     const double Ts = P.Ts;
     const double* q = P.q;
     // weighted terms of step i (row i-1 of adj holds step i, i = 1..N)
@@ -309,13 +337,14 @@ MPC_HD FaceZ face_basis(double mu, int ax, int ay, int zt) {
 // ---- phase: packed reduced Hessian  A = Z'(H + rho I)Z  over the stance variables ----------------
 // H = 2(B'QB + R) (src/QPSolver.cpp:58) restricted to stance foot-steps; eliminated variables get
 // a unit diagonal.  Work item = one pair of horizon steps (j >= l).
-template <int N, class G>
-MPC_HD void build_hessian(const Tron1Const& P, Tron1Work<N>& S, double rho, bool use_face, const G& g) {
+template <class WK, class G>
+MPC_HD void build_hessian(const Tron1Const& P, WK& S, double rho, bool use_face, const G& g) {
+    [[maybe_unused]] constexpr int N = WK::N;
     const double Ts2 = P.Ts * P.Ts, Ts4 = Ts2 * Ts2, im2 = P.inv_m * P.inv_m;
     const double* q = P.q;
     for (int pr = g.tid(); pr < N * (N + 1) / 2; pr += g.size()) {
         // unrank pr -> (j, l), j >= l
-        int j = (int)((sqrt(8.0 * pr + 1.0) - 1.0) * 0.5);
+        int j = (int)((sqrtf(8.0f * (float)pr + 1.0f) - 1.0f) * 0.5f);
         while (j * (j + 1) / 2 > pr) --j;
         while ((j + 1) * (j + 2) / 2 <= pr) ++j;
         int l = pr - j * (j + 1) / 2;
@@ -394,10 +423,76 @@ MPC_HD void build_hessian(const Tron1Const& P, Tron1Work<N>& S, double rho, bool
     g.sync();
 }
 
+#if defined(__CUDA_ARCH__)
+// ---- device fast path: right-looking Cholesky with ONE ROW PER THREAD held in registers ------------
+// Thread t owns row t of [H; rhs'] (rows 0..nc, row nc is the rhs).  Column k: the pivot comes from
+// its owner by warp shuffle (one-warp groups) or through shared memory, every row scales its entry
+// with rsqrt, publishes it in the packed factor (which doubles as the broadcast buffer), and the
+// trailing update reads column k by uniform-address (broadcast) loads.  Static indexing keeps the row
+// in registers; `k < n` / `j < n` predicates are group-uniform.  Result layout == generic path:
+// packed L in S.A, 1/L_kk in S.dinv, L^-1 rhs in row nc.
+template <class WK, class G>
+__device__ __noinline__ bool cholesky_regs(WK& S, const G& g) {
+    constexpr int NC = WK::NC;
+    const int n = S.nc, t = g.tid();
+    double* A = S.A;
+    double a[NC];
+    const bool row = t <= n;
+    const double* mine = A + MPC_PK(t, 0);
+#pragma unroll
+    for (int j = 0; j < NC; ++j) a[j] = (row && j < n && (j <= t || t == n)) ? mine[j] : 0.0;
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+        if (k < n) {
+            double d;
+            if (G::kThreads == 32) d = __shfl_sync(0xffffffffu, a[k], k);
+            else {
+                if (t == k) S.w[k] = a[k];
+                g.sync();
+                d = S.w[k];
+            }
+            if (!(d > 0.0)) { ok = false; d = 1.0; }
+            const double rs = rsqrt(d);
+            const double l = a[k] * rs;
+            if (row && t > k) A[MPC_PK(t, k)] = l;
+            if (t == k) S.dinv[k] = rs;
+            g.sync();
+            const double* col = A;   // column k entries L[j][k] live at PK(j,k)
+#pragma unroll
+            for (int j = k + 1; j < NC; ++j)
+                if (j < n) a[j] -= l * col[MPC_PK(j, k)];
+        }
+    }
+    g.sync();
+    return ok;
+}
+
+// backward solve L' x = y for one-warp groups: y_i lives in lane i, x_k is broadcast by shuffle
+template <class WK, class G>
+__device__ __noinline__ void backward_regs(WK& S, const G& g) {
+    constexpr int NC = WK::NC;
+    const int n = S.nc, t = g.tid();
+    const double* A = S.A;
+    double y = (t < n) ? A[MPC_PK(n, t)] : 0.0;
+#pragma unroll
+    for (int k = NC - 1; k >= 0; --k) {
+        if (k < n) {
+            const double xk = __shfl_sync(0xffffffffu, y, k) * S.dinv[k];
+            if (t < k) y -= A[MPC_PK(k, t)] * xk;
+            if (t == k) y = xk;
+        }
+    }
+    if (t < n) S.w[t] = y;
+    g.sync();
+}
+#endif
+
 // ---- phase: left-looking packed Cholesky of the leading nc x nc block; row nc (the rhs) is carried
 // along so that on exit A[PK(nc, k)] = (L^-1 rhs)_k.  Returns false if not positive definite.
-template <int N, class G>
-MPC_HD bool cholesky_with_rhs(Tron1Work<N>& S, const G& g) {
+template <class WK, class G>
+MPC_HD bool cholesky_with_rhs(WK& S, const G& g) {
+    [[maybe_unused]] constexpr int N = WK::N;
     const int n = S.nc;
     double* A = S.A;
     if (g.tid() == 0) S.flag = 0;
@@ -427,8 +522,9 @@ MPC_HD bool cholesky_with_rhs(Tron1Work<N>& S, const G& g) {
 }
 
 // backward solve L' x = y with y = A[row nc], result in S.w[0..nc)
-template <int N, class G>
-MPC_HD void backward_solve(Tron1Work<N>& S, const G& g) {
+template <class WK, class G>
+MPC_HD void backward_solve(WK& S, const G& g) {
+    [[maybe_unused]] constexpr int N = WK::N;
     const int n = S.nc;
     double* A = S.A;
     for (int i = g.tid(); i < n; i += g.size()) S.w[i] = A[MPC_PK(n, i)];
@@ -444,8 +540,9 @@ MPC_HD void backward_solve(Tron1Work<N>& S, const G& g) {
 }
 
 // forward solve L y = b with b in S.w (used by ADMM where the factor is reused)
-template <int N, class G>
-MPC_HD void forward_solve(Tron1Work<N>& S, const G& g) {
+template <class WK, class G>
+MPC_HD void forward_solve(WK& S, const G& g) {
+    [[maybe_unused]] constexpr int N = WK::N;
     const int n = S.nc;
     double* A = S.A;
     for (int k = 0; k < n; ++k) {
@@ -480,18 +577,22 @@ MPC_HD void project_pyramid(double mu, double fmax, const double v[3], double ou
 }
 
 // ---- gradient g = H u + f  at u (full layout) -----------------------------------------------------
-template <int N, class G>
-MPC_HD void gradient(const Tron1Const& P, Tron1Work<N>& S, const G& g) {
-    input_response<N>(P, S, S.u, g);
-    adjoint<N>(P, S, S.ee, S.g, g);
+template <class WK, class G>
+MPC_HD void gradient(const Tron1Const& P, WK& S, const G& g) {
+    [[maybe_unused]] constexpr int N = WK::N;
+    input_response<WK>(P, S, S.u, g);
+    MPC_TICK(S, g, 10);
+    adjoint<WK>(P, S, S.ee, S.g, g);
+    MPC_TICK(S, g, 11);
     for (int i = g.tid(); i < 6 * N; i += g.size()) S.g[i] += S.f[i] + 2.0 * P.r * S.u[i];
     g.sync();
 }
 
 // ---- one active-face solve: u = argmin q on the affine hull of the current face -------------------
 // returns false when the reduced Hessian is not positive definite (never for valid inputs)
-template <int N, class G>
-MPC_HD bool face_solve(const Tron1Const& P, Tron1Work<N>& S, const G& g) {
+template <class WK, class G>
+MPC_HD bool face_solve(const Tron1Const& P, WK& S, const G& g) {
+    [[maybe_unused]] constexpr int N = WK::N;
     // fixed part: z = fmax on zt==1 foot-steps
     bool any_fixed = false;
     for (int s = 0; s < 2 * N; ++s) any_fixed |= (S.contact[s] && S.zt[s] == 1);
@@ -502,8 +603,10 @@ MPC_HD bool face_solve(const Tron1Const& P, Tron1Work<N>& S, const G& g) {
         S.u[3 * s + 2] = fz;
     }
     g.sync();
-    if (any_fixed) gradient<N>(P, S, g);   // g0 = f + H u_fix
-    build_hessian<N>(P, S, 0.0, true, g);
+    if (any_fixed) gradient<WK>(P, S, g);   // g0 = f + H u_fix
+    MPC_TICK(S, g, 4);
+    build_hessian<WK>(P, S, 0.0, true, g);
+    MPC_TICK(S, g, 5);
     const int n = S.nc;
     for (int s = g.tid(); s < 2 * N; s += g.size()) {
         if (!S.contact[s]) continue;
@@ -516,8 +619,22 @@ MPC_HD bool face_solve(const Tron1Const& P, Tron1Work<N>& S, const G& g) {
     }
     if (g.tid() == 0) S.A[MPC_PK(n, n)] = 1.0;
     g.sync();
-    bool ok = cholesky_with_rhs<N>(S, g);
-    backward_solve<N>(S, g);
+    MPC_TICK(S, g, 6);
+    bool ok;
+#if defined(__CUDA_ARCH__)
+    if constexpr (G::kThreads >= WK::NC + 1 && WK::NC <= 60) {
+        ok = cholesky_regs<WK>(S, g);
+        MPC_TICK(S, g, 7);
+        if constexpr (G::kThreads == 32) backward_regs<WK>(S, g);
+        else backward_solve<WK>(S, g);
+    } else
+#endif
+    {
+        ok = cholesky_with_rhs<WK>(S, g);
+        MPC_TICK(S, g, 7);
+        backward_solve<WK>(S, g);
+    }
+    MPC_TICK(S, g, 8);
     for (int s = g.tid(); s < 2 * N; s += g.size()) {
         if (!S.contact[s]) continue;
         const double* w = S.w + 3 * S.cidx[s];
@@ -528,14 +645,50 @@ MPC_HD bool face_solve(const Tron1Const& P, Tron1Work<N>& S, const G& g) {
         S.u[3 * s + 1] = S.ay[s] != 0 ? (double)S.ay[s] * P.mu * fz : (zt == 2 ? 0.0 : w[1]);
     }
     g.sync();
+    MPC_TICK(S, g, 9);
     return ok;
 }
 
 // ---- optimality check of S.u: natural residual |u - P_C(u - gamma g)|_inf, predicts the next face --
 // returns true if converged; `changed` tells whether the predicted face differs from the current one
-template <int N, class G>
-MPC_HD bool check_optimality(const Tron1Const& P, Tron1Work<N>& S, const G& g, bool& changed, double& resid) {
-    gradient<N>(P, S, g);
+template <class WK, class G>
+MPC_HD bool check_optimality(const Tron1Const& P, WK& S, const G& g, bool& changed, double& resid) {
+    [[maybe_unused]] constexpr int N = WK::N;
+    gradient<WK>(P, S, g);
+#if defined(__CUDA_ARCH__)
+    if constexpr (G::kThreads == 32 && 2 * N <= 32) {
+        // one foot-step per lane, reductions by warp shuffles
+        const int s = g.tid();
+        double r = 0.0, um = 1.0;
+        bool ch = false;
+        if (s < 2 * N && S.contact[s]) {
+            double v[3], o[3];
+            int ax, ay, zt;
+            for (int c = 0; c < 3; ++c) v[c] = S.u[3 * s + c] - P.gamma * S.g[3 * s + c];
+            project_pyramid(P.mu, P.f_max, v, o, ax, ay, zt);
+            for (int c = 0; c < 3; ++c) {
+                double d = fabs(S.u[3 * s + c] - o[c]);
+                r = d > r ? d : r;
+                double a = fabs(S.u[3 * s + c]);
+                um = a > um ? a : um;
+            }
+            S.nax[s] = (int8_t)ax; S.nay[s] = (int8_t)ay; S.nzt[s] = (int8_t)zt;
+            ch = (ax != S.ax[s]) || (ay != S.ay[s]) || (zt != S.zt[s]);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            double r2 = __shfl_xor_sync(0xffffffffu, r, off), u2 = __shfl_xor_sync(0xffffffffu, um, off);
+            r = r2 > r ? r2 : r;
+            um = u2 > um ? u2 : um;
+        }
+        changed = __any_sync(0xffffffffu, ch);
+        resid = r;
+        g.sync();
+        MPC_TICK(S, g, 12);
+        return r <= P.tol * um;
+    } else
+#endif
+    {
     for (int s = g.tid(); s < 2 * N; s += g.size()) {
         double r = 0.0, um = 0.0;
         if (S.contact[s]) {
@@ -552,49 +705,58 @@ MPC_HD bool check_optimality(const Tron1Const& P, Tron1Work<N>& S, const G& g, b
             S.nax[s] = (int8_t)ax; S.nay[s] = (int8_t)ay; S.nzt[s] = (int8_t)zt;
         }
         S.res[s] = r;
-        S.tau[s] = um;   // scratch: per foot-step |u|_inf
+        S.tau()[s] = um;   // scratch: per foot-step |u|_inf
     }
     g.sync();
     double r = 0.0, um = 1.0;
     bool ch = false;
     for (int s = 0; s < 2 * N; ++s) {
         r = S.res[s] > r ? S.res[s] : r;
-        um = S.tau[s] > um ? S.tau[s] : um;
+        um = S.tau()[s] > um ? S.tau()[s] : um;
         if (S.contact[s]) ch |= (S.nax[s] != S.ax[s]) || (S.nay[s] != S.ay[s]) || (S.nzt[s] != S.zt[s]);
     }
     g.sync();
     changed = ch;
     resid = r;
+    MPC_TICK(S, g, 12);
     return r <= P.tol * um;
+    }
 }
 
-template <int N, class G>
-MPC_HD void adopt_predicted_face(Tron1Work<N>& S, const G& g) {
+template <class WK, class G>
+MPC_HD void adopt_predicted_face(WK& S, const G& g) {
+    [[maybe_unused]] constexpr int N = WK::N;
     for (int s = g.tid(); s < 2 * N; s += g.size()) { S.ax[s] = S.nax[s]; S.ay[s] = S.nay[s]; S.zt[s] = S.nzt[s]; }
     g.sync();
 }
 
 // ---- setup shared by solve and dump: inputs must already be in S.x0 / S.feet / S.contact ---------
-template <int N, class G>
-MPC_HD void setup_instance(const Tron1Const& P, Tron1Work<N>& S, const double* xref, const G& g) {
+template <class WK, class G>
+MPC_HD void setup_instance(const Tron1Const& P, WK& S, const double* xref, const G& g) {
+    [[maybe_unused]] constexpr int N = WK::N;
     if (g.tid() == 0) {
         int c = 0;
         for (int s = 0; s < 2 * N; ++s) { S.cidx[s] = (int16_t)c; c += S.contact[s] ? 1 : 0; }
         S.nc = 3 * c;
     }
     for (int s = g.tid(); s < 2 * N; s += g.size()) { S.ax[s] = 0; S.ay[s] = 0; S.zt[s] = 0; }
-    for (int k = g.tid(); k < N; k += g.size()) model_step<N>(P, S, xref, k);
+    for (int k = g.tid(); k < N; k += g.size()) model_step<WK>(P, S, xref, k);
     g.sync();
-    horizon_sums<N>(P, S, g);
-    free_response<N>(P, S, xref, g);
-    adjoint<N>(P, S, S.e0, S.f, g);   // f = 2 B' Q (A x0 - x_ref)   (src/QPSolver.cpp:59-60)
+    MPC_TICK(S, g, 0);
+    horizon_sums<WK>(P, S, g);
+    MPC_TICK(S, g, 1);
+    free_response<WK>(P, S, xref, g);
+    MPC_TICK(S, g, 2);
+    adjoint<WK>(P, S, S.ee, S.f, g);   // f = 2 B' Q (A x0 - x_ref)   (src/QPSolver.cpp:59-60)
+    MPC_TICK(S, g, 3);
 }
 
 // ---- full QP solve of one instance.  On exit S.u holds the forces (full layout). -----------------
 // iters = face solves + ADMM iterations.
-template <int N, class G>
-MPC_HD int solve_instance(const Tron1Const& P, Tron1Work<N>& S, const double* xref, const G& g, int& iters) {
-    setup_instance<N>(P, S, xref, g);
+template <class WK, class G>
+MPC_HD int solve_instance(const Tron1Const& P, WK& S, const double* xref, const G& g, int& iters) {
+    [[maybe_unused]] constexpr int N = WK::N;
+    setup_instance<WK>(P, S, xref, g);
     iters = 0;
     if (S.nc == 0) {
         for (int i = g.tid(); i < 6 * N; i += g.size()) S.u[i] = 0.0;
@@ -606,15 +768,15 @@ MPC_HD int solve_instance(const Tron1Const& P, Tron1Work<N>& S, const double* xr
     // phase A: active-face (semismooth Newton) iterations, cold start from the interior face
     for (int it = 0; it < P.max_newton; ++it) {
         ++iters;
-        if (!face_solve<N>(P, S, g)) return ST_FAILED;
-        if (check_optimality<N>(P, S, g, changed, resid)) return ST_SOLVED;
+        if (!face_solve<WK>(P, S, g)) return ST_FAILED;
+        if (check_optimality<WK>(P, S, g, changed, resid)) return ST_SOLVED;
         if (!changed) break;   // same face predicted but not optimal: numerical stall -> ADMM
-        adopt_predicted_face<N>(S, g);
+        adopt_predicted_face<WK>(S, g);
     }
     // phase B: ADMM on  min q(u) + I_C(z), u = z  with periodic active-face polish
     const int n = S.nc;
     double hmax = 0.0;
-    build_hessian<N>(P, S, 0.0, false, g);
+    build_hessian<WK>(P, S, 0.0, false, g);
     for (int i = 0; i < n; ++i) hmax = S.A[MPC_PK(i, i)] > hmax ? S.A[MPC_PK(i, i)] : hmax;
     g.sync();
     const double rho = sqrt(2.0 * P.r * hmax * 4.0);
@@ -632,10 +794,10 @@ MPC_HD int solve_instance(const Tron1Const& P, Tron1Work<N>& S, const double* xr
     for (int it = 0; it < P.max_admm; ++it) {
         ++iters;
         if (!have_factor) {
-            build_hessian<N>(P, S, rho, false, g);
+            build_hessian<WK>(P, S, rho, false, g);
             for (int i = g.tid(); i <= n; i += g.size()) S.A[MPC_PK(n, i)] = (i == n) ? 1.0 : 0.0;
             g.sync();
-            if (!cholesky_with_rhs<N>(S, g)) return ST_FAILED;
+            if (!cholesky_with_rhs<WK>(S, g)) return ST_FAILED;
             have_factor = true;
         }
         for (int s = g.tid(); s < 2 * N; s += g.size()) {
@@ -644,10 +806,10 @@ MPC_HD int solve_instance(const Tron1Const& P, Tron1Work<N>& S, const double* xr
             for (int c = 0; c < 3; ++c) S.w[b + c] = rho * (S.z[b + c] - S.y[b + c]) - S.f[3 * s + c];
         }
         g.sync();
-        forward_solve<N>(S, g);
+        forward_solve<WK>(S, g);
         for (int i = g.tid(); i < n; i += g.size()) S.A[MPC_PK(n, i)] = S.w[i];
         g.sync();
-        backward_solve<N>(S, g);
+        backward_solve<WK>(S, g);
         if (g.tid() == 0) S.flag = 0;
         g.sync();
         for (int s = g.tid(); s < 2 * N; s += g.size()) {
@@ -671,8 +833,8 @@ MPC_HD int solve_instance(const Tron1Const& P, Tron1Work<N>& S, const double* xr
         if ((stable >= 3 && since_polish >= 8) || since_polish >= 40) {
             since_polish = 0;
             have_factor = false;
-            if (!face_solve<N>(P, S, g)) return ST_FAILED;
-            if (check_optimality<N>(P, S, g, changed, resid)) return ST_SOLVED;
+            if (!face_solve<WK>(P, S, g)) return ST_FAILED;
+            if (check_optimality<WK>(P, S, g, changed, resid)) return ST_SOLVED;
         }
     }
     // not certified: return the last ADMM iterate (feasible by construction)
@@ -684,8 +846,9 @@ MPC_HD int solve_instance(const Tron1Const& P, Tron1Work<N>& S, const double* xr
 
 // ---- parity dump helpers (closed-form prediction matrices, column-major like Eigen) --------------
 // A_aug: 13(N+1) x 13, block i = A_{i-1}...A_0   (src/QPSolver.cpp:36-40)
-template <int N>
-MPC_HD double a_aug_entry(const Tron1Const& P, const Tron1Work<N>& S, int i, int r, int c) {
+template <class WK>
+MPC_HD double a_aug_entry(const Tron1Const& P, const WK& S, int i, int r, int c) {
+    [[maybe_unused]] constexpr int N = WK::N;
     double v = (r == c) ? 1.0 : 0.0;
     double di = (double)i, Ts = P.Ts;
     if (r < 3 && c >= 6 && c < 9) {   // Theta <- omega : Ts C_i
@@ -699,8 +862,9 @@ MPC_HD double a_aug_entry(const Tron1Const& P, const Tron1Work<N>& S, int i, int
     return v;
 }
 // B_aug block (i,j), i > j: 13 x 6 (src/QPSolver.cpp:42-47 generalised to the per-step model)
-template <int N>
-MPC_HD double b_aug_entry(const Tron1Const& P, const Tron1Work<N>& S, int i, int j, int r, int c) {
+template <class WK>
+MPC_HD double b_aug_entry(const Tron1Const& P, const WK& S, int i, int j, int r, int c) {
+    [[maybe_unused]] constexpr int N = WK::N;
     if (i <= j) return 0.0;
     const double Ts = P.Ts;
     const int a = c / 3, cc = c % 3;

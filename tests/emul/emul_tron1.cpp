@@ -14,37 +14,50 @@
 using namespace mpcb200;
 
 struct GrpSerial {
+    static constexpr int kThreads = 1;
     int tid() const { return 0; }
     int size() const { return 1; }
     void sync() const {}
 };
 
-template <int N>
-static int run_solve(const Tron1Const& P, const double* x0, const double* xref, const double* feet,
-                     const uint8_t* contact, double* forces, int* iters) {
-    auto* S = new Tron1Work<N>();
-    std::memcpy(S->x0, x0, sizeof(double) * 13);
-    std::memcpy(S->feet, feet, sizeof(double) * ((P.per_step_feet && P.ltv) ? 6 * N : 6));
+template <int N, int NC>
+static int run_solve_nc(const Tron1Const& P, const double* x0, const double* xref, const double* feet,
+                        const uint8_t* contact, double* forces, int* iters) {
+    using Work = Tron1Work<N, NC>;
+    auto* S = new Work();
+    S->x0 = x0;
+    S->feet = feet;
     for (int s = 0; s < 2 * N; ++s) S->contact[s] = contact[s] ? 1 : 0;
     GrpSerial g;
     int it = 0;
-    int st = solve_instance<N>(P, *S, xref, g, it);
+    int st = solve_instance<Work>(P, *S, xref, g, it);
     std::memcpy(forces, S->u, sizeof(double) * 6 * N);
     if (iters) *iters = it;
     delete S;
     return st;
 }
 
+// same routing as the kernel wrapper: small capacity class when the instance fits, else the large one
+template <int N>
+static int run_solve(const Tron1Const& P, const double* x0, const double* xref, const double* feet,
+                     const uint8_t* contact, double* forces, int* iters) {
+    int c = 0;
+    for (int s = 0; s < 2 * N; ++s) c += contact[s] ? 1 : 0;
+    if (3 * c <= 3 * N) return run_solve_nc<N, 3 * N>(P, x0, xref, feet, contact, forces, iters);
+    return run_solve_nc<N, 6 * N>(P, x0, xref, feet, contact, forces, iters);
+}
+
 template <int N>
 static void run_dump(const Tron1Const& P, const double* x0, const double* xref, const double* feet,
                      double* H, double* f, double* A_aug, double* B_aug) {
-    auto* S = new Tron1Work<N>();
-    std::memcpy(S->x0, x0, sizeof(double) * 13);
-    std::memcpy(S->feet, feet, sizeof(double) * ((P.per_step_feet && P.ltv) ? 6 * N : 6));
+    using Work = Tron1Work<N, 6 * N>;
+    auto* S = new Work();
+    S->x0 = x0;
+    S->feet = feet;
     for (int s = 0; s < 2 * N; ++s) S->contact[s] = 1;
     GrpSerial g;
-    setup_instance<N>(P, *S, xref, g);
-    build_hessian<N>(P, *S, 0.0, false, g);
+    setup_instance<Work>(P, *S, xref, g);
+    build_hessian<Work>(P, *S, 0.0, false, g);
     const int n = 6 * N, p = 13 * (N + 1);
     if (H)
         for (int i = 0; i < n; ++i)
@@ -53,12 +66,12 @@ static void run_dump(const Tron1Const& P, const double* x0, const double* xref, 
     if (A_aug)
         for (int i = 0; i <= N; ++i)
             for (int r = 0; r < 13; ++r)
-                for (int c = 0; c < 13; ++c) A_aug[(13 * i + r) + p * c] = a_aug_entry<N>(P, *S, i, r, c);
+                for (int c = 0; c < 13; ++c) A_aug[(13 * i + r) + p * c] = a_aug_entry<Work>(P, *S, i, r, c);
     if (B_aug)
         for (int i = 0; i <= N; ++i)
             for (int j = 0; j < N; ++j)
                 for (int r = 0; r < 13; ++r)
-                    for (int c = 0; c < 6; ++c) B_aug[(13 * i + r) + p * (6 * j + c)] = b_aug_entry<N>(P, *S, i, j, r, c);
+                    for (int c = 0; c < 6; ++c) B_aug[(13 * i + r) + p * (6 * j + c)] = b_aug_entry<Work>(P, *S, i, j, r, c);
     delete S;
 }
 

@@ -1,0 +1,37 @@
+"""Per-phase cycle breakdown of the solve kernel (profiling build, -DMPC_PHASE_TIMING).
+Builds a separate library under gpurun_out/ so the product .so is untouched.
+usage (on the GPU box): python tools/phase_timing.py [standing]"""
+import ctypes as C, os, subprocess, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+out = os.path.join(ROOT, "gpurun_out", "libmpc_b200_timing.so")
+os.makedirs(os.path.dirname(out), exist_ok=True)
+csrc = os.path.join(ROOT, "mpc_limx_control_b200", "csrc")
+subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-DMPC_PHASE_TIMING",
+                       "-Xcompiler", "-fPIC", "-shared", "-o", out, os.path.join(csrc, "mpc_b200.cu"), os.path.join(csrc, "lti_b200.cu")])
+from mpc_limx_control_b200 import _capi, synth
+_capi.LIB_PATH = out
+import torch
+from mpc_limx_control_b200.engine import Engine
+standing = len(sys.argv) > 1 and sys.argv[1] == "standing"
+N, B = 10, 4096
+d = synth.tron1_batch(1001, B, N, 0.005, standing=standing)
+eng = Engine(horizon=N, max_batch=B)
+t = {k: torch.from_numpy(d[k]).cuda() for k in ("x0", "x_ref", "feet", "iter")}
+L = _capi.lib()
+buf = (C.c_ulonglong * 16)()
+for _ in range(3):
+    eng.solve(t["x0"], t["x_ref"], t["feet"], it=t["iter"])
+torch.cuda.synchronize()
+L.mpc_b200_debug_phase_cycles(buf, 1)
+F, st, it = eng.solve(t["x0"], t["x_ref"], t["feet"], it=t["iter"])
+torch.cuda.synchronize()
+L.mpc_b200_debug_phase_cycles(buf, 0)
+names = ["model", "horizon_sums", "free_response", "adjoint(f)", "ufix/grad0", "build_hessian", "rhs", "cholesky", "backward",
+         "recover_u", "input_response", "adjoint(g)", "project/check", "tail"]
+v = np.array(list(buf), dtype=np.float64)[:14] / B
+print(f"standing={standing} mean iters {it.float().mean().item():.2f}; cycles per instance (thread-0 wall, includes stalls):")
+for n_, c in zip(names, v):
+    print(f"  {n_:15s} {c:9.0f}  {100 * c / v.sum():5.1f}%")
+print(f"  {'total':15s} {v.sum():9.0f}")
