@@ -66,6 +66,9 @@ typedef struct mpc_b200_tron1_params {
     int32_t max_newton;   /* active-face iterations before the ADMM fallback (default 12) */
     int32_t max_admm;     /* ADMM iteration cap (default 2000) */
     double tol;           /* natural-residual tolerance relative to max(1,|u|_inf) (default 1e-9) */
+    /* nominal base->foot offsets (include/MPCParam.h:64-73), used by the closed-loop rollout */
+    double foot_offset_left[3];
+    double foot_offset_right[3];
 } mpc_b200_tron1_params;
 
 /* library / device */
@@ -107,6 +110,23 @@ int mpc_b200_tron1_solve_host(mpc_b200_engine *e, int B, const double *x0, const
 int mpc_b200_tron1_condense_device(mpc_b200_engine *e, int B, const double *d_x0, const double *d_x_ref,
                                    const double *d_feet, double *d_H, double *d_f, double *d_A_aug,
                                    double *d_B_aug, void *stream);
+
+/* mpcQP's reference generator (include/mpcQP.h:74-97) for a batch: x_ref[b] from x0[b] and the
+ * per-instance commanded yaw rate / forward velocity.  Device pointers. */
+int mpc_b200_tron1_reference_device(mpc_b200_engine *e, int B, const double *d_x0, const double *d_omega_yaw,
+                                    const double *d_velocity_x, double *d_x_ref, void *stream);
+
+/* Closed-loop rollout (BASELINE configs[4]): `steps` control steps of
+ *   reference(x) -> contact schedule(iter0 + s*mpc_step) -> linearise -> condense -> solve -> x <- Ad x + Bd u_0
+ * with the state resident on the device, feet at their nominal offsets under the base, and the
+ * previous step's optimal face (shifted by one horizon step) as warm start.  The plant is the
+ * model (QPSolver::updateState, src/QPSolver.cpp:108-111).  Device pointers:
+ *   d_x [B][13] in/out (initial -> final state), d_omega_yaw/d_velocity_x [B], d_iter0 [B] (<0 standing),
+ *   d_u_traj [B][steps][6] first-step forces (may be NULL), d_uncertified [B] number of steps whose
+ *   solve was not certified (may be NULL), d_iters [B] total solver iterations (may be NULL). */
+int mpc_b200_tron1_rollout_device(mpc_b200_engine *e, int B, int steps, double *d_x, const double *d_omega_yaw,
+                                  const double *d_velocity_x, const int32_t *d_iter0, double *d_u_traj,
+                                  int32_t *d_uncertified, int32_t *d_iters, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Generic condensed-MPC path: the reference class QPSolver (include/QPSolver.h:13-37), any NX/NU/N.

@@ -18,6 +18,7 @@ SYMBOLS = [
     "mpc_b200_tron1_default_params", "mpc_b200_create", "mpc_b200_destroy", "mpc_b200_last_error",
     "mpc_b200_launch_count", "mpc_b200_contact_schedule_device", "mpc_b200_tron1_solve_device",
     "mpc_b200_tron1_solve_host", "mpc_b200_tron1_condense_device",
+    "mpc_b200_tron1_reference_device", "mpc_b200_tron1_rollout_device",
     "mpc_b200_lti_create", "mpc_b200_lti_destroy", "mpc_b200_lti_last_error", "mpc_b200_lti_launch_count",
     "mpc_b200_lti_discretize", "mpc_b200_lti_build_qp", "mpc_b200_qp_solve_dense", "mpc_b200_lti_update_state",
 ]
@@ -31,6 +32,7 @@ class Tron1Params(C.Structure):
         ("gait_dt", C.c_float), ("gait_mpc_step", C.c_int32),
         ("gait_swing_time", C.c_float), ("gait_stance_time", C.c_float),
         ("max_newton", C.c_int32), ("max_admm", C.c_int32), ("tol", C.c_double),
+        ("foot_offset_left", C.c_double * 3), ("foot_offset_right", C.c_double * 3),
     ]
 
 
@@ -69,6 +71,8 @@ def lib():
         L.mpc_b200_tron1_solve_device.argtypes = [vp, ip, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         L.mpc_b200_tron1_solve_host.argtypes = [vp, ip, vp, vp, vp, vp, vp, vp, vp, vp]
         L.mpc_b200_tron1_condense_device.argtypes = [vp, ip, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.mpc_b200_tron1_reference_device.argtypes = [vp, ip, vp, vp, vp, vp, vp]
+        L.mpc_b200_tron1_rollout_device.argtypes = [vp, ip, ip, vp, vp, vp, vp, vp, vp, vp, vp]
         dd = C.c_double
         L.mpc_b200_lti_create.argtypes = [ip, C.POINTER(vp)]
         L.mpc_b200_lti_destroy.argtypes = [vp]
@@ -88,7 +92,7 @@ def default_params(**overrides):
     p = Tron1Params()
     lib().mpc_b200_tron1_default_params(C.byref(p))
     for k, v in overrides.items():
-        if k in ("inertia", "q"):
+        if k in ("inertia", "q", "foot_offset_left", "foot_offset_right"):
             for i, x in enumerate(v):
                 getattr(p, k)[i] = float(x)
         else:

@@ -212,6 +212,90 @@ tron1_solve_kernel(const __grid_constant__ Tron1Const P, int B, const double* __
     }
 }
 
+// ---- mpcQP reference generator for a batch (include/mpcQP.h:74-97) -------------------------------------
+struct GrpThread {   // a single thread acting as a whole group
+    static constexpr int kThreads = 1;
+    __device__ __forceinline__ int tid() const { return 0; }
+    __device__ __forceinline__ int size() const { return 1; }
+    __device__ __forceinline__ void sync() const {}
+};
+__global__ void tron1_reference_kernel(const __grid_constant__ Tron1Const P, int B, int N, const double* __restrict__ x0,
+                                       const double* __restrict__ oy, const double* __restrict__ vx, double* __restrict__ xr) {
+    const int XR = 13 * (N + 1);
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < (size_t)B * XR; idx += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(idx / XR), r = (int)(idx % XR), i = r / 13, c = r % 13;
+        const double* x = x0 + (size_t)b * 13;
+        const double t = (double)i * P.Ts;
+        double v = x[c];
+        if (c == 2) v = x[2] + t * oy[b];
+        else if (c == 3) v = x[3] + t * vx[b];
+        else if (c == 9) v = (i == 0) ? x[9] : vx[b];
+        else if (c == 12) v = -9.8;
+        xr[idx] = v;
+    }
+}
+
+// ---- closed-loop rollout (BASELINE configs[4]): state resident in shared memory for all steps -----------
+template <int N, int IPC>
+struct RollStage {
+    static constexpr int XR = 13 * (N + 1);
+    alignas(16) double xr[IPC * XR];
+    alignas(16) double x[IPC * 14];
+    alignas(16) double feet[IPC * 6];
+};
+
+template <int N, int NC, int WPI, int IPC, int MINB, bool STANDING>
+__global__ void __launch_bounds__(32 * WPI * IPC, MINB)
+tron1_rollout_kernel(const __grid_constant__ Tron1Const P, int B, int steps, double* __restrict__ x,
+                     const double* __restrict__ oy, const double* __restrict__ vx, const int32_t* __restrict__ iter0,
+                     double* __restrict__ u_traj, int32_t* __restrict__ uncert, int32_t* __restrict__ iters_total) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    using Stage = RollStage<N, IPC>;
+    using Work = Tron1Work<N, NC>;
+    Stage& st = *reinterpret_cast<Stage*>(smem_raw);
+    constexpr size_t stage_bytes = (sizeof(Stage) + 15) & ~size_t(15);
+    Work* works = reinterpret_cast<Work*>(smem_raw + stage_bytes);
+    GrpCuda<WPI> g;
+    g.t = threadIdx.x % (32 * WPI);
+    g.gid = threadIdx.x / (32 * WPI);
+    const int b = blockIdx.x * IPC + g.gid;
+    if (b >= B) return;
+    const int it0 = iter0[b];
+    if ((it0 < 0) != STANDING) return;   // the other capacity class handles this instance
+    Work& S = works[g.gid];
+    double* xs = st.x + g.gid * 14;
+    double* fs = st.feet + g.gid * 6;
+    double* xr = st.xr + g.gid * Stage::XR;
+    S.x0 = xs;
+    S.feet = fs;
+    for (int i = g.t; i < 13; i += g.size()) xs[i] = x[(size_t)b * 13 + i];
+    const double oyb = oy[b], vxb = vx[b];
+    g.sync();
+    int bad = 0, tot = 0;
+    for (int s = 0; s < steps; ++s) {
+        if (g.t == 0) nominal_feet(xs, P.foot_off_l, P.foot_off_r, fs);
+        make_reference(xs, oyb, vxb, P.Ts, N, xr, g);
+        for (int k = g.t; k < N; k += g.size()) {
+            int l, r;
+            gait_contact(P, it0 < 0 ? it0 : it0 + (s + k) * P.gait_mpc_step, l, r);
+            S.contact[2 * k] = (int8_t)l;
+            S.contact[2 * k + 1] = (int8_t)r;
+        }
+        g.sync();
+        int its = 0;
+        const int code = solve_instance<Work>(P, S, xr, g, its, s > 0);
+        if (u_traj && g.t < 6) u_traj[((size_t)b * steps + s) * 6 + g.t] = S.u[g.t];
+        bad += code != 0;
+        tot += its;
+        integrate_state<Work>(P, S, xs, g);
+    }
+    for (int i = g.t; i < 13; i += g.size()) x[(size_t)b * 13 + i] = xs[i];
+    if (g.t == 0) {
+        if (uncert) uncert[b] = bad;
+        if (iters_total) iters_total[b] = tot;
+    }
+}
+
 // ---- parity dump: one warp per instance -------------------------------------------------------------
 template <int N>
 __global__ void __launch_bounds__(32)
@@ -356,6 +440,18 @@ static int dispatch_solve(mpc_b200_engine* e, int B, const double* x0, const dou
         case 20: return launch_solve<20, 2, 2, 2, 2, 2>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s);
         default: return set_err(e, MPC_B200_EINVAL, "unsupported horizon");
     }
+}
+
+template <int N, int NC, int WPI, int IPC, int MINB, bool STANDING>
+static int launch_rollout_one(mpc_b200_engine* e, int B, int steps, double* x, const double* oy, const double* vx,
+                              const int32_t* iter0, double* u_traj, int32_t* uncert, int32_t* iters, cudaStream_t s) {
+    auto k = tron1_rollout_kernel<N, NC, WPI, IPC, MINB, STANDING>;
+    const size_t smem = ((sizeof(RollStage<N, IPC>) + 15) & ~size_t(15)) + sizeof(Tron1Work<N, NC>) * IPC;
+    CU(e, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<(B + IPC - 1) / IPC, 32 * WPI * IPC, smem, s>>>(e->C, B, steps, x, oy, vx, iter0, u_traj, uncert, iters);
+    CU(e, cudaGetLastError());
+    e->launches++;
+    return MPC_B200_OK;
 }
 
 extern "C" {
@@ -504,6 +600,40 @@ int mpc_b200_tron1_condense_device(mpc_b200_engine* e, int B, const double* d_x0
     CU(e, cudaGetLastError());
     e->launches++;
     return MPC_B200_OK;
+}
+
+int mpc_b200_tron1_reference_device(mpc_b200_engine* e, int B, const double* d_x0, const double* d_omega_yaw,
+                                    const double* d_velocity_x, double* d_x_ref, void* stream) {
+    if (!e || !d_x0 || !d_omega_yaw || !d_velocity_x || !d_x_ref || B < 1) return set_err(e, MPC_B200_EINVAL, "reference: bad argument");
+    CU(e, cudaSetDevice(e->device));
+    const size_t total = (size_t)B * 13 * (e->N + 1);
+    int grid = (int)((total + 255) / 256);
+    if (grid > e->num_sms * 16) grid = e->num_sms * 16;
+    tron1_reference_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(e->C, B, e->N, d_x0, d_omega_yaw, d_velocity_x, d_x_ref);
+    CU(e, cudaGetLastError());
+    e->launches++;
+    return MPC_B200_OK;
+}
+
+int mpc_b200_tron1_rollout_device(mpc_b200_engine* e, int B, int steps, double* d_x, const double* d_omega_yaw,
+                                  const double* d_velocity_x, const int32_t* d_iter0, double* d_u_traj,
+                                  int32_t* d_uncertified, int32_t* d_iters, void* stream) {
+    if (!e || !d_x || !d_omega_yaw || !d_velocity_x || !d_iter0 || B < 1 || steps < 1)
+        return set_err(e, MPC_B200_EINVAL, "rollout: bad argument");
+    if (e->C.per_step_feet) return set_err(e, MPC_B200_EINVAL, "rollout: per_step_feet engines are not supported (nominal feet)");
+    CU(e, cudaSetDevice(e->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc;
+    if (e->N == 10) {
+        rc = launch_rollout_one<10, 30, 1, 4, 4, false>(e, B, steps, d_x, d_omega_yaw, d_velocity_x, d_iter0, d_u_traj, d_uncertified, d_iters, s);
+        if (rc) return rc;
+        return launch_rollout_one<10, 60, 1, 4, 1, true>(e, B, steps, d_x, d_omega_yaw, d_velocity_x, d_iter0, d_u_traj, d_uncertified, d_iters, s);
+    } else if (e->N == 20) {
+        rc = launch_rollout_one<20, 60, 2, 2, 2, false>(e, B, steps, d_x, d_omega_yaw, d_velocity_x, d_iter0, d_u_traj, d_uncertified, d_iters, s);
+        if (rc) return rc;
+        return launch_rollout_one<20, 120, 2, 2, 1, true>(e, B, steps, d_x, d_omega_yaw, d_velocity_x, d_iter0, d_u_traj, d_uncertified, d_iters, s);
+    }
+    return set_err(e, MPC_B200_EINVAL, "unsupported horizon");
 }
 
 int mpc_b200_measure_fp64_peak(int device, double* tflops) {

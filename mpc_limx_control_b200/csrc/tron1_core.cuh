@@ -48,6 +48,7 @@ struct Tron1Const {
     int max_newton, max_admm;
     float gait_dt, gait_swing, gait_stance;
     int gait_mpc_step;
+    double foot_off_l[3], foot_off_r[3];   // nominal base->foot offsets (include/MPCParam.h:64-73)
 };
 
 enum { ST_SOLVED = 0, ST_MAXITER = 1, ST_FAILED = 2 };
@@ -442,19 +443,24 @@ __device__ __noinline__ bool cholesky_regs(WK& S, const G& g) {
 #pragma unroll
     for (int j = 0; j < NC; ++j) a[j] = (row && j < n && (j <= t || t == n)) ? mine[j] : 0.0;
     bool ok = true;
+    // `piv` carries the next pivot candidate: after column k every thread forms a[k+1] - l*l from its own
+    // registers; only the owner of row k+1 holds the true value, and it is the one the shuffle reads.
+    // This keeps the shared-memory round trip (STS -> sync -> LDS) off the pivot-to-pivot critical path.
+    double piv = a[0];
 #pragma unroll
     for (int k = 0; k < NC; ++k) {
         if (k < n) {
             double d;
-            if (G::kThreads == 32) d = __shfl_sync(0xffffffffu, a[k], k);
+            if (G::kThreads == 32) d = __shfl_sync(0xffffffffu, piv, k);
             else {
-                if (t == k) S.w[k] = a[k];
+                if (t == k) S.w[k] = piv;
                 g.sync();
                 d = S.w[k];
             }
             if (!(d > 0.0)) { ok = false; d = 1.0; }
             const double rs = rsqrt(d);
             const double l = a[k] * rs;
+            if (k + 1 < NC) piv = a[k + 1 < NC ? k + 1 : k] - l * l;
             if (row && t > k) A[MPC_PK(t, k)] = l;
             if (t == k) S.dinv[k] = rs;
             g.sync();
@@ -732,14 +738,28 @@ MPC_HD void adopt_predicted_face(WK& S, const G& g) {
 
 // ---- setup shared by solve and dump: inputs must already be in S.x0 / S.feet / S.contact ---------
 template <class WK, class G>
-MPC_HD void setup_instance(const Tron1Const& P, WK& S, const double* xref, const G& g) {
+MPC_HD void setup_instance(const Tron1Const& P, WK& S, const double* xref, const G& g, bool warm = false) {
     [[maybe_unused]] constexpr int N = WK::N;
     if (g.tid() == 0) {
         int c = 0;
         for (int s = 0; s < 2 * N; ++s) { S.cidx[s] = (int16_t)c; c += S.contact[s] ? 1 : 0; }
         S.nc = 3 * c;
     }
-    for (int s = g.tid(); s < 2 * N; s += g.size()) { S.ax[s] = 0; S.ay[s] = 0; S.zt[s] = 0; }
+    if (!warm) {
+        for (int s = g.tid(); s < 2 * N; s += g.size()) { S.ax[s] = 0; S.ay[s] = 0; S.zt[s] = 0; }
+    } else {
+        // warm start (closed-loop rollout): the optimal face of the previous control step, shifted by one
+        // horizon step, is the first guess; the new last step starts in the interior
+        g.sync();
+        for (int s = g.tid(); s < 2 * N; s += g.size()) {
+            const bool in = s + 2 < 2 * N;
+            S.nax[s] = in ? S.ax[s + 2] : (int8_t)0;
+            S.nay[s] = in ? S.ay[s + 2] : (int8_t)0;
+            S.nzt[s] = in ? S.zt[s + 2] : (int8_t)0;
+        }
+        g.sync();
+        for (int s = g.tid(); s < 2 * N; s += g.size()) { S.ax[s] = S.nax[s]; S.ay[s] = S.nay[s]; S.zt[s] = S.nzt[s]; }
+    }
     for (int k = g.tid(); k < N; k += g.size()) model_step<WK>(P, S, xref, k);
     g.sync();
     MPC_TICK(S, g, 0);
@@ -754,9 +774,9 @@ MPC_HD void setup_instance(const Tron1Const& P, WK& S, const double* xref, const
 // ---- full QP solve of one instance.  On exit S.u holds the forces (full layout). -----------------
 // iters = face solves + ADMM iterations.
 template <class WK, class G>
-MPC_HD int solve_instance(const Tron1Const& P, WK& S, const double* xref, const G& g, int& iters) {
+MPC_HD int solve_instance(const Tron1Const& P, WK& S, const double* xref, const G& g, int& iters, bool warm = false) {
     [[maybe_unused]] constexpr int N = WK::N;
-    setup_instance<WK>(P, S, xref, g);
+    setup_instance<WK>(P, S, xref, g, warm);
     iters = 0;
     if (S.nc == 0) {
         for (int i = g.tid(); i < 6 * N; i += g.size()) S.u[i] = 0.0;
@@ -842,6 +862,63 @@ MPC_HD int solve_instance(const Tron1Const& P, WK& S, const double* xref, const 
         for (int c = 0; c < 3; ++c) S.u[3 * s + c] = S.contact[s] ? S.z[3 * S.cidx[s] + c] : 0.0;
     g.sync();
     return ST_MAXITER;
+}
+
+// ---- reference trajectory of mpcQP (reference include/mpcQP.h:74-97): x_ref 13 x (N+1), step-major ------
+template <class G>
+MPC_HD void make_reference(const double* x0, double omega_yaw, double velocity_x, double Ts, int N, double* xr, const G& g) {
+    for (int idx = g.tid(); idx < 13 * (N + 1); idx += g.size()) {
+        const int i = idx / 13, c = idx % 13;
+        const double t = (double)i * Ts;
+        double v = x0[c];
+        if (c == 2) v = x0[2] + t * omega_yaw;
+        else if (c == 3) v = x0[3] + t * velocity_x;
+        else if (c == 9) v = (i == 0) ? x0[9] : velocity_x;
+        else if (c == 12) v = -9.8;
+        xr[idx] = v;
+    }
+}
+
+// nominal foot positions under the base: p_xy + Rz(yaw) offset_xy, on the ground (z = 0)
+// (offsets: reference include/MPCParam.h:64-73; the same rule synth.py uses without the random term)
+MPC_HD void nominal_feet(const double* x, const double* off_l, const double* off_r, double* feet) {
+    double s, c;
+    sincos(x[2], &s, &c);
+    feet[0] = x[3] + c * off_l[0] - s * off_l[1];
+    feet[1] = x[4] + s * off_l[0] + c * off_l[1];
+    feet[2] = 0.0;
+    feet[3] = x[3] + c * off_r[0] - s * off_r[1];
+    feet[4] = x[4] + s * off_r[0] + c * off_r[1];
+    feet[5] = 0.0;
+}
+
+// ---- plant update of the closed loop: x <- Ad x + Bd u0 (reference src/QPSolver.cpp:108-111) with the
+// step-0 model already in S (closed-form ZOH).  u0 = S.u[0..5].  One thread does the 12 updates.
+template <class WK, class G>
+MPC_HD void integrate_state(const Tron1Const& P, WK& S, double* x, const G& g) {
+    if (g.tid() == 0) {
+        const double Ts = P.Ts;
+        const double* W0 = S.W;
+        const double* u = S.u;
+        double tau[3], phi[3];
+        for (int i = 0; i < 3; ++i) {
+            tau[i] = W0[i * 3] * u[0] + W0[i * 3 + 1] * u[1] + W0[i * 3 + 2] * u[2]
+                   + W0[9 + i * 3] * u[3] + W0[9 + i * 3 + 1] * u[4] + W0[9 + i * 3 + 2] * u[5];
+            phi[i] = (u[i] + u[3 + i]) * P.inv_m;
+        }
+        phi[2] += x[12];   // gravity state enters v_z_dot
+        const double cz = S.cs[0], sz = S.cs[1];
+        const double a0 = x[6] + 0.5 * Ts * tau[0], a1 = x[7] + 0.5 * Ts * tau[1], a2 = x[8] + 0.5 * Ts * tau[2];
+        x[0] += Ts * (cz * a0 + sz * a1);
+        x[1] += Ts * (-sz * a0 + cz * a1);
+        x[2] += Ts * a2;
+        for (int i = 0; i < 3; ++i) {
+            x[3 + i] += Ts * (x[9 + i] + 0.5 * Ts * phi[i]);
+            x[6 + i] += Ts * tau[i];
+            x[9 + i] += Ts * phi[i];
+        }
+    }
+    g.sync();
 }
 
 // ---- parity dump helpers (closed-form prediction matrices, column-major like Eigen) --------------

@@ -32,6 +32,10 @@ inline void tron1_default_params(mpc_b200_tron1_params& p) {
     p.max_newton = 12;
     p.max_admm = 2000;
     p.tol = 1e-9;
+    // reference include/MPCParam.h:13-38,64-73
+    const double ox = 0.05556 - 0.077 - 0.15 + 0.145 + 0.0, oz = -0.2602 + 0.0 - 0.25981 - 0.2598 - 0.032;
+    p.foot_offset_left[0] = ox; p.foot_offset_left[1] = -0.105 - 0.0205 - (-0.0205) + 0.0 + 0.0; p.foot_offset_left[2] = oz;
+    p.foot_offset_right[0] = ox; p.foot_offset_right[1] = 0.105 + 0.0205 + (-0.0205) + 0.0 + 0.0; p.foot_offset_right[2] = oz;
 }
 
 // returns non-zero on invalid parameters
@@ -66,6 +70,7 @@ inline int make_tron1_const(const mpc_b200_tron1_params& p, Tron1Const& c) {
     c.gait_swing = p.gait_swing_time;
     c.gait_stance = p.gait_stance_time;
     c.gait_mpc_step = p.gait_mpc_step;
+    for (int k = 0; k < 3; ++k) { c.foot_off_l[k] = p.foot_offset_left[k]; c.foot_off_r[k] = p.foot_offset_right[k]; }
     return 0;
 }
 

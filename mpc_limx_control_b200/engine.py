@@ -106,6 +106,31 @@ class Engine:
             out["B_aug"] = Bm.cpu().numpy().transpose(0, 2, 1)
         return out
 
+    def reference(self, x0, omega_yaw, velocity_x):
+        """mpcQP's reference generator for a batch (device tensors): x_ref [B,N+1,13]."""
+        B = x0.shape[0]
+        self._check_dev(x0, torch.float64, B * 13, "x0")
+        self._check_dev(omega_yaw, torch.float64, B, "omega_yaw")
+        self._check_dev(velocity_x, torch.float64, B, "velocity_x")
+        xr = torch.empty((B, self.N + 1, 13), dtype=torch.float64, device=self.tdev)
+        _capi.check(self.lib.mpc_b200_tron1_reference_device(self.h, B, _ptr(x0), _ptr(omega_yaw), _ptr(velocity_x), _ptr(xr),
+                                                             self._stream()), self.h)
+        return xr
+
+    def rollout(self, x, omega_yaw, velocity_x, it0, steps, want_traj=False):
+        """Closed-loop rollout; x [B,13] is updated in place. Returns (u_traj or None, uncertified[B], iters[B])."""
+        B = x.shape[0]
+        self._check_dev(x, torch.float64, B * 13, "x")
+        self._check_dev(omega_yaw, torch.float64, B, "omega_yaw")
+        self._check_dev(velocity_x, torch.float64, B, "velocity_x")
+        self._check_dev(it0, torch.int32, B, "iter0")
+        traj = torch.empty((B, steps, 6), dtype=torch.float64, device=self.tdev) if want_traj else None
+        bad = torch.zeros((B,), dtype=torch.int32, device=self.tdev)
+        its = torch.zeros((B,), dtype=torch.int32, device=self.tdev)
+        _capi.check(self.lib.mpc_b200_tron1_rollout_device(self.h, B, int(steps), _ptr(x), _ptr(omega_yaw), _ptr(velocity_x),
+                                                           _ptr(it0), _ptr(traj), _ptr(bad), _ptr(its), self._stream()), self.h)
+        return traj, bad, its
+
     # -- host-buffer entry point (the reference-facing call: H2D + solve + D2H inside) -------------
     def solve_host(self, x0, x_ref, feet, contact=None, it=None, forces=None, status=None, iters=None):
         """numpy arrays or CPU torch tensors (pinned recommended) in and out."""

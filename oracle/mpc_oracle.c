@@ -846,6 +846,31 @@ int orc_tron1_solve(const orc_tron1_params *p, int N, const double *x0, const do
     return st;
 }
 
+int orc_tron1_rollout(const orc_tron1_params *p, const orc_gait_params *g, int N, int steps, double *x,
+                      double omega_yaw, double velocity_x, int iter0, const double off_l[3],
+                      const double off_r[3], double *u_traj) {
+    int bad = 0;
+    double *xr = dalloc((size_t)13 * (N + 1)), *U = dalloc((size_t)6 * N);
+    uint8_t *contact = (uint8_t *)calloc((size_t)2 * N, 1);
+    orc_tron1_params q = *p;
+    q.per_step_feet = 0;
+    for (int s = 0; s < steps; ++s) {
+        double c = cos(x[2]), sn = sin(x[2]), feet[6], Ac[169], Bc[78], Ad[169], Bd[78];
+        feet[0] = x[3] + c * off_l[0] - sn * off_l[1]; feet[1] = x[4] + sn * off_l[0] + c * off_l[1]; feet[2] = 0.0;
+        feet[3] = x[3] + c * off_r[0] - sn * off_r[1]; feet[4] = x[4] + sn * off_r[0] + c * off_r[1]; feet[5] = 0.0;
+        orc_tron1_reference(x, N, q.Ts, omega_yaw, velocity_x, xr);
+        orc_contact_schedule(g, iter0 < 0 ? iter0 : iter0 + s * g->mpc_step, N, contact);
+        int it = 0;
+        if (orc_tron1_solve(&q, N, x, xr, feet, contact, U, &it)) ++bad;
+        if (u_traj) memcpy(u_traj + (size_t)6 * s, U, sizeof(double) * 6);
+        orc_tron1_model(&q, x[2], x + 3, feet, Ac, Bc);
+        orc_discretize(13, 6, Ac, Bc, q.Ts, Ad, Bd);
+        orc_update_state(13, 6, Ad, Bd, x, U);
+    }
+    free(xr); free(U); free(contact);
+    return bad;
+}
+
 typedef struct {
     const orc_tron1_params *p;
     int N, B, tid, nthreads;

@@ -135,6 +135,15 @@ int orc_tron1_solve_batch(const orc_tron1_params *p, int N, int B, const double 
                           const double *feet, const uint8_t *contact, double *forces,
                           int32_t *status, int32_t *iters, int nthreads);
 
+/* closed-loop rollout of ONE instance (BASELINE configs[4]): per control step s
+ *   feet = nominal offsets under the base (z = 0), x_ref = orc_tron1_reference(x), contact schedule at
+ *   iter0 + s*mpc_step (iter0 < 0: standing), solve (cold-start active set), x <- Ad x + Bd u_0
+ *   (src/QPSolver.cpp:108-111) with Ad, Bd = orc_discretize of the model at x.
+ * x[13] in/out, u_traj[steps][6] (may be NULL). returns the number of steps whose QP did not solve. */
+int orc_tron1_rollout(const orc_tron1_params *p, const orc_gait_params *g, int N, int steps, double *x,
+                      double omega_yaw, double velocity_x, int iter0, const double off_l[3],
+                      const double off_r[3], double *u_traj);
+
 #ifdef __cplusplus
 }
 #endif

@@ -75,7 +75,46 @@ static void run_dump(const Tron1Const& P, const double* x0, const double* xref, 
     delete S;
 }
 
+template <int N, int NC>
+static int run_rollout(const Tron1Const& P, int steps, double* x, double oy, double vx, int it0, double* u_traj, int* iters) {
+    using Work = Tron1Work<N, NC>;
+    auto* S = new Work();
+    double feet[6], xr[13 * (N + 1)];
+    S->x0 = x;
+    S->feet = feet;
+    GrpSerial g;
+    int bad = 0, tot = 0;
+    for (int s = 0; s < steps; ++s) {
+        nominal_feet(x, P.foot_off_l, P.foot_off_r, feet);
+        make_reference(x, oy, vx, P.Ts, N, xr, g);
+        for (int k = 0; k < N; ++k) {
+            int l, r;
+            gait_contact(P, it0 < 0 ? it0 : it0 + (s + k) * P.gait_mpc_step, l, r);
+            S->contact[2 * k] = (int8_t)l;
+            S->contact[2 * k + 1] = (int8_t)r;
+        }
+        int its = 0;
+        int code = solve_instance<Work>(P, *S, xr, g, its, s > 0);
+        if (u_traj) std::memcpy(u_traj + 6 * s, S->u, sizeof(double) * 6);
+        bad += code != 0;
+        tot += its;
+        integrate_state<Work>(P, *S, x, g);
+    }
+    if (iters) *iters = tot;
+    delete S;
+    return bad;
+}
+
 extern "C" {
+
+int emul_tron1_rollout(const mpc_b200_tron1_params* prm, int N, int steps, double* x, double oy, double vx, int it0,
+                       double* u_traj, int* iters) {
+    Tron1Const P;
+    if (make_tron1_const(*prm, P)) return -1;
+    if (N != 10) return -2;
+    return it0 < 0 ? run_rollout<10, 60>(P, steps, x, oy, vx, it0, u_traj, iters)
+                   : run_rollout<10, 30>(P, steps, x, oy, vx, it0, u_traj, iters);
+}
 
 int emul_tron1_solve(const mpc_b200_tron1_params* prm, int N, const double* x0, const double* xref,
                      const double* feet, const uint8_t* contact, double* forces, int* iters) {

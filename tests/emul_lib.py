@@ -36,6 +36,9 @@ def default_params(**kw):
     p.ltv = 1; p.per_step_feet = 0
     p.gait_dt = 0.001; p.gait_mpc_step = 5; p.gait_swing_time = 0.5; p.gait_stance_time = 0.5
     p.max_newton = 12; p.max_admm = 2000; p.tol = 1e-9
+    ox = 0.05556 - 0.077 - 0.15 + 0.145 + 0.0; oz = -0.2602 + 0.0 - 0.25981 - 0.2598 - 0.032
+    for i, v in enumerate([ox, -0.105 - 0.0205 - (-0.0205), oz]): p.foot_offset_left[i] = v
+    for i, v in enumerate([ox, 0.105 + 0.0205 + (-0.0205), oz]): p.foot_offset_right[i] = v
     for k, v in kw.items():
         if k in ("inertia", "q"):
             for i, x in enumerate(np.asarray(v, float).reshape(-1)): getattr(p, k)[i] = x
@@ -65,6 +68,14 @@ def dump(p, N, x0, x_ref, feet):
                                A.ctypes.data_as(_dp), Bm.ctypes.data_as(_dp))
     assert rc == 0
     return dict(H=H, f=f, A_aug=A, B_aug=Bm)
+
+
+def rollout(p, N, steps, x, omega_yaw, velocity_x, iter0):
+    x = np.array(x, dtype=np.float64)
+    U = np.zeros((steps, 6)); it = C.c_int(0)
+    bad = lib().emul_tron1_rollout(C.byref(p), N, int(steps), x.ctypes.data_as(_dp), C.c_double(omega_yaw),
+                                   C.c_double(velocity_x), int(iter0), U.ctypes.data_as(_dp), C.byref(it))
+    return x, U, bad, it.value
 
 
 def gait_contact(p, it, N):

@@ -191,3 +191,13 @@ def tron1_solve_batch(p, N, x0, x_ref, feet, contact, nthreads=1):
                                 _p(forces), status.ctypes.data_as(C.POINTER(C.c_int32)),
                                 iters.ctypes.data_as(C.POINTER(C.c_int32)), int(nthreads))
     return forces, status, iters
+
+
+def tron1_rollout(p, N, steps, x, omega_yaw, velocity_x, iter0, off_l, off_r, g=None):
+    g = g or gait_defaults()
+    x = np.array(x, dtype=np.float64)
+    off_l = np.ascontiguousarray(off_l, dtype=np.float64); off_r = np.ascontiguousarray(off_r, dtype=np.float64)
+    U = np.zeros((steps, 6))
+    bad = lib().orc_tron1_rollout(C.byref(p), C.byref(g), N, int(steps), _p(x), C.c_double(omega_yaw), C.c_double(velocity_x),
+                                  int(iter0), _p(off_l), _p(off_r), _p(U))
+    return x, U, bad

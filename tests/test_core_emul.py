@@ -101,3 +101,18 @@ def test_gait_matches_golden(golden):
         c = E.gait_contact(pe, int(it), 1)
         assert c[0, 0] == 1 - l and c[0, 1] == 1 - r
     assert np.all(E.gait_contact(pe, -1, 5) == 1)   # standing
+
+
+def test_rollout_vs_oracle():
+    """closed loop (BASELINE configs[4] shape, short): emulated device source vs the oracle loop"""
+    N, Ts, steps = 10, 0.005, 40
+    d = synth.tron1_batch(1004, 4, N, Ts)
+    pe = E.default_params(Ts=Ts); po = O.tron1_defaults(Ts=Ts)
+    offl = list(pe.foot_offset_left); offr = list(pe.foot_offset_right)
+    for b, it0 in zip(range(4), (int(d["iter"][0]), 480, -1, int(d["iter"][3]))):   # 480: the gait switches mid-rollout
+        xe, Ue, bad_e, its = E.rollout(pe, N, steps, d["x0"][b], d["omega_yaw"][b], d["velocity_x"][b], it0)
+        xo, Uo, bad_o = O.tron1_rollout(po, N, steps, d["x0"][b], d["omega_yaw"][b], d["velocity_x"][b], it0, offl, offr)
+        assert bad_e == 0 and bad_o == 0
+        assert np.abs(Ue - Uo).max() / max(1.0, np.abs(Uo).max()) < 1e-6
+        assert np.abs(xe - xo).max() < 1e-8
+        assert its >= steps

@@ -227,3 +227,62 @@ def test_fp64_peak_measurement(torch_cuda):
     from mpc_limx_control_b200.engine import measure_fp64_peak
     tf = measure_fp64_peak(0)
     assert 5.0 < tf < 80.0, tf
+
+
+def test_reference_generator(torch_cuda):
+    """mpcQP's reference generator on the device == synth's numpy restatement of include/mpcQP.h:74-97"""
+    torch = torch_cuda
+    for N in (10, 20):
+        d = synth.tron1_batch(12, 257, N, 0.005)
+        eng = make_engine(N, 257)
+        xr = eng.reference(torch.from_numpy(d["x0"]).cuda(), torch.from_numpy(d["omega_yaw"]).cuda(),
+                           torch.from_numpy(d["velocity_x"]).cuda())
+        torch.cuda.synchronize()
+        assert np.abs(xr.cpu().numpy() - d["x_ref"]).max() < 1e-14    # FMA contraction: last-bit differences only
+        eng.close()
+
+
+def test_rollout_vs_oracle(torch_cuda):
+    """closed-loop rollout (BASELINE configs[4] shape): device loop vs the oracle loop, incl. a standing
+    instance (large capacity class) and one whose gait switches support foot mid-rollout"""
+    torch = torch_cuda
+    N, Ts, steps, B = 10, 0.005, 40, 9
+    d = synth.tron1_batch(1004, B, N, Ts)
+    it0 = d["iter"].copy(); it0[1] = 480; it0[2] = -1; it0[5] = 995
+    eng = make_engine(N, B, Ts=Ts)
+    x = torch.from_numpy(d["x0"].copy()).cuda()
+    traj, bad, its = eng.rollout(x, torch.from_numpy(d["omega_yaw"]).cuda(), torch.from_numpy(d["velocity_x"]).cuda(),
+                                 torch.from_numpy(it0).cuda(), steps, want_traj=True)
+    torch.cuda.synchronize()
+    assert int(bad.sum()) == 0 and int(its.min()) >= steps
+    po = O.tron1_defaults(Ts=Ts)
+    offl = list(eng.params.foot_offset_left); offr = list(eng.params.foot_offset_right)
+    X = x.cpu().numpy(); U = traj.cpu().numpy()
+    for b in range(B):
+        xo, Uo, bo = O.tron1_rollout(po, N, steps, d["x0"][b], d["omega_yaw"][b], d["velocity_x"][b], int(it0[b]), offl, offr)
+        assert bo == 0
+        assert np.abs(U[b] - Uo).max() / max(1.0, np.abs(Uo).max()) < 1e-4
+        assert np.abs(X[b] - xo).max() < 1e-6
+    eng.close()
+
+
+def test_rollout_properties_larger(torch_cuda):
+    torch = torch_cuda
+    N, Ts, steps, B = 10, 0.005, 200, 1024
+    d = synth.tron1_batch(1004, B, N, Ts)
+    eng = make_engine(N, B, Ts=Ts)
+    x = torch.from_numpy(d["x0"].copy()).cuda(); x2 = x.clone()
+    args = (torch.from_numpy(d["omega_yaw"]).cuda(), torch.from_numpy(d["velocity_x"]).cuda(), torch.from_numpy(d["iter"]).cuda())
+    traj, bad, its = eng.rollout(x, *args, steps, want_traj=True)
+    # two half rollouts == one full rollout (state fully carried; the clock advances by steps*mpc_step)
+    _, bad2a, _ = eng.rollout(x2, *args, steps // 2)
+    it_half = (torch.from_numpy(d["iter"]) + (steps // 2) * 5).to(torch.int32).cuda()
+    _, bad2b, _ = eng.rollout(x2, args[0], args[1], it_half, steps // 2)
+    torch.cuda.synchronize()
+    assert int(bad.sum()) == 0 and int(bad2a.sum()) == 0 and int(bad2b.sum()) == 0
+    X = x.cpu().numpy(); U = traj.cpu().numpy()
+    assert np.isfinite(X).all() and np.isfinite(U).all()
+    assert np.abs(X - x2.cpu().numpy()).max() < 1e-9
+    assert (U[..., 2] >= -1e-12).all() and (U[..., 5] >= -1e-12).all()
+    assert (np.abs(U[..., 0]) <= 0.5 * U[..., 2] + 1e-9).all()
+    eng.close()
