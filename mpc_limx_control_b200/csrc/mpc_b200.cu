@@ -436,7 +436,7 @@ static int dispatch_solve(mpc_b200_engine* e, int B, const double* x0, const dou
                           int32_t* iters, cudaStream_t s) {
     if (B > e->max_batch) return set_err(e, MPC_B200_ECAPACITY, "solve: B > max_batch");
     switch (e->N) {
-        case 10: return launch_solve<10, 1, 4, 4, 1, 4>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s);
+        case 10: return launch_solve<10, 1, 4, 4, 2, 2>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s);
         case 20: return launch_solve<20, 2, 2, 2, 2, 2>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s);
         default: return set_err(e, MPC_B200_EINVAL, "unsupported horizon");
     }
@@ -627,7 +627,7 @@ int mpc_b200_tron1_rollout_device(mpc_b200_engine* e, int B, int steps, double* 
     if (e->N == 10) {
         rc = launch_rollout_one<10, 30, 1, 4, 4, false>(e, B, steps, d_x, d_omega_yaw, d_velocity_x, d_iter0, d_u_traj, d_uncertified, d_iters, s);
         if (rc) return rc;
-        return launch_rollout_one<10, 60, 1, 4, 1, true>(e, B, steps, d_x, d_omega_yaw, d_velocity_x, d_iter0, d_u_traj, d_uncertified, d_iters, s);
+        return launch_rollout_one<10, 60, 2, 2, 1, true>(e, B, steps, d_x, d_omega_yaw, d_velocity_x, d_iter0, d_u_traj, d_uncertified, d_iters, s);
     } else if (e->N == 20) {
         rc = launch_rollout_one<20, 60, 2, 2, 2, false>(e, B, steps, d_x, d_omega_yaw, d_velocity_x, d_iter0, d_u_traj, d_uncertified, d_iters, s);
         if (rc) return rc;

@@ -447,22 +447,25 @@ __device__ __noinline__ bool cholesky_regs(WK& S, const G& g) {
     // registers; only the owner of row k+1 holds the true value, and it is the one the shuffle reads.
     // This keeps the shared-memory round trip (STS -> sync -> LDS) off the pivot-to-pivot critical path.
     double piv = a[0];
+    if (G::kThreads != 32) {   // multi-warp groups exchange the pivot through shared memory
+        if (t == 0) S.w[0] = piv;
+        g.sync();
+    }
 #pragma unroll
     for (int k = 0; k < NC; ++k) {
         if (k < n) {
             double d;
             if (G::kThreads == 32) d = __shfl_sync(0xffffffffu, piv, k);
-            else {
-                if (t == k) S.w[k] = piv;
-                g.sync();
-                d = S.w[k];
-            }
+            else d = S.w[k];
             if (!(d > 0.0)) { ok = false; d = 1.0; }
             const double rs = rsqrt(d);
             const double l = a[k] * rs;
             if (k + 1 < NC) piv = a[k + 1 < NC ? k + 1 : k] - l * l;
             if (row && t > k) A[MPC_PK(t, k)] = l;
             if (t == k) S.dinv[k] = rs;
+            // the owner of row k+1 publishes the next pivot together with its column entry: one
+            // barrier per column covers both
+            if (G::kThreads != 32 && t == k + 1 && k + 1 < NC) S.w[k + 1] = piv;
             g.sync();
             const double* col = A;   // column k entries L[j][k] live at PK(j,k)
 #pragma unroll
@@ -474,23 +477,34 @@ __device__ __noinline__ bool cholesky_regs(WK& S, const G& g) {
     return ok;
 }
 
-// backward solve L' x = y for one-warp groups: y_i lives in lane i, x_k is broadcast by shuffle
+// backward solve L' x = y with y_i held by thread i; x_k is broadcast by shuffle (one warp) or through
+// shared memory (one barrier per step)
 template <class WK, class G>
 __device__ __noinline__ void backward_regs(WK& S, const G& g) {
     constexpr int NC = WK::NC;
     const int n = S.nc, t = g.tid();
     const double* A = S.A;
     double y = (t < n) ? A[MPC_PK(n, t)] : 0.0;
+    if (G::kThreads == 32) {
 #pragma unroll
-    for (int k = NC - 1; k >= 0; --k) {
-        if (k < n) {
-            const double xk = __shfl_sync(0xffffffffu, y, k) * S.dinv[k];
-            if (t < k) y -= A[MPC_PK(k, t)] * xk;
-            if (t == k) y = xk;
+        for (int k = NC - 1; k >= 0; --k) {
+            if (k < n) {
+                const double xk = __shfl_sync(0xffffffffu, y, k) * S.dinv[k];
+                if (t < k) y -= A[MPC_PK(k, t)] * xk;
+                if (t == k) y = xk;
+            }
         }
+        if (t < n) S.w[t] = y;
+        g.sync();
+    } else {
+        g.sync();   // S.w is free (the factorisation no longer reads its pivots)
+        for (int k = n - 1; k >= 0; --k) {
+            if (t == k) { y *= S.dinv[k]; S.w[k] = y; }
+            g.sync();
+            if (t < k) y -= A[MPC_PK(k, t)] * S.w[k];
+        }
+        g.sync();
     }
-    if (t < n) S.w[t] = y;
-    g.sync();
 }
 #endif
 
@@ -631,8 +645,7 @@ MPC_HD bool face_solve(const Tron1Const& P, WK& S, const G& g) {
     if constexpr (G::kThreads >= WK::NC + 1 && WK::NC <= 60) {
         ok = cholesky_regs<WK>(S, g);
         MPC_TICK(S, g, 7);
-        if constexpr (G::kThreads == 32) backward_regs<WK>(S, g);
-        else backward_solve<WK>(S, g);
+        backward_regs<WK>(S, g);
     } else
 #endif
     {
