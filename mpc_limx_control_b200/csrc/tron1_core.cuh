@@ -477,6 +477,26 @@ __device__ __noinline__ bool cholesky_regs(WK& S, const G& g) {
     return ok;
 }
 
+// forward solve L y = b (b in S.w) for one-warp groups; y goes to row nc of the packed factor, which is
+// where backward_regs expects it.  Column access A[PK(i,k)] over i is bank-conflict free.
+template <class WK, class G>
+__device__ __noinline__ void forward_regs(WK& S, const G& g) {
+    constexpr int NC = WK::NC;
+    const int n = S.nc, t = g.tid();
+    double* A = S.A;
+    double y = (t < n) ? S.w[t] : 0.0;
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+        if (k < n) {
+            const double yk = __shfl_sync(0xffffffffu, y, k) * S.dinv[k];
+            if (t > k && t < n) y -= A[MPC_PK(t, k)] * yk;
+            if (t == k) y = yk;
+        }
+    }
+    if (t < n) A[MPC_PK(n, t)] = y;
+    g.sync();
+}
+
 // backward solve L' x = y with y_i held by thread i; x_k is broadcast by shuffle (one warp) or through
 // shared memory (one barrier per step)
 template <class WK, class G>
@@ -830,7 +850,13 @@ MPC_HD int solve_instance(const Tron1Const& P, WK& S, const double* xref, const 
             build_hessian<WK>(P, S, rho, false, g);
             for (int i = g.tid(); i <= n; i += g.size()) S.A[MPC_PK(n, i)] = (i == n) ? 1.0 : 0.0;
             g.sync();
-            if (!cholesky_with_rhs<WK>(S, g)) return ST_FAILED;
+            bool okf;
+#if defined(__CUDA_ARCH__)
+            if constexpr (G::kThreads >= WK::NC + 1 && WK::NC <= 60) okf = cholesky_regs<WK>(S, g);
+            else
+#endif
+                okf = cholesky_with_rhs<WK>(S, g);
+            if (!okf) return ST_FAILED;
             have_factor = true;
         }
         for (int s = g.tid(); s < 2 * N; s += g.size()) {
@@ -839,10 +865,18 @@ MPC_HD int solve_instance(const Tron1Const& P, WK& S, const double* xref, const 
             for (int c = 0; c < 3; ++c) S.w[b + c] = rho * (S.z[b + c] - S.y[b + c]) - S.f[3 * s + c];
         }
         g.sync();
-        forward_solve<WK>(S, g);
-        for (int i = g.tid(); i < n; i += g.size()) S.A[MPC_PK(n, i)] = S.w[i];
-        g.sync();
-        backward_solve<WK>(S, g);
+#if defined(__CUDA_ARCH__)
+        if constexpr (G::kThreads == 32 && WK::NC <= 31) {
+            forward_regs<WK>(S, g);
+            backward_regs<WK>(S, g);
+        } else
+#endif
+        {
+            forward_solve<WK>(S, g);
+            for (int i = g.tid(); i < n; i += g.size()) S.A[MPC_PK(n, i)] = S.w[i];
+            g.sync();
+            backward_solve<WK>(S, g);
+        }
         if (g.tid() == 0) S.flag = 0;
         g.sync();
         for (int s = g.tid(); s < 2 * N; s += g.size()) {
