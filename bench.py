@@ -206,6 +206,22 @@ def run_gpu(args):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * B * Ke / float(te.item())
+    # controller-shaped host call (command in, first-step force out: the reference mpcQP's own I/O)
+    from mpc_limx_control_b200.engine import control_host
+    pin_c = {k: torch.from_numpy(d[k]).pin_memory() for k in ("omega_yaw", "velocity_x")}
+    u0h = torch.empty((B, 6), dtype=torch.float64).pin_memory()
+    args_c = (pin["x0"].numpy(), pin_c["omega_yaw"].numpy(), pin_c["velocity_x"].numpy(), pin["feet"].numpy())
+    for _ in range(max(3, W // 4)):
+        control_host(eng, *args_c, it=pin["iter"].numpy(), u0=u0h.numpy(), status=sh.numpy(), iters=ih.numpy())
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        control_host(eng, *args_c, it=pin["iter"].numpy(), u0=u0h.numpy(), status=sh.numpy(), iters=ih.numpy())
+    torch.cuda.synchronize()
+    tc = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+    e2e_ctrl_value = world * B * Ke / float(tc.item())
     clocks = sampler.stop() if sampler else None
 
     if rank != 0:
@@ -263,6 +279,11 @@ def run_gpu(args):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": B * (104 + 104 * (N + 1) + 48 + 4),
                 "d2h_bytes_per_step": B * (48 * N + 8), "steps": Ke},
+        "e2e_controller": {"value": e2e_ctrl_value, "unit": "solves/s", "h2d_bytes_per_step": B * (104 + 16 + 48 + 4),
+                           "d2h_bytes_per_step": B * (48 + 8), "steps": Ke,
+                           "what": "mpc_b200_tron1_control_host: state + (yaw-rate, vx) command + feet + gait clock in, "
+                                   "u = U_opt.col(0) out (the reference mpcQP constructor's own inputs/outputs); x_ref is "
+                                   "generated on the device"},
         "gpu_launches": int(launches),
         "latency": {"p50_us": float(np.percentile(lat, 50)), "p99_us": float(np.percentile(lat, 99)), "calls": len(lat),
                     "what": "B=1 host call -> forces on host (pinned buffers)"},

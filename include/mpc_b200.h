@@ -99,10 +99,21 @@ int mpc_b200_tron1_solve_device(mpc_b200_engine *e, int B, const double *d_x0, c
                                 const double *d_feet, const uint8_t *d_contact, const int32_t *d_iter,
                                 double *d_forces, int32_t *d_status, int32_t *d_iters, void *stream);
 
-/* Same with HOST buffers (pinned recommended): H2D copies, solve, D2H copies, stream sync. */
+/* Same with HOST buffers (pinned recommended): H2D copies, solve, D2H copies, stream sync.
+ * Large transfers (>= 6 MB per call) are split into chunks pipelined over several streams (copies overlap
+ * the solve);
+ * batches <= 64 take a packed single-copy path (one H2D, one D2H). */
 int mpc_b200_tron1_solve_host(mpc_b200_engine *e, int B, const double *x0, const double *x_ref,
                               const double *feet, const uint8_t *contact, const int32_t *iter,
                               double *forces, int32_t *status, int32_t *iters);
+
+/* Controller-shaped host entry, the closest analogue of the reference's mpcQP constructor
+ * (include/mpcQP.h:35-119): state, commanded yaw rate / forward velocity (the reference generator of
+ * include/mpcQP.h:74-97 runs on the device), feet and gait in; u = U_opt.col(0) (include/mpcQP.h:118)
+ * out: u0 [B][6].  Moves 172 B in and 56 B out per instance instead of 1,300 / 488. */
+int mpc_b200_tron1_control_host(mpc_b200_engine *e, int B, const double *x0, const double *omega_yaw,
+                                const double *velocity_x, const double *feet, const uint8_t *contact,
+                                const int32_t *iter, double *u0, int32_t *status, int32_t *iters);
 
 /* Parity dump of the condensed problem (any output may be NULL), device pointers:
  *   H [B][6N x 6N], f [B][6N], A_aug [B][13(N+1) x 13], B_aug [B][13(N+1) x 6N]  (column-major)

@@ -18,7 +18,7 @@ SYMBOLS = [
     "mpc_b200_tron1_default_params", "mpc_b200_create", "mpc_b200_destroy", "mpc_b200_last_error",
     "mpc_b200_launch_count", "mpc_b200_contact_schedule_device", "mpc_b200_tron1_solve_device",
     "mpc_b200_tron1_solve_host", "mpc_b200_tron1_condense_device",
-    "mpc_b200_tron1_reference_device", "mpc_b200_tron1_rollout_device",
+    "mpc_b200_tron1_reference_device", "mpc_b200_tron1_rollout_device", "mpc_b200_tron1_control_host",
     "mpc_b200_lti_create", "mpc_b200_lti_destroy", "mpc_b200_lti_last_error", "mpc_b200_lti_launch_count",
     "mpc_b200_lti_discretize", "mpc_b200_lti_build_qp", "mpc_b200_qp_solve_dense", "mpc_b200_lti_update_state",
 ]
@@ -73,6 +73,7 @@ def lib():
         L.mpc_b200_tron1_condense_device.argtypes = [vp, ip, vp, vp, vp, vp, vp, vp, vp, vp]
         L.mpc_b200_tron1_reference_device.argtypes = [vp, ip, vp, vp, vp, vp, vp]
         L.mpc_b200_tron1_rollout_device.argtypes = [vp, ip, ip, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.mpc_b200_tron1_control_host.argtypes = [vp, ip] + [vp] * 9
         dd = C.c_double
         L.mpc_b200_lti_create.argtypes = [ip, C.POINTER(vp)]
         L.mpc_b200_lti_destroy.argtypes = [vp]

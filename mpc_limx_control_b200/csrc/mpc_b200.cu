@@ -379,7 +379,13 @@ struct mpc_b200_engine {
     double *d_x0 = nullptr, *d_xref = nullptr, *d_feet = nullptr, *d_forces = nullptr;
     uint8_t* d_contact = nullptr;
     int32_t *d_iter = nullptr, *d_status = nullptr, *d_iters = nullptr;
-    int32_t *d_ovf_list = nullptr, *d_ovf_count = nullptr;   // capacity-overflow routing: list, {length, readers}
+    int32_t *d_ovf_list = nullptr, *d_ovf_count = nullptr;   // capacity-overflow routing: list, {length, readers} per slot
+    double *d_oy = nullptr, *d_vx = nullptr, *d_u0 = nullptr; // controller-shaped entry: commands in, first-step force out
+    static constexpr int kPipe = 4;                          // chunks in flight in the host-buffer entry
+    static constexpr int kSmallB = 64;                       // packed single-copy path below this batch size
+    cudaStream_t pipe[kPipe] = {};
+    unsigned char *h_small = nullptr, *d_small = nullptr;    // pinned / device staging of the packed path
+    size_t small_bytes = 0;
     int num_sms = 148;
     int64_t launches = 0;
     std::string err;
@@ -407,7 +413,7 @@ static size_t solve_smem_bytes() {
 template <int N, int WPI_S, int IPC_S, int MINB_S, int WPI_L, int IPC_L>
 static int launch_solve(mpc_b200_engine* e, int B, const double* x0, const double* xref, const double* feet,
                         const uint8_t* contact, const int32_t* iter, double* forces, int32_t* status,
-                        int32_t* iters, cudaStream_t s) {
+                        int32_t* iters, cudaStream_t s, int32_t* ovf_list, int32_t* ovf_count) {
     auto ks = tron1_solve_kernel<N, 3 * N, WPI_S, IPC_S, MINB_S, false>;
     auto kl = tron1_solve_kernel<N, 6 * N, WPI_L, IPC_L, 1, true>;
     const size_t smem_s = solve_smem_bytes<N, 3 * N, IPC_S>();
@@ -419,12 +425,12 @@ static int launch_solve(mpc_b200_engine* e, int B, const double* x0, const doubl
         configured[e->device & 63] = true;
     }
     ks<<<(B + IPC_S - 1) / IPC_S, 32 * WPI_S * IPC_S, smem_s, s>>>(e->C, B, x0, xref, feet, contact, iter, forces, status,
-                                                                 iters, e->d_ovf_list, e->d_ovf_count);
+                                                                 iters, ovf_list, ovf_count);
     CU(e, cudaGetLastError());
     int grid_l = (B + IPC_L - 1) / IPC_L;
     if (grid_l > e->num_sms * 2) grid_l = e->num_sms * 2;
     kl<<<grid_l, 32 * WPI_L * IPC_L, smem_l, s>>>(e->C, B, x0, xref, feet, contact, iter, forces, status, iters,
-                                                  e->d_ovf_list, e->d_ovf_count);
+                                                  ovf_list, ovf_count);
     CU(e, cudaGetLastError());
     e->launches += 2;
     return MPC_B200_OK;
@@ -433,11 +439,13 @@ static int launch_solve(mpc_b200_engine* e, int B, const double* x0, const doubl
 // compiled configurations per horizon
 static int dispatch_solve(mpc_b200_engine* e, int B, const double* x0, const double* xref, const double* feet,
                           const uint8_t* contact, const int32_t* iter, double* forces, int32_t* status,
-                          int32_t* iters, cudaStream_t s) {
-    if (B > e->max_batch) return set_err(e, MPC_B200_ECAPACITY, "solve: B > max_batch");
+                          int32_t* iters, cudaStream_t s, int slot = 0, int list_offset = 0) {
+    if (B + list_offset > e->max_batch) return set_err(e, MPC_B200_ECAPACITY, "solve: B > max_batch");
+    int32_t* ol = e->d_ovf_list + list_offset;
+    int32_t* oc = e->d_ovf_count + 2 * slot;
     switch (e->N) {
-        case 10: return launch_solve<10, 1, 4, 4, 2, 2>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s);
-        case 20: return launch_solve<20, 2, 2, 2, 2, 2>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s);
+        case 10: return launch_solve<10, 1, 4, 4, 2, 2>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc);
+        case 20: return launch_solve<20, 2, 2, 2, 2, 2>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc);
         default: return set_err(e, MPC_B200_EINVAL, "unsupported horizon");
     }
 }
@@ -509,8 +517,17 @@ int mpc_b200_create(const mpc_b200_tron1_params* p, int horizon, int max_batch, 
               cudaMalloc(&e->d_status, sizeof(int32_t) * max_batch) == cudaSuccess &&
               cudaMalloc(&e->d_iters, sizeof(int32_t) * max_batch) == cudaSuccess &&
               cudaMalloc(&e->d_ovf_list, sizeof(int32_t) * max_batch) == cudaSuccess &&
-              cudaMalloc(&e->d_ovf_count, 2 * sizeof(int32_t)) == cudaSuccess &&
-              cudaMemset(e->d_ovf_count, 0, 2 * sizeof(int32_t)) == cudaSuccess;
+              cudaMalloc(&e->d_ovf_count, 2 * (mpc_b200_engine::kPipe + 1) * sizeof(int32_t)) == cudaSuccess &&
+              cudaMemset(e->d_ovf_count, 0, 2 * (mpc_b200_engine::kPipe + 1) * sizeof(int32_t)) == cudaSuccess &&
+              cudaMalloc(&e->d_oy, sizeof(double) * max_batch) == cudaSuccess &&
+              cudaMalloc(&e->d_vx, sizeof(double) * max_batch) == cudaSuccess &&
+              cudaMalloc(&e->d_u0, sizeof(double) * 6 * max_batch) == cudaSuccess;
+    for (int i = 0; ok && i < mpc_b200_engine::kPipe; ++i)
+        ok = cudaStreamCreateWithFlags(&e->pipe[i], cudaStreamNonBlocking) == cudaSuccess;
+    // packed staging of the small-batch path: inputs and outputs of kSmallB instances, 16-byte aligned segments
+    e->small_bytes = (size_t)mpc_b200_engine::kSmallB * (sizeof(double) * (13 + 13 * (N + 1) + fstride + 2 + 6 * N) + 2 * N + 16) + 1024;
+    ok = ok && cudaHostAlloc((void**)&e->h_small, e->small_bytes, cudaHostAllocDefault) == cudaSuccess &&
+         cudaMalloc((void**)&e->d_small, e->small_bytes) == cudaSuccess;
     e->num_sms = prop.multiProcessorCount;
     if (!ok) {
         cudaGetLastError();
@@ -528,6 +545,10 @@ int mpc_b200_destroy(mpc_b200_engine* e) {
     cudaFree(e->d_x0); cudaFree(e->d_xref); cudaFree(e->d_feet); cudaFree(e->d_forces);
     cudaFree(e->d_contact); cudaFree(e->d_iter); cudaFree(e->d_status); cudaFree(e->d_iters);
     cudaFree(e->d_ovf_list); cudaFree(e->d_ovf_count);
+    cudaFree(e->d_oy); cudaFree(e->d_vx); cudaFree(e->d_u0);
+    for (int i = 0; i < mpc_b200_engine::kPipe; ++i) if (e->pipe[i]) { cudaStreamSynchronize(e->pipe[i]); cudaStreamDestroy(e->pipe[i]); }
+    if (e->h_small) cudaFreeHost(e->h_small);
+    cudaFree(e->d_small);
     delete e;
     return MPC_B200_OK;
 }
@@ -556,28 +577,146 @@ int mpc_b200_tron1_solve_device(mpc_b200_engine* e, int B, const double* d_x0, c
     return dispatch_solve(e, B, d_x0, d_x_ref, d_feet, d_contact, d_iter, d_forces, d_status, d_iters, (cudaStream_t)stream);
 }
 
+// first-step forces u_0 of every instance, packed [B][6]
+__global__ void gather_u0_kernel(int B, int N, const double* __restrict__ forces, double* __restrict__ u0) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < B * 6) u0[idx] = forces[(size_t)(idx / 6) * 6 * N + idx % 6];
+}
+
+namespace {
+// packed layout of the small-batch path: every segment starts 16-byte aligned (TMA bulk copies)
+struct SmallLayout {
+    size_t x0, xref, feet, oy, vx, sched, in_bytes, forces, u0, status, iters, total;
+};
+inline size_t up16(size_t v) { return (v + 15) & ~size_t(15); }
+SmallLayout small_layout(int B, int N, size_t fstride, bool has_contact, bool cmd) {
+    SmallLayout L;
+    size_t o = 0;
+    L.x0 = o; o = up16(o + sizeof(double) * 13 * B);
+    L.xref = o; if (!cmd) o = up16(o + sizeof(double) * 13 * (N + 1) * B);
+    L.feet = o; o = up16(o + sizeof(double) * fstride * B);
+    L.oy = o; if (cmd) o = up16(o + sizeof(double) * B);
+    L.vx = o; if (cmd) o = up16(o + sizeof(double) * B);
+    L.sched = o; o = up16(o + (has_contact ? (size_t)2 * N * B : sizeof(int32_t) * B));
+    L.in_bytes = o;
+    L.forces = o; if (!cmd) o = up16(o + sizeof(double) * 6 * N * B);
+    L.u0 = o; if (cmd) o = up16(o + sizeof(double) * 6 * B);
+    L.status = o; o = up16(o + sizeof(int32_t) * B);
+    L.iters = o; o = up16(o + sizeof(int32_t) * B);
+    L.total = o;
+    return L;
+}
+}  // namespace
+
+// shared implementation of the two host-buffer entry points.
+//   cmd == false: x_ref in, full horizon forces out (forces_out [B][N][6])
+//   cmd == true : (omega_yaw, velocity_x) in -> reference generated on the device (include/mpcQP.h:74-97),
+//                 first-step forces out (forces_out [B][6]), i.e. u = U_opt.col(0) (include/mpcQP.h:118)
+static int solve_host_impl(mpc_b200_engine* e, int B, const double* x0, const double* x_ref, const double* oy,
+                           const double* vx, const double* feet, const uint8_t* contact, const int32_t* iter,
+                           double* forces_out, int32_t* status, int32_t* iters, bool cmd) {
+    const int N = e->N;
+    const size_t fstride = (e->C.per_step_feet && e->C.ltv) ? 6 * (size_t)N : 6;
+    const size_t XR = 13 * (size_t)(N + 1);
+    if (B <= mpc_b200_engine::kSmallB) {
+        // ---- latency path: pack on the host, ONE H2D, kernels, ONE D2H ------------------------------------
+        const SmallLayout L = small_layout(B, N, fstride, contact != nullptr, cmd);
+        unsigned char* h = e->h_small;
+        unsigned char* d = e->d_small;
+        cudaStream_t s = e->stream;
+        memcpy(h + L.x0, x0, sizeof(double) * 13 * B);
+        if (!cmd) memcpy(h + L.xref, x_ref, sizeof(double) * XR * B);
+        memcpy(h + L.feet, feet, sizeof(double) * fstride * B);
+        if (cmd) { memcpy(h + L.oy, oy, sizeof(double) * B); memcpy(h + L.vx, vx, sizeof(double) * B); }
+        if (contact) memcpy(h + L.sched, contact, (size_t)2 * N * B); else memcpy(h + L.sched, iter, sizeof(int32_t) * B);
+        CU(e, cudaMemcpyAsync(d, h, L.in_bytes, cudaMemcpyHostToDevice, s));
+        const double* dxr = (const double*)(d + L.xref);
+        double* dforces = (double*)(d + L.forces);
+        if (cmd) {
+            tron1_reference_kernel<<<(int)((XR * B + 255) / 256), 256, 0, s>>>(e->C, B, N, (const double*)(d + L.x0), (const double*)(d + L.oy),
+                                                                              (const double*)(d + L.vx), e->d_xref);
+            CU(e, cudaGetLastError());
+            e->launches++;
+            dxr = e->d_xref;
+            dforces = e->d_forces;
+        }
+        int rc = dispatch_solve(e, B, (const double*)(d + L.x0), dxr, (const double*)(d + L.feet),
+                                contact ? (const uint8_t*)(d + L.sched) : nullptr, contact ? nullptr : (const int32_t*)(d + L.sched),
+                                dforces, (int32_t*)(d + L.status), (int32_t*)(d + L.iters), s);
+        if (rc) return rc;
+        if (cmd) {
+            gather_u0_kernel<<<(B * 6 + 127) / 128, 128, 0, s>>>(B, N, e->d_forces, (double*)(d + L.u0));
+            CU(e, cudaGetLastError());
+            e->launches++;
+        }
+        CU(e, cudaMemcpyAsync(h + L.in_bytes, d + L.in_bytes, L.total - L.in_bytes, cudaMemcpyDeviceToHost, s));
+        CU(e, cudaStreamSynchronize(s));
+        if (cmd) memcpy(forces_out, h + L.u0, sizeof(double) * 6 * B);
+        else memcpy(forces_out, h + L.forces, sizeof(double) * 6 * N * B);
+        if (status) memcpy(status, h + L.status, sizeof(int32_t) * B);
+        if (iters) memcpy(iters, h + L.iters, sizeof(int32_t) * B);
+        return MPC_B200_OK;
+    }
+    // ---- throughput path: chunks pipelined over kPipe streams (H2D / solve / D2H of different chunks overlap) --
+    // chunking pays only when the copies outweigh the per-call API overhead (~5 us per memcpy / launch)
+    const size_t bytes = (size_t)B * (cmd ? 172 + 56 : sizeof(double) * (13 + XR + fstride + 6 * (size_t)N));
+    const int nchunk = bytes >= (size_t)24 << 20 ? mpc_b200_engine::kPipe : (bytes >= (size_t)6 << 20 ? 2 : 1);
+    int chunk = (B + nchunk - 1) / nchunk;
+    chunk = (chunk + 3) & ~3;   // chunk starts stay multiples of 4: CTA slices remain 16-byte aligned
+    for (int c = 0, first = 0; first < B; ++c, first += chunk) {
+        const int nb = (B - first < chunk) ? (B - first) : chunk;
+        cudaStream_t s = e->pipe[c % mpc_b200_engine::kPipe];
+        const size_t f = first;
+        CU(e, cudaMemcpyAsync(e->d_x0 + 13 * f, x0 + 13 * f, sizeof(double) * 13 * nb, cudaMemcpyHostToDevice, s));
+        if (!cmd) CU(e, cudaMemcpyAsync(e->d_xref + XR * f, x_ref + XR * f, sizeof(double) * XR * nb, cudaMemcpyHostToDevice, s));
+        CU(e, cudaMemcpyAsync(e->d_feet + fstride * f, feet + fstride * f, sizeof(double) * fstride * nb, cudaMemcpyHostToDevice, s));
+        if (contact) CU(e, cudaMemcpyAsync(e->d_contact + 2 * N * f, contact + 2 * N * f, (size_t)2 * N * nb, cudaMemcpyHostToDevice, s));
+        else CU(e, cudaMemcpyAsync(e->d_iter + f, iter + f, sizeof(int32_t) * nb, cudaMemcpyHostToDevice, s));
+        if (cmd) {
+            CU(e, cudaMemcpyAsync(e->d_oy + f, oy + f, sizeof(double) * nb, cudaMemcpyHostToDevice, s));
+            CU(e, cudaMemcpyAsync(e->d_vx + f, vx + f, sizeof(double) * nb, cudaMemcpyHostToDevice, s));
+            int grid = (int)((XR * nb + 255) / 256);
+            if (grid > e->num_sms * 16) grid = e->num_sms * 16;
+            tron1_reference_kernel<<<grid, 256, 0, s>>>(e->C, nb, N, e->d_x0 + 13 * f, e->d_oy + f, e->d_vx + f, e->d_xref + XR * f);
+            CU(e, cudaGetLastError());
+            e->launches++;
+        }
+        int rc = dispatch_solve(e, nb, e->d_x0 + 13 * f, e->d_xref + XR * f, e->d_feet + fstride * f,
+                                contact ? e->d_contact + 2 * N * f : nullptr, contact ? nullptr : e->d_iter + f,
+                                e->d_forces + 6 * N * f, e->d_status + f, e->d_iters + f, s, 1 + c % mpc_b200_engine::kPipe, first);
+        if (rc) return rc;
+        if (cmd) {
+            gather_u0_kernel<<<(nb * 6 + 255) / 256, 256, 0, s>>>(nb, N, e->d_forces + 6 * N * f, e->d_u0 + 6 * f);
+            CU(e, cudaGetLastError());
+            e->launches++;
+            CU(e, cudaMemcpyAsync(forces_out + 6 * f, e->d_u0 + 6 * f, sizeof(double) * 6 * nb, cudaMemcpyDeviceToHost, s));
+        } else {
+            CU(e, cudaMemcpyAsync(forces_out + 6 * N * f, e->d_forces + 6 * N * f, sizeof(double) * 6 * N * nb, cudaMemcpyDeviceToHost, s));
+        }
+        if (status) CU(e, cudaMemcpyAsync(status + f, e->d_status + f, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, s));
+        if (iters) CU(e, cudaMemcpyAsync(iters + f, e->d_iters + f, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, s));
+    }
+    for (int i = 0; i < mpc_b200_engine::kPipe; ++i) CU(e, cudaStreamSynchronize(e->pipe[i]));
+    return MPC_B200_OK;
+}
+
 int mpc_b200_tron1_solve_host(mpc_b200_engine* e, int B, const double* x0, const double* x_ref, const double* feet,
                               const uint8_t* contact, const int32_t* iter, double* forces, int32_t* status, int32_t* iters) {
     if (!e || !x0 || !x_ref || !feet || !forces || B < 1) return set_err(e, MPC_B200_EINVAL, "solve_host: bad argument");
     if ((contact == nullptr) == (iter == nullptr)) return set_err(e, MPC_B200_EINVAL, "solve_host: pass exactly one of contact / iter");
     if (B > e->max_batch) return set_err(e, MPC_B200_ECAPACITY, "solve_host: B > max_batch");
     CU(e, cudaSetDevice(e->device));
-    const int N = e->N;
-    const size_t fstride = (e->C.per_step_feet && e->C.ltv) ? 6 * (size_t)N : 6;
-    cudaStream_t s = e->stream;
-    CU(e, cudaMemcpyAsync(e->d_x0, x0, sizeof(double) * 13 * B, cudaMemcpyHostToDevice, s));
-    CU(e, cudaMemcpyAsync(e->d_xref, x_ref, sizeof(double) * 13 * (N + 1) * (size_t)B, cudaMemcpyHostToDevice, s));
-    CU(e, cudaMemcpyAsync(e->d_feet, feet, sizeof(double) * fstride * B, cudaMemcpyHostToDevice, s));
-    if (contact) CU(e, cudaMemcpyAsync(e->d_contact, contact, (size_t)2 * N * B, cudaMemcpyHostToDevice, s));
-    else CU(e, cudaMemcpyAsync(e->d_iter, iter, sizeof(int32_t) * B, cudaMemcpyHostToDevice, s));
-    int rc = dispatch_solve(e, B, e->d_x0, e->d_xref, e->d_feet, contact ? e->d_contact : nullptr,
-                            contact ? nullptr : e->d_iter, e->d_forces, e->d_status, e->d_iters, s);
-    if (rc) return rc;
-    CU(e, cudaMemcpyAsync(forces, e->d_forces, sizeof(double) * 6 * N * (size_t)B, cudaMemcpyDeviceToHost, s));
-    if (status) CU(e, cudaMemcpyAsync(status, e->d_status, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, s));
-    if (iters) CU(e, cudaMemcpyAsync(iters, e->d_iters, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, s));
-    CU(e, cudaStreamSynchronize(s));
-    return MPC_B200_OK;
+    return solve_host_impl(e, B, x0, x_ref, nullptr, nullptr, feet, contact, iter, forces, status, iters, false);
+}
+
+int mpc_b200_tron1_control_host(mpc_b200_engine* e, int B, const double* x0, const double* omega_yaw, const double* velocity_x,
+                                const double* feet, const uint8_t* contact, const int32_t* iter, double* u0, int32_t* status,
+                                int32_t* iters) {
+    if (!e || !x0 || !omega_yaw || !velocity_x || !feet || !u0 || B < 1) return set_err(e, MPC_B200_EINVAL, "control_host: bad argument");
+    if ((contact == nullptr) == (iter == nullptr)) return set_err(e, MPC_B200_EINVAL, "control_host: pass exactly one of contact / iter");
+    if (B > e->max_batch) return set_err(e, MPC_B200_ECAPACITY, "control_host: B > max_batch");
+    CU(e, cudaSetDevice(e->device));
+    return solve_host_impl(e, B, x0, nullptr, omega_yaw, velocity_x, feet, contact, iter, u0, status, iters, true);
 }
 
 int mpc_b200_tron1_condense_device(mpc_b200_engine* e, int B, const double* d_x0, const double* d_x_ref,

@@ -157,6 +157,28 @@ class Engine:
         return forces, status, iters
 
 
+def _np(a, dt):
+    if a is None:
+        return None
+    if isinstance(a, torch.Tensor):
+        a = a.numpy()
+    return np.ascontiguousarray(a, dtype=dt)
+
+
+def control_host(eng, x0, omega_yaw, velocity_x, feet, contact=None, it=None, u0=None, status=None, iters=None):
+    """Controller-shaped host call: state + velocity command + feet + gait -> first-step forces [B,6]."""
+    x0 = _np(x0, np.float64); oy = _np(omega_yaw, np.float64); vx = _np(velocity_x, np.float64); feet = _np(feet, np.float64)
+    contact = _np(contact, np.uint8); it = _np(it, np.int32)
+    B = x0.shape[0]
+    u0 = np.empty((B, 6)) if u0 is None else u0
+    status = np.empty(B, np.int32) if status is None else status
+    iters = np.empty(B, np.int32) if iters is None else iters
+    p = lambda a: None if a is None else C.c_void_p(as_np_out(a).ctypes.data)
+    rc = eng.lib.mpc_b200_tron1_control_host(eng.h, B, p(x0), p(oy), p(vx), p(feet), p(contact), p(it), p(u0), p(status), p(iters))
+    _capi.check(rc, eng.h)
+    return u0, status, iters
+
+
 def as_np_out(a):
     if isinstance(a, torch.Tensor):
         return a.numpy()

@@ -286,3 +286,32 @@ def test_rollout_properties_larger(torch_cuda):
     assert (U[..., 2] >= -1e-12).all() and (U[..., 5] >= -1e-12).all()
     assert (np.abs(U[..., 0]) <= 0.5 * U[..., 2] + 1e-9).all()
     eng.close()
+
+
+def test_host_paths_packed_and_pipelined(torch_cuda):
+    """solve_host small-batch packed path (B<=64) and chunk-pipelined path (B>=1024, ragged tail),
+    and the controller-shaped entry (command in, first-step force out), all bit-identical to the
+    device entry point on the same inputs."""
+    torch = torch_cuda
+    from mpc_limx_control_b200.engine import control_host
+    N, Ts = 10, 0.005
+    for B in (1, 7, 64, 65, 2050, 6001):
+        d = synth.tron1_batch(21, B, N, Ts)
+        if B == 7:
+            d["iter"][3] = -1          # one standing instance: exercises the overflow class in the packed path
+        eng = make_engine(N, max(B, 8), Ts=Ts)
+        t = to_dev(torch, d)
+        F, st, it = eng.solve(t["x0"], t["x_ref"], t["feet"], it=t["iter"])
+        torch.cuda.synchronize()
+        F = F.cpu().numpy(); st = st.cpu().numpy()
+        assert (st == 0).all()
+        Fh, sh, ih = eng.solve_host(d["x0"], d["x_ref"], d["feet"], it=d["iter"])
+        assert np.array_equal(Fh, F) and np.array_equal(sh, st)
+        contact = np.stack([O.contact_schedule(int(i), N) for i in d["iter"]])
+        Fh2, sh2, _ = eng.solve_host(d["x0"], d["x_ref"], d["feet"], contact=contact)
+        assert np.array_equal(Fh2, F)
+        u0, s0, i0 = control_host(eng, d["x0"], d["omega_yaw"], d["velocity_x"], d["feet"], it=d["iter"])
+        assert (s0 == 0).all()
+        # the device reference generator may differ from numpy's x_ref in the last bit (FMA) -> tiny tolerance
+        assert np.abs(u0 - F[:, 0, :]).max() / max(1.0, np.abs(F).max()) < 1e-9
+        eng.close()
