@@ -22,7 +22,10 @@ KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum", "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum",
         "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
         "smsp__cycles_active.avg", "sm__cycles_elapsed.max", "sm__cycles_active.avg",
-        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__inst_executed_op_shared_ld.sum", "smsp__inst_executed_op_shared_st.sum"]
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__inst_executed_op_shared_ld.sum", "smsp__inst_executed_op_shared_st.sum",
+        "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum.per_cycle_elapsed", "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum.per_cycle_elapsed",
+        "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum.per_cycle_elapsed", "sm__sass_thread_inst_executed_op_dfma_pred_on.sum.peak_sustained",
+        "sm__cycles_elapsed.avg", "sm__cycles_elapsed.avg.per_second"]
 
 summary = {"tag": tag}
 if os.path.exists(rep):
@@ -41,13 +44,31 @@ if os.path.exists(rep):
     if kernels:
         def num(s):
             return float(s.split()[0].replace(",", ""))
-        k0 = kernels[-1]
+        def dur_us(k):
+            v, u = k["gpu__time_duration.sum"].split()[:2]
+            return float(v.replace(",", "")) * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(u, 1.0)
+        k0 = max(kernels, key=dur_us)   # the hot kernel of the step
         unit_r = k0["dram__bytes_read.sum"].split()[1]
         mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         traffic = num(k0["dram__bytes_read.sum"]) * mult[unit_r] + num(k0["dram__bytes_write.sum"]) * mult[k0["dram__bytes_write.sum"].split()[1]]
         summary["dram_bytes_per_launch"] = traffic
-        json.dump({"dram_bytes_per_launch": traffic, "source": f"profiles/{tag}_solve_kernel.json (ncu --set full)"},
-                  open(os.path.join(out, "traffic.json"), "w"))
+        # executed FP64 work of the hot kernel (first kernel in the report): thread-level DFMA/DMUL/DADD
+        try:
+            k1 = k0
+            cyc = num(k1["sm__cycles_elapsed.max"])
+            dfma = num(k1["smsp__sass_thread_inst_executed_op_dfma_pred_on.sum.per_cycle_elapsed"])
+            dmul = num(k1["smsp__sass_thread_inst_executed_op_dmul_pred_on.sum.per_cycle_elapsed"])
+            dadd = num(k1["smsp__sass_thread_inst_executed_op_dadd_pred_on.sum.per_cycle_elapsed"])
+            peak = num(k1["sm__sass_thread_inst_executed_op_dfma_pred_on.sum.peak_sustained"])
+            summary["executed_fp64"] = {"dfma_per_cycle": dfma, "dmul_per_cycle": dmul, "dadd_per_cycle": dadd,
+                                        "flops_per_cycle": 2 * dfma + dmul + dadd, "dfma_peak_per_cycle": peak,
+                                        "frac_of_dfma_peak": (2 * dfma + dmul + dadd) / (2 * peak),
+                                        "flops_per_launch": (2 * dfma + dmul + dadd) * cyc, "cycles_elapsed_max": cyc}
+        except Exception as ex:
+            summary["executed_fp64"] = {"error": str(ex)}
+        json.dump({"dram_bytes_per_launch": traffic, "source": f"profiles/{tag}_solve_kernel.json (ncu --set full)",
+                   "executed_fp64": summary.get("executed_fp64"), "batch": 4096},
+                  open(os.path.join(out, "traffic.json"), "w"), indent=1)
 if os.path.exists(lst):
     rows = [r for r in csv.reader(open(lst)) if len(r) > 5]
     h = [i for i, r in enumerate(rows) if r[0] == "ID"][0]
