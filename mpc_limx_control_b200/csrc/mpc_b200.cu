@@ -87,16 +87,16 @@ struct CtaStage {
 // per-instance workspace small enough for 12-16 resident instances per SM; instances that need more
 // (double support) are appended to an overflow list and solved by the NC = 6N instantiation, which
 // runs INDIRECT (list-driven, grid-stride, plain loads) right after.  No host synchronisation.
-template <int N, int NC, int WPI, int IPC, int MINB, bool INDIRECT>
+template <int N, int NC, int WPI, int IPC, int MINB, bool INDIRECT, bool AINL = true>
 __global__ void __launch_bounds__(32 * WPI * IPC, MINB)
 tron1_solve_kernel(const __grid_constant__ Tron1Const P, int B, const double* __restrict__ x0,
                    const double* __restrict__ xref, const double* __restrict__ feet,
                    const uint8_t* __restrict__ contact, const int32_t* __restrict__ iter,
                    double* __restrict__ forces, int32_t* __restrict__ status, int32_t* __restrict__ iters,
-                   int32_t* __restrict__ ovf_list, int32_t* __restrict__ ovf_count) {
+                   int32_t* __restrict__ ovf_list, int32_t* __restrict__ ovf_count, double* __restrict__ ext_A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using Stage = CtaStage<N, IPC>;
-    using Work = Tron1Work<N, NC>;
+    using Work = Tron1Work<N, NC, AINL>;
     Stage& st = *reinterpret_cast<Stage*>(smem_raw);
     constexpr size_t stage_bytes = (sizeof(Stage) + 15) & ~size_t(15);
     Work* works = reinterpret_cast<Work*>(smem_raw + stage_bytes);
@@ -109,6 +109,8 @@ tron1_solve_kernel(const __grid_constant__ Tron1Const P, int B, const double* __
     Work& S = works[g.gid];
     S.x0 = st.x0 + g.gid * 13;
     S.feet = st.feet + g.gid * fstride;
+    if (Work::AINL) S.A = S.Astore;
+    else S.A = ext_A + ((size_t)blockIdx.x * IPC + g.gid) * Work::PKN;   // one slab per resident group
     const double* xr_s = st.xr + g.gid * XR;
 
     auto load_contact = [&](int b) {   // fills S.contact, returns the compact size 3 * stance foot-steps
@@ -263,6 +265,7 @@ tron1_rollout_kernel(const __grid_constant__ Tron1Const P, int B, int steps, dou
     const int it0 = iter0[b];
     if ((it0 < 0) != STANDING) return;   // the other capacity class handles this instance
     Work& S = works[g.gid];
+    S.A = S.Astore;
     double* xs = st.x + g.gid * 14;
     double* fs = st.feet + g.gid * 6;
     double* xr = st.xr + g.gid * Stage::XR;
@@ -297,17 +300,19 @@ tron1_rollout_kernel(const __grid_constant__ Tron1Const P, int B, int steps, dou
 }
 
 // ---- parity dump: one warp per instance -------------------------------------------------------------
-template <int N>
+template <int N, bool AINL>
 __global__ void __launch_bounds__(32)
 tron1_condense_kernel(const __grid_constant__ Tron1Const P, int B, const double* __restrict__ x0,
                       const double* __restrict__ xref, const double* __restrict__ feet,
                       double* __restrict__ H, double* __restrict__ f, double* __restrict__ A_aug,
-                      double* __restrict__ B_aug) {
+                      double* __restrict__ B_aug, double* __restrict__ ext_A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    using Work = Tron1Work<N, 6 * N>;
+    using Work = Tron1Work<N, 6 * N, AINL>;
     Work& S = *reinterpret_cast<Work*>(smem_raw);
     const int b = blockIdx.x;
     if (b >= B) return;
+    if (AINL) S.A = S.Astore;
+    else S.A = ext_A + (size_t)b * Work::PKN;
     GrpCuda<1> g;
     g.t = threadIdx.x;
     g.gid = 0;
@@ -385,6 +390,8 @@ struct mpc_b200_engine {
     static constexpr int kSmallB = 64;                       // packed single-copy path below this batch size
     cudaStream_t pipe[kPipe] = {};
     unsigned char *h_small = nullptr, *d_small = nullptr;    // pinned / device staging of the packed path
+    double* d_extA = nullptr;                                // global-memory factor slabs (N = 50 double support)
+    int extA_slabs = 0;
     size_t small_bytes = 0;
     int num_sms = 148;
     int64_t launches = 0;
@@ -410,14 +417,14 @@ static size_t solve_smem_bytes() {
 }
 
 // small class (direct, TMA-staged) followed by the large class (indirect, overflow list)
-template <int N, int WPI_S, int IPC_S, int MINB_S, int WPI_L, int IPC_L>
+template <int N, int WPI_S, int IPC_S, int MINB_S, int WPI_L, int IPC_L, bool AINL_L = true>
 static int launch_solve(mpc_b200_engine* e, int B, const double* x0, const double* xref, const double* feet,
                         const uint8_t* contact, const int32_t* iter, double* forces, int32_t* status,
                         int32_t* iters, cudaStream_t s, int32_t* ovf_list, int32_t* ovf_count) {
-    auto ks = tron1_solve_kernel<N, 3 * N, WPI_S, IPC_S, MINB_S, false>;
-    auto kl = tron1_solve_kernel<N, 6 * N, WPI_L, IPC_L, 1, true>;
-    const size_t smem_s = solve_smem_bytes<N, 3 * N, IPC_S>();
-    const size_t smem_l = solve_smem_bytes<N, 6 * N, IPC_L>();
+    auto ks = tron1_solve_kernel<N, 3 * N, WPI_S, IPC_S, MINB_S, false, true>;
+    auto kl = tron1_solve_kernel<N, 6 * N, WPI_L, IPC_L, 1, true, AINL_L>;
+    const size_t smem_s = ((sizeof(CtaStage<N, IPC_S>) + 15) & ~size_t(15)) + sizeof(Tron1Work<N, 3 * N, true>) * IPC_S;
+    const size_t smem_l = ((sizeof(CtaStage<N, IPC_L>) + 15) & ~size_t(15)) + sizeof(Tron1Work<N, 6 * N, AINL_L>) * IPC_L;
     static bool configured[64] = {};
     if (!configured[e->device & 63]) {
         CU(e, cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
@@ -425,12 +432,13 @@ static int launch_solve(mpc_b200_engine* e, int B, const double* x0, const doubl
         configured[e->device & 63] = true;
     }
     ks<<<(B + IPC_S - 1) / IPC_S, 32 * WPI_S * IPC_S, smem_s, s>>>(e->C, B, x0, xref, feet, contact, iter, forces, status,
-                                                                 iters, ovf_list, ovf_count);
+                                                                 iters, ovf_list, ovf_count, nullptr);
     CU(e, cudaGetLastError());
     int grid_l = (B + IPC_L - 1) / IPC_L;
     if (grid_l > e->num_sms * 2) grid_l = e->num_sms * 2;
+    if (!AINL_L && grid_l * IPC_L > e->extA_slabs) grid_l = e->extA_slabs / IPC_L;
     kl<<<grid_l, 32 * WPI_L * IPC_L, smem_l, s>>>(e->C, B, x0, xref, feet, contact, iter, forces, status, iters,
-                                                  ovf_list, ovf_count);
+                                                  ovf_list, ovf_count, AINL_L ? nullptr : e->d_extA);
     CU(e, cudaGetLastError());
     e->launches += 2;
     return MPC_B200_OK;
@@ -446,6 +454,7 @@ static int dispatch_solve(mpc_b200_engine* e, int B, const double* x0, const dou
     switch (e->N) {
         case 10: return launch_solve<10, 1, 4, 4, 2, 2>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc);
         case 20: return launch_solve<20, 2, 2, 2, 2, 2>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc);
+        case 50: return launch_solve<50, 8, 1, 1, 8, 1, false>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc);
         default: return set_err(e, MPC_B200_EINVAL, "unsupported horizon");
     }
 }
@@ -492,7 +501,7 @@ int mpc_b200_tron1_default_params(mpc_b200_tron1_params* p) {
 
 int mpc_b200_create(const mpc_b200_tron1_params* p, int horizon, int max_batch, int device, mpc_b200_engine** out) {
     if (!p || !out || max_batch < 1) return MPC_B200_EINVAL;
-    if (horizon != 10 && horizon != 20) return MPC_B200_EINVAL;
+    if (horizon != 10 && horizon != 20 && horizon != 50) return MPC_B200_EINVAL;
     *out = nullptr;
     int ndev = mpc_b200_device_count();
     if (device < 0 || device >= ndev) return MPC_B200_ENODEV;
@@ -529,6 +538,11 @@ int mpc_b200_create(const mpc_b200_tron1_params* p, int horizon, int max_batch, 
     ok = ok && cudaHostAlloc((void**)&e->h_small, e->small_bytes, cudaHostAllocDefault) == cudaSuccess &&
          cudaMalloc((void**)&e->d_small, e->small_bytes) == cudaSuccess;
     e->num_sms = prop.multiProcessorCount;
+    if (ok && horizon == 50) {   // double-support factor (301*302/2 doubles = 364 KB) does not fit shared memory
+        e->extA_slabs = e->num_sms * 2;
+        if (e->extA_slabs > max_batch) e->extA_slabs = max_batch;
+        ok = cudaMalloc(&e->d_extA, sizeof(double) * Tron1Work<50, 300, false>::PKN * (size_t)e->extA_slabs) == cudaSuccess;
+    }
     if (!ok) {
         cudaGetLastError();
         mpc_b200_destroy(e);
@@ -549,6 +563,7 @@ int mpc_b200_destroy(mpc_b200_engine* e) {
     for (int i = 0; i < mpc_b200_engine::kPipe; ++i) if (e->pipe[i]) { cudaStreamSynchronize(e->pipe[i]); cudaStreamDestroy(e->pipe[i]); }
     if (e->h_small) cudaFreeHost(e->h_small);
     cudaFree(e->d_small);
+    cudaFree(e->d_extA);
     delete e;
     return MPC_B200_OK;
 }
@@ -726,15 +741,30 @@ int mpc_b200_tron1_condense_device(mpc_b200_engine* e, int B, const double* d_x0
     CU(e, cudaSetDevice(e->device));
     cudaStream_t s = (cudaStream_t)stream;
     if (e->N == 10) {
-        auto k = tron1_condense_kernel<10>;
-        size_t smem = sizeof(Tron1Work<10, 60>);
+        auto k = tron1_condense_kernel<10, true>;
+        size_t smem = sizeof(Tron1Work<10, 60, true>);
         CU(e, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<B, 32, smem, s>>>(e->C, B, d_x0, d_x_ref, d_feet, d_H, d_f, d_A_aug, d_B_aug);
+        k<<<B, 32, smem, s>>>(e->C, B, d_x0, d_x_ref, d_feet, d_H, d_f, d_A_aug, d_B_aug, nullptr);
     } else if (e->N == 20) {
-        auto k = tron1_condense_kernel<20>;
-        size_t smem = sizeof(Tron1Work<20, 120>);
+        auto k = tron1_condense_kernel<20, true>;
+        size_t smem = sizeof(Tron1Work<20, 120, true>);
         CU(e, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<B, 32, smem, s>>>(e->C, B, d_x0, d_x_ref, d_feet, d_H, d_f, d_A_aug, d_B_aug);
+        k<<<B, 32, smem, s>>>(e->C, B, d_x0, d_x_ref, d_feet, d_H, d_f, d_A_aug, d_B_aug, nullptr);
+    } else if (e->N == 50) {
+        // the 300 x 300 packed factor lives in a temporary global workspace (parity dump only)
+        using W50 = Tron1Work<50, 300, false>;
+        double* ws = nullptr;
+        if (cudaMalloc(&ws, sizeof(double) * W50::PKN * (size_t)B) != cudaSuccess) { cudaGetLastError(); return set_err(e, MPC_B200_ENOMEM, "condense: workspace"); }
+        auto k = tron1_condense_kernel<50, false>;
+        size_t smem = sizeof(W50);
+        cudaError_t ce = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (ce == cudaSuccess) {
+            k<<<B, 32, smem, s>>>(e->C, B, d_x0, d_x_ref, d_feet, d_H, d_f, d_A_aug, d_B_aug, ws);
+            ce = cudaGetLastError();
+            if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+        }
+        cudaFree(ws);
+        if (ce != cudaSuccess) return set_err(e, MPC_B200_ECUDA, "condense<50>", ce);
     } else return set_err(e, MPC_B200_EINVAL, "unsupported horizon");
     CU(e, cudaGetLastError());
     e->launches++;

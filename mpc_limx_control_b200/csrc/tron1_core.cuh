@@ -77,14 +77,19 @@ MPC_HD void gait_contact(const Tron1Const& P, int iter, int& left_stance, int& r
 // N_ = horizon, NC_ = capacity in compact decision variables (3 per stance foot-step).
 // NC_ = 3N serves gaits with one stance foot per step (the reference's alternating gait),
 // NC_ = 6N serves double support; the kernel wrapper routes instances by their actual size.
-template <int N_, int NC_>
+// AINL_ = the packed factor lives inside the struct (shared memory); false = the wrapper points S.A at
+// external storage (global memory) -- needed when (NC+1)(NC+2)/2 doubles exceed shared memory (N = 50
+// double support: 364 KB).
+template <int N_, int NC_, bool AINL_ = true>
 struct Tron1Work {
     static constexpr int N = N_;
     static constexpr int NC = NC_;
+    static constexpr bool AINL = AINL_;
     static constexpr int NS = 2 * N;     // foot-steps
     static constexpr int NV = 6 * N;     // decision variables (full layout)
     static constexpr int PKN = (NC + 1) * (NC + 2) / 2;  // packed lower triangle incl. rhs row
-    double A[PKN];          // packed reduced Hessian / Cholesky factor; row nc holds the rhs
+    double* A;              // packed reduced Hessian / Cholesky factor; row nc holds the rhs
+    double Astore[AINL ? PKN : 2];
     double dinv[NC];        // 1 / L_kk
     double w[NC], z[NC], y[NC];   // compact solve vector, ADMM iterates
     double W[N * 18];       // W[k][foot] 3x3 row-major:  Iw_k^-1 [r]x

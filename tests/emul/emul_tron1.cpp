@@ -25,6 +25,7 @@ static int run_solve_nc(const Tron1Const& P, const double* x0, const double* xre
                         const uint8_t* contact, double* forces, int* iters) {
     using Work = Tron1Work<N, NC>;
     auto* S = new Work();
+    S->A = S->Astore;
     S->x0 = x0;
     S->feet = feet;
     for (int s = 0; s < 2 * N; ++s) S->contact[s] = contact[s] ? 1 : 0;
@@ -52,6 +53,7 @@ static void run_dump(const Tron1Const& P, const double* x0, const double* xref, 
                      double* H, double* f, double* A_aug, double* B_aug) {
     using Work = Tron1Work<N, 6 * N>;
     auto* S = new Work();
+    S->A = S->Astore;
     S->x0 = x0;
     S->feet = feet;
     for (int s = 0; s < 2 * N; ++s) S->contact[s] = 1;
@@ -79,6 +81,7 @@ template <int N, int NC>
 static int run_rollout(const Tron1Const& P, int steps, double* x, double oy, double vx, int it0, double* u_traj, int* iters) {
     using Work = Tron1Work<N, NC>;
     auto* S = new Work();
+    S->A = S->Astore;
     double feet[6], xr[13 * (N + 1)];
     S->x0 = x;
     S->feet = feet;
@@ -124,6 +127,7 @@ int emul_tron1_solve(const mpc_b200_tron1_params* prm, int N, const double* x0, 
         case 4: return run_solve<4>(P, x0, xref, feet, contact, forces, iters);
         case 10: return run_solve<10>(P, x0, xref, feet, contact, forces, iters);
         case 20: return run_solve<20>(P, x0, xref, feet, contact, forces, iters);
+        case 50: return run_solve<50>(P, x0, xref, feet, contact, forces, iters);
         default: return -2;
     }
 }
@@ -136,6 +140,7 @@ int emul_tron1_dump(const mpc_b200_tron1_params* prm, int N, const double* x0, c
         case 4: run_dump<4>(P, x0, xref, feet, H, f, A_aug, B_aug); return 0;
         case 10: run_dump<10>(P, x0, xref, feet, H, f, A_aug, B_aug); return 0;
         case 20: run_dump<20>(P, x0, xref, feet, H, f, A_aug, B_aug); return 0;
+        case 50: run_dump<50>(P, x0, xref, feet, H, f, A_aug, B_aug); return 0;
         default: return -2;
     }
 }

@@ -31,9 +31,9 @@ def test_golden_cases(golden):
 @pytest.mark.parametrize("N,Ts,ltv,standing,scale,mu", [
     (10, 0.005, 0, False, 1, 0.5), (10, 0.005, 1, False, 1, 0.5), (20, 0.005, 1, True, 1, 0.5),
     (10, 0.05, 1, False, 3, 0.5), (10, 0.001, 1, False, 1, 0.5), (10, 0.02, 1, True, 8, 0.2),
-    (20, 0.05, 1, True, 6, 0.3), (4, 0.01, 1, True, 3, 0.5)])
+    (20, 0.05, 1, True, 6, 0.3), (4, 0.01, 1, True, 3, 0.5), (50, 0.005, 1, False, 1, 0.5), (50, 0.01, 1, True, 3, 0.4)])
 def test_random_vs_oracle(N, Ts, ltv, standing, scale, mu):
-    B = 10
+    B = 10 if N < 50 else 2       # N = 50: BASELINE config 4 (n = 150 / 300 variables)
     d = synth.tron1_batch(31, B, N, Ts, standing=standing)
     po = O.tron1_defaults(Ts=Ts, ltv=ltv, mu=mu); pe = E.default_params(Ts=Ts, ltv=ltv, mu=mu)
     for b in range(B):

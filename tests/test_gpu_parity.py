@@ -66,6 +66,8 @@ def test_golden_cases(torch_cuda, golden):
     (10, 0.02, 1, True, 8, 0.2, 48),       # friction pyramid heavily active
     (20, 0.005, 1, False, 1, 0.5, 21),     # config-3 horizon
     (20, 0.05, 1, True, 6, 0.3, 16),       # N=20 stress
+    (50, 0.005, 1, False, 1, 0.5, 5),      # config-4 horizon, single stance (n = 150, factor in shared memory)
+    (50, 0.01, 1, True, 3, 0.4, 3),        # config-4 horizon, double support (n = 300, factor in global memory)
 ])
 def test_batch_vs_oracle(torch_cuda, N, Ts, ltv, standing, scale, mu, B):
     torch = torch_cuda

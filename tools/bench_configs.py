@@ -77,6 +77,9 @@ if __name__ == "__main__":
     solve_config("3: B=65536 N=20 randomised (one GPU's worth of the 8-GPU shard = 8192)", 8192, 20, 1002)
     if not quick:
         solve_config("3f: B=65536 N=20 on one GPU", 65536, 20, 1002, reps=5)
+    solve_config("4: B=8192 N=50 long horizon, trot (n = 150, factor in shared memory)", 8192, 50, 1003, reps=3)
+    if not quick:
+        solve_config("4s: B=1024 N=50 long horizon, double support (n = 300, factor in global memory)", 1024, 50, 1003, standing=True, reps=2)
     rollout_config("5: closed loop, 2048 instances (16384/8 GPUs) x 1000 steps", 2048, 10, 100 if quick else 1000, 1004)
     if not quick:
         rollout_config("5f: closed loop, 16384 instances x 1000 steps on one GPU", 16384, 10, 1000, 1004)
