@@ -109,8 +109,7 @@ tron1_solve_kernel(const __grid_constant__ Tron1Const P, int B, const double* __
     Work& S = works[g.gid];
     S.x0 = st.x0 + g.gid * 13;
     S.feet = st.feet + g.gid * fstride;
-    if (Work::AINL) S.A = S.Astore;
-    else S.A = ext_A + ((size_t)blockIdx.x * IPC + g.gid) * Work::PKN;   // one slab per resident group
+    S.Aext = Work::AINL ? nullptr : ext_A + ((size_t)blockIdx.x * IPC + g.gid) * Work::PKN;   // one slab per resident group
     const double* xr_s = st.xr + g.gid * XR;
 
     auto load_contact = [&](int b) {   // fills S.contact, returns the compact size 3 * stance foot-steps
@@ -265,7 +264,7 @@ tron1_rollout_kernel(const __grid_constant__ Tron1Const P, int B, int steps, dou
     const int it0 = iter0[b];
     if ((it0 < 0) != STANDING) return;   // the other capacity class handles this instance
     Work& S = works[g.gid];
-    S.A = S.Astore;
+    S.Aext = nullptr;
     double* xs = st.x + g.gid * 14;
     double* fs = st.feet + g.gid * 6;
     double* xr = st.xr + g.gid * Stage::XR;
@@ -311,8 +310,7 @@ tron1_condense_kernel(const __grid_constant__ Tron1Const P, int B, const double*
     Work& S = *reinterpret_cast<Work*>(smem_raw);
     const int b = blockIdx.x;
     if (b >= B) return;
-    if (AINL) S.A = S.Astore;
-    else S.A = ext_A + (size_t)b * Work::PKN;
+    S.Aext = AINL ? nullptr : ext_A + (size_t)b * Work::PKN;
     GrpCuda<1> g;
     g.t = threadIdx.x;
     g.gid = 0;
@@ -329,7 +327,7 @@ tron1_condense_kernel(const __grid_constant__ Tron1Const P, int B, const double*
         double* Hb = H + (size_t)b * n * n;
         for (int idx = g.t; idx < n * n; idx += 32) {
             int i = idx % n, j = idx / n;
-            Hb[idx] = i >= j ? S.A[MPC_PK(i, j)] : S.A[MPC_PK(j, i)];
+            Hb[idx] = i >= j ? S.Ap()[MPC_PK(i, j)] : S.Ap()[MPC_PK(j, i)];
         }
     }
     if (f) for (int i = g.t; i < n; i += 32) f[(size_t)b * n + i] = S.f[i];

@@ -88,8 +88,8 @@ struct Tron1Work {
     static constexpr int NS = 2 * N;     // foot-steps
     static constexpr int NV = 6 * N;     // decision variables (full layout)
     static constexpr int PKN = (NC + 1) * (NC + 2) / 2;  // packed lower triangle incl. rhs row
-    double* A;              // packed reduced Hessian / Cholesky factor; row nc holds the rhs
-    double Astore[AINL ? PKN : 2];
+    double* Aext;           // external packed factor storage (only used when !AINL)
+    double Astore[AINL ? PKN : 2];   // packed reduced Hessian / Cholesky factor; row nc holds the rhs
     double dinv[NC];        // 1 / L_kk
     double w[NC], z[NC], y[NC];   // compact solve vector, ADMM iterates
     double W[N * 18];       // W[k][foot] 3x3 row-major:  Iw_k^-1 [r]x
@@ -112,6 +112,8 @@ struct Tron1Work {
     long long t_last;
 #endif
     MPC_HD double* tau() { return adj; }
+    // address of the packed factor: a compile-time offset for the shared-memory case, a pointer otherwise
+    MPC_HD double* Ap() { if constexpr (AINL) return Astore; else return Aext; }
 };
 
 #define MPC_PK(i, j) ((i) * ((i) + 1) / 2 + (j))
@@ -421,7 +423,7 @@ MPC_HD void build_hessian(const Tron1Const& P, WK& S, double rho, bool use_face,
                 for (int r = 0; r < 3; ++r)
                     for (int c = 0; c < 3; ++c) {
                         if (sa == sb && c > r) continue;
-                        S.A[MPC_PK(ra + r, cb + c)] = T[r * 3 + c];
+                        S.Ap()[MPC_PK(ra + r, cb + c)] = T[r * 3 + c];
                     }
             }
         }
@@ -441,7 +443,7 @@ template <class WK, class G>
 __device__ __noinline__ bool cholesky_regs(WK& S, const G& g) {
     constexpr int NC = WK::NC;
     const int n = S.nc, t = g.tid();
-    double* A = S.A;
+    double* A = S.Ap();
     double a[NC];
     const bool row = t <= n;
     const double* mine = A + MPC_PK(t, 0);
@@ -488,7 +490,7 @@ template <class WK, class G>
 __device__ __noinline__ void forward_regs(WK& S, const G& g) {
     constexpr int NC = WK::NC;
     const int n = S.nc, t = g.tid();
-    double* A = S.A;
+    double* A = S.Ap();
     double y = (t < n) ? S.w[t] : 0.0;
 #pragma unroll
     for (int k = 0; k < NC; ++k) {
@@ -508,7 +510,7 @@ template <class WK, class G>
 __device__ __noinline__ void backward_regs(WK& S, const G& g) {
     constexpr int NC = WK::NC;
     const int n = S.nc, t = g.tid();
-    const double* A = S.A;
+    const double* A = S.Ap();
     double y = (t < n) ? A[MPC_PK(n, t)] : 0.0;
     if (G::kThreads == 32) {
 #pragma unroll
@@ -539,7 +541,7 @@ template <class WK, class G>
 MPC_HD bool cholesky_with_rhs(WK& S, const G& g) {
     [[maybe_unused]] constexpr int N = WK::N;
     const int n = S.nc;
-    double* A = S.A;
+    double* A = S.Ap();
     if (g.tid() == 0) S.flag = 0;
     g.sync();
     for (int k = 0; k < n; ++k) {
@@ -571,7 +573,7 @@ template <class WK, class G>
 MPC_HD void backward_solve(WK& S, const G& g) {
     [[maybe_unused]] constexpr int N = WK::N;
     const int n = S.nc;
-    double* A = S.A;
+    double* A = S.Ap();
     for (int i = g.tid(); i < n; i += g.size()) S.w[i] = A[MPC_PK(n, i)];
     g.sync();
     for (int k = n - 1; k >= 0; --k) {
@@ -589,7 +591,7 @@ template <class WK, class G>
 MPC_HD void forward_solve(WK& S, const G& g) {
     [[maybe_unused]] constexpr int N = WK::N;
     const int n = S.nc;
-    double* A = S.A;
+    double* A = S.Ap();
     for (int k = 0; k < n; ++k) {
         double yk = S.w[k] * S.dinv[k];
         g.sync();
@@ -657,12 +659,12 @@ MPC_HD bool face_solve(const Tron1Const& P, WK& S, const G& g) {
         if (!S.contact[s]) continue;
         FaceZ Z = face_basis(P.mu, S.ax[s], S.ay[s], S.zt[s]);
         const double* g0 = any_fixed ? S.g + 3 * s : S.f + 3 * s;
-        double* rhs = S.A + MPC_PK(n, 3 * S.cidx[s]);
+        double* rhs = S.Ap() + MPC_PK(n, 3 * S.cidx[s]);
         rhs[0] = -Z.fx * g0[0];
         rhs[1] = -Z.fy * g0[1];
         rhs[2] = -Z.fz * (Z.mx * g0[0] + Z.my * g0[1] + g0[2]);
     }
-    if (g.tid() == 0) S.A[MPC_PK(n, n)] = 1.0;
+    if (g.tid() == 0) S.Ap()[MPC_PK(n, n)] = 1.0;
     g.sync();
     MPC_TICK(S, g, 6);
     bool ok;
@@ -835,7 +837,7 @@ MPC_HD int solve_instance(const Tron1Const& P, WK& S, const double* xref, const 
     const int n = S.nc;
     double hmax = 0.0;
     build_hessian<WK>(P, S, 0.0, false, g);
-    for (int i = 0; i < n; ++i) hmax = S.A[MPC_PK(i, i)] > hmax ? S.A[MPC_PK(i, i)] : hmax;
+    for (int i = 0; i < n; ++i) hmax = S.Ap()[MPC_PK(i, i)] > hmax ? S.Ap()[MPC_PK(i, i)] : hmax;
     g.sync();
     const double rho = sqrt(2.0 * P.r * hmax * 4.0);
     // start from the projection of the last face solution
@@ -853,7 +855,7 @@ MPC_HD int solve_instance(const Tron1Const& P, WK& S, const double* xref, const 
         ++iters;
         if (!have_factor) {
             build_hessian<WK>(P, S, rho, false, g);
-            for (int i = g.tid(); i <= n; i += g.size()) S.A[MPC_PK(n, i)] = (i == n) ? 1.0 : 0.0;
+            for (int i = g.tid(); i <= n; i += g.size()) S.Ap()[MPC_PK(n, i)] = (i == n) ? 1.0 : 0.0;
             g.sync();
             bool okf;
 #if defined(__CUDA_ARCH__)
@@ -878,7 +880,7 @@ MPC_HD int solve_instance(const Tron1Const& P, WK& S, const double* xref, const 
 #endif
         {
             forward_solve<WK>(S, g);
-            for (int i = g.tid(); i < n; i += g.size()) S.A[MPC_PK(n, i)] = S.w[i];
+            for (int i = g.tid(); i < n; i += g.size()) S.Ap()[MPC_PK(n, i)] = S.w[i];
             g.sync();
             backward_solve<WK>(S, g);
         }

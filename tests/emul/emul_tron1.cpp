@@ -25,7 +25,7 @@ static int run_solve_nc(const Tron1Const& P, const double* x0, const double* xre
                         const uint8_t* contact, double* forces, int* iters) {
     using Work = Tron1Work<N, NC>;
     auto* S = new Work();
-    S->A = S->Astore;
+    S->Aext = nullptr;
     S->x0 = x0;
     S->feet = feet;
     for (int s = 0; s < 2 * N; ++s) S->contact[s] = contact[s] ? 1 : 0;
@@ -53,7 +53,7 @@ static void run_dump(const Tron1Const& P, const double* x0, const double* xref, 
                      double* H, double* f, double* A_aug, double* B_aug) {
     using Work = Tron1Work<N, 6 * N>;
     auto* S = new Work();
-    S->A = S->Astore;
+    S->Aext = nullptr;
     S->x0 = x0;
     S->feet = feet;
     for (int s = 0; s < 2 * N; ++s) S->contact[s] = 1;
@@ -63,7 +63,7 @@ static void run_dump(const Tron1Const& P, const double* x0, const double* xref, 
     const int n = 6 * N, p = 13 * (N + 1);
     if (H)
         for (int i = 0; i < n; ++i)
-            for (int j = 0; j <= i; ++j) { H[i + n * j] = S->A[MPC_PK(i, j)]; H[j + n * i] = S->A[MPC_PK(i, j)]; }
+            for (int j = 0; j <= i; ++j) { H[i + n * j] = S->Ap()[MPC_PK(i, j)]; H[j + n * i] = S->Ap()[MPC_PK(i, j)]; }
     if (f) std::memcpy(f, S->f, sizeof(double) * n);
     if (A_aug)
         for (int i = 0; i <= N; ++i)
@@ -81,7 +81,7 @@ template <int N, int NC>
 static int run_rollout(const Tron1Const& P, int steps, double* x, double oy, double vx, int it0, double* u_traj, int* iters) {
     using Work = Tron1Work<N, NC>;
     auto* S = new Work();
-    S->A = S->Astore;
+    S->Aext = nullptr;
     double feet[6], xr[13 * (N + 1)];
     S->x0 = x;
     S->feet = feet;
