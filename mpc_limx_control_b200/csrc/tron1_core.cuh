@@ -91,6 +91,7 @@ struct Tron1Work {
     double* Aext;           // external packed factor storage (only used when !AINL)
     double Astore[AINL ? PKN : 2];   // packed reduced Hessian / Cholesky factor; row nc holds the rhs
     double dinv[NC];        // 1 / L_kk
+    alignas(16) double colbuf[2 * (NC + 2)];   // double-buffered broadcast copy of the current factor column
     double w[NC], z[NC], y[NC];   // compact solve vector, ADMM iterates
     double W[N * 18];       // W[k][foot] 3x3 row-major:  Iw_k^-1 [r]x
     double cs[N * 2];       // cos, sin of yaw_k
@@ -439,16 +440,17 @@ MPC_HD void build_hessian(const Tron1Const& P, WK& S, double rho, bool use_face,
 // trailing update reads column k by uniform-address (broadcast) loads.  Static indexing keeps the row
 // in registers; `k < n` / `j < n` predicates are group-uniform.  Result layout == generic path:
 // packed L in S.A, 1/L_kk in S.dinv, L^-1 rhs in row nc.
-template <class WK, class G>
-__device__ __noinline__ bool cholesky_regs(WK& S, const G& g) {
+// FULL = (nc == NC): the common case, compiled without the per-element `j < n` predicates.
+template <class WK, class G, bool FULL>
+__device__ __forceinline__ bool cholesky_regs_body(WK& S, const G& g) {
     constexpr int NC = WK::NC;
-    const int n = S.nc, t = g.tid();
+    const int n = FULL ? NC : S.nc, t = g.tid();
     double* A = S.Ap();
     double a[NC];
     const bool row = t <= n;
     const double* mine = A + MPC_PK(t, 0);
 #pragma unroll
-    for (int j = 0; j < NC; ++j) a[j] = (row && j < n && (j <= t || t == n)) ? mine[j] : 0.0;
+    for (int j = 0; j < NC; ++j) a[j] = (row && (FULL || j < n) && (j <= t || t == n)) ? mine[j] : 0.0;
     bool ok = true;
     // `piv` carries the next pivot candidate: after column k every thread forms a[k+1] - l*l from its own
     // registers; only the owner of row k+1 holds the true value, and it is the one the shuffle reads.
@@ -460,7 +462,7 @@ __device__ __noinline__ bool cholesky_regs(WK& S, const G& g) {
     }
 #pragma unroll
     for (int k = 0; k < NC; ++k) {
-        if (k < n) {
+        if (FULL || k < n) {
             double d;
             if (G::kThreads == 32) d = __shfl_sync(0xffffffffu, piv, k);
             else d = S.w[k];
@@ -468,57 +470,89 @@ __device__ __noinline__ bool cholesky_regs(WK& S, const G& g) {
             const double rs = rsqrt(d);
             const double l = a[k] * rs;
             if (k + 1 < NC) piv = a[k + 1 < NC ? k + 1 : k] - l * l;
-            if (row && t > k) A[MPC_PK(t, k)] = l;
+            // column k is published twice: in the packed factor (kept for the solves) and in a contiguous,
+            // double-buffered broadcast array that the trailing update reads with 128-bit loads
+            double* cb = S.colbuf + (k & 1) * (NC + 2);
+            if (row && t > k) { A[MPC_PK(t, k)] = l; cb[t] = l; }
             if (t == k) S.dinv[k] = rs;
             // the owner of row k+1 publishes the next pivot together with its column entry: one
             // barrier per column covers both
             if (G::kThreads != 32 && t == k + 1 && k + 1 < NC) S.w[k + 1] = piv;
             g.sync();
-            const double* col = A;   // column k entries L[j][k] live at PK(j,k)
+            int j = k + 1;
+            if ((j & 1) && j < NC) { if (FULL || j < n) a[j] -= l * cb[j]; ++j; }
 #pragma unroll
-            for (int j = k + 1; j < NC; ++j)
-                if (j < n) a[j] -= l * col[MPC_PK(j, k)];
+            for (; j + 1 < NC; j += 2) {
+                if (FULL || j < n) {   // nc is a multiple of 3 and j even: both elements lie inside or the pair is cut
+                    const double2 c2 = *reinterpret_cast<const double2*>(cb + j);
+                    a[j] -= l * c2.x;
+                    if (FULL || j + 1 < n) a[j + 1] -= l * c2.y;
+                }
+            }
+            if (j < NC && (FULL || j < n)) a[j] -= l * cb[j];
         }
     }
     g.sync();
     return ok;
 }
 
+template <class WK, class G>
+__device__ __noinline__ bool cholesky_regs(WK& S, const G& g) {
+    if (S.nc == WK::NC) return cholesky_regs_body<WK, G, true>(S, g);
+    return cholesky_regs_body<WK, G, false>(S, g);
+}
+
 // forward solve L y = b (b in S.w) for one-warp groups; y goes to row nc of the packed factor, which is
 // where backward_regs expects it.  Column access A[PK(i,k)] over i is bank-conflict free.
-template <class WK, class G>
-__device__ __noinline__ void forward_regs(WK& S, const G& g) {
+// The L entries each lane needs do not depend on the recurrence, so they are loaded up front and the
+// loop body is shuffle -> multiply -> fma only.
+template <class WK, class G, bool FULL>
+__device__ __forceinline__ void forward_regs_body(WK& S, const G& g) {
     constexpr int NC = WK::NC;
-    const int n = S.nc, t = g.tid();
+    const int n = FULL ? NC : S.nc, t = g.tid();
     double* A = S.Ap();
     double y = (t < n) ? S.w[t] : 0.0;
+    const double di = (t < n) ? S.dinv[t] : 0.0;
+    double lrow[NC];
+    const double* mine = A + MPC_PK(t < n ? t : 0, 0);
+#pragma unroll
+    for (int k = 0; k < NC; ++k) lrow[k] = (t < n && k < t) ? mine[k] : 0.0;
 #pragma unroll
     for (int k = 0; k < NC; ++k) {
-        if (k < n) {
-            const double yk = __shfl_sync(0xffffffffu, y, k) * S.dinv[k];
-            if (t > k && t < n) y -= A[MPC_PK(t, k)] * yk;
-            if (t == k) y = yk;
+        if (FULL || k < n) {
+            if (t == k) y *= di;                       // y_k is final once all columns < k are applied
+            const double yk = __shfl_sync(0xffffffffu, y, k);
+            if (t > k) y -= lrow[k] * yk;
         }
     }
     if (t < n) A[MPC_PK(n, t)] = y;
     g.sync();
 }
+template <class WK, class G>
+__device__ __noinline__ void forward_regs(WK& S, const G& g) {
+    if (S.nc == WK::NC) forward_regs_body<WK, G, true>(S, g);
+    else forward_regs_body<WK, G, false>(S, g);
+}
 
 // backward solve L' x = y with y_i held by thread i; x_k is broadcast by shuffle (one warp) or through
-// shared memory (one barrier per step)
-template <class WK, class G>
-__device__ __noinline__ void backward_regs(WK& S, const G& g) {
+// shared memory (one barrier per step).  Lane t needs column t of L (L[k][t], k > t): loaded up front.
+template <class WK, class G, bool FULL>
+__device__ __forceinline__ void backward_regs_body(WK& S, const G& g) {
     constexpr int NC = WK::NC;
-    const int n = S.nc, t = g.tid();
+    const int n = FULL ? NC : S.nc, t = g.tid();
     const double* A = S.Ap();
     double y = (t < n) ? A[MPC_PK(n, t)] : 0.0;
     if (G::kThreads == 32) {
+        const double di = (t < n) ? S.dinv[t] : 0.0;
+        double lcol[NC];
+#pragma unroll
+        for (int k = 0; k < NC; ++k) lcol[k] = (k < n && t < k) ? A[MPC_PK(k, t)] : 0.0;
 #pragma unroll
         for (int k = NC - 1; k >= 0; --k) {
-            if (k < n) {
-                const double xk = __shfl_sync(0xffffffffu, y, k) * S.dinv[k];
-                if (t < k) y -= A[MPC_PK(k, t)] * xk;
-                if (t == k) y = xk;
+            if (FULL || k < n) {
+                if (t == k) y *= di;
+                const double xk = __shfl_sync(0xffffffffu, y, k);
+                if (t < k) y -= lcol[k] * xk;
             }
         }
         if (t < n) S.w[t] = y;
@@ -532,6 +566,11 @@ __device__ __noinline__ void backward_regs(WK& S, const G& g) {
         }
         g.sync();
     }
+}
+template <class WK, class G>
+__device__ __noinline__ void backward_regs(WK& S, const G& g) {
+    if (S.nc == WK::NC) backward_regs_body<WK, G, true>(S, g);
+    else backward_regs_body<WK, G, false>(S, g);
 }
 #endif
 
