@@ -172,6 +172,7 @@ tron1_solve_kernel(const __grid_constant__ Tron1Const P, int B, const double* __
             for (int i = threadIdx.x; i < valid * 13; i += blockDim.x) st.x0[i] = g0[i];
             for (int i = threadIdx.x; i < valid * fstride; i += blockDim.x) st.feet[i] = gf[i];
         }
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the overflow grid may queue up behind us
         // the contact schedule is evaluated while the copies are in flight
         const bool mine = g.gid < valid;
         const int b = first + g.gid;
@@ -189,6 +190,9 @@ tron1_solve_kernel(const __grid_constant__ Tron1Const P, int B, const double* __
         }
         finish(b);
     } else {
+        // launched with programmatic stream serialisation: this grid may start while the DIRECT grid
+        // drains; everything it reads is produced by that grid, so wait for its completion first
+        asm volatile("griddepcontrol.wait;" ::: "memory");
         // ovf_count[0] = list length, ovf_count[1] = CTAs that have read it; the last reader clears both
         // so the next call starts from zero without a memset (calls of one engine never overlap)
         __shared__ int s_count;
@@ -435,8 +439,16 @@ static int launch_solve(mpc_b200_engine* e, int B, const double* x0, const doubl
     int grid_l = (B + IPC_L - 1) / IPC_L;
     if (grid_l > e->num_sms * 2) grid_l = e->num_sms * 2;
     if (!AINL_L && grid_l * IPC_L > e->extA_slabs) grid_l = e->extA_slabs / IPC_L;
-    kl<<<grid_l, 32 * WPI_L * IPC_L, smem_l, s>>>(e->C, B, x0, xref, feet, contact, iter, forces, status, iters,
-                                                  ovf_list, ovf_count, AINL_L ? nullptr : e->d_extA);
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid_l); cfg.blockDim = dim3(32 * WPI_L * IPC_L); cfg.dynamicSmemBytes = smem_l; cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        double* ext = AINL_L ? nullptr : e->d_extA;
+        CU(e, cudaLaunchKernelEx(&cfg, kl, e->C, B, x0, xref, feet, contact, iter, forces, status, iters, ovf_list, ovf_count, ext));
+    }
     CU(e, cudaGetLastError());
     e->launches += 2;
     return MPC_B200_OK;
