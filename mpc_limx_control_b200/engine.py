@@ -87,6 +87,33 @@ class Engine:
         _capi.check(rc, self.h)
         return forces, status, iters
 
+    def bind_solve(self, x0, x_ref, feet, contact=None, it=None, forces=None, status=None, iters=None):
+        """Validate the tensors once and return a zero-overhead callable that issues exactly one
+        mpc_b200_tron1_solve_device call on torch's current stream (for hot loops: the Python-side
+        checks and pointer marshalling of solve() cost more than a 4096-instance batch takes on the GPU).
+        The tensors must stay alive and unmoved while the callable is used."""
+        B, N = x0.shape[0], self.N
+        self._check_dev(x0, torch.float64, B * 13, "x0")
+        self._check_dev(x_ref, torch.float64, B * 13 * (N + 1), "x_ref")
+        self._check_dev(feet, torch.float64, B * (6 * N if self.per_step_feet else 6), "feet")
+        if contact is not None:
+            self._check_dev(contact, torch.uint8, B * 2 * N, "contact")
+        if it is not None:
+            self._check_dev(it, torch.int32, B, "iter")
+        for t, dt, n, nm in ((forces, torch.float64, B * 6 * N, "forces"), (status, torch.int32, B, "status"), (iters, torch.int32, B, "iters")):
+            if t is not None:
+                self._check_dev(t, dt, n, nm)
+        args = (self.h, B, _ptr(x0), _ptr(x_ref), _ptr(feet), _ptr(contact), _ptr(it), _ptr(forces), _ptr(status), _ptr(iters),
+                self._stream())
+        fn = self.lib.mpc_b200_tron1_solve_device
+        keep = (x0, x_ref, feet, contact, it, forces, status, iters)
+
+        def call(_fn=fn, _args=args, _keep=keep):
+            rc = _fn(*_args)
+            if rc:
+                _capi.check(rc, self.h)
+        return call
+
     def condense(self, x0, x_ref, feet, want_pred=True):
         """Parity dump: H [B,n,n], f [B,n], A_aug [B,13(N+1),13], B_aug [B,13(N+1),n] as numpy,
         column-major per instance (returned arrays are indexed [b][row][col])."""
