@@ -753,7 +753,7 @@ MPC_HD bool check_optimality(const Tron1Const& P, WK& S, const G& g, bool& chang
             project_pyramid(P.mu, P.f_max, v, o, ax, ay, zt);
             for (int c = 0; c < 3; ++c) {
                 double d = fabs(S.u[3 * s + c] - o[c]);
-                r = d > r ? d : r;
+                r = (!(d <= r) && r == r) ? d : r;   // NaN-propagating max
                 double a = fabs(S.u[3 * s + c]);
                 um = a > um ? a : um;
             }
@@ -763,7 +763,7 @@ MPC_HD bool check_optimality(const Tron1Const& P, WK& S, const G& g, bool& chang
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
             double r2 = __shfl_xor_sync(0xffffffffu, r, off), u2 = __shfl_xor_sync(0xffffffffu, um, off);
-            r = r2 > r ? r2 : r;
+            r = (!(r2 <= r) && r == r) ? r2 : r;   // NaN-propagating max
             um = u2 > um ? u2 : um;
         }
         changed = __any_sync(0xffffffffu, ch);
@@ -783,7 +783,7 @@ MPC_HD bool check_optimality(const Tron1Const& P, WK& S, const G& g, bool& chang
             project_pyramid(P.mu, P.f_max, v, o, ax, ay, zt);
             for (int c = 0; c < 3; ++c) {
                 double d = fabs(S.u[3 * s + c] - o[c]);
-                r = d > r ? d : r;
+                r = (!(d <= r) && r == r) ? d : r;   // NaN-propagating max
                 double a = fabs(S.u[3 * s + c]);
                 um = a > um ? a : um;
             }
@@ -796,7 +796,7 @@ MPC_HD bool check_optimality(const Tron1Const& P, WK& S, const G& g, bool& chang
     double r = 0.0, um = 1.0;
     bool ch = false;
     for (int s = 0; s < 2 * N; ++s) {
-        r = S.res[s] > r ? S.res[s] : r;
+        r = (!(S.res[s] <= r) && r == r) ? S.res[s] : r;   // NaN-propagating max
         um = S.tau()[s] > um ? S.tau()[s] : um;
         if (S.contact[s]) ch |= (S.nax[s] != S.ax[s]) || (S.nay[s] != S.ay[s]) || (S.nzt[s] != S.zt[s]);
     }
@@ -857,6 +857,32 @@ MPC_HD int solve_instance(const Tron1Const& P, WK& S, const double* xref, const 
     [[maybe_unused]] constexpr int N = WK::N;
     setup_instance<WK>(P, S, xref, g, warm);
     iters = 0;
+    // non-finite inputs (NaN/inf state, reference or feet) poison f: report failure instead of iterating
+    // (a NaN would otherwise slip through the max-reductions of the optimality check)
+    // (a non-finite H is caught by the factorisation's pivot test)
+    bool bad;
+    {
+        double acc = 0.0;
+        for (int i = g.tid(); i < 6 * N; i += g.size()) acc += S.f[i] * 0.0;   // 0 unless f[i] is NaN/inf
+        bad = (acc != 0.0 || acc != acc);
+    }
+#if defined(__CUDA_ARCH__)
+    if constexpr (G::kThreads == 32) bad = __any_sync(0xffffffffu, bad);
+    else
+#endif
+    {
+        if (g.tid() == 0) S.flag = 0;
+        g.sync();
+        if (bad) S.flag = 1;
+        g.sync();
+        bad = S.flag != 0;
+        g.sync();
+    }
+    if (bad) {
+        for (int i = g.tid(); i < 6 * N; i += g.size()) S.u[i] = 0.0;
+        g.sync();
+        return ST_FAILED;
+    }
     if (S.nc == 0) {
         for (int i = g.tid(); i < 6 * N; i += g.size()) S.u[i] = 0.0;
         g.sync();

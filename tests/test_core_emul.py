@@ -116,3 +116,16 @@ def test_rollout_vs_oracle():
         assert np.abs(Ue - Uo).max() / max(1.0, np.abs(Uo).max()) < 1e-6
         assert np.abs(xe - xo).max() < 1e-8
         assert its >= steps
+
+
+def test_non_finite_input_reports_failure():
+    """NaN / inf in the state must surface as status 2 (never a silent 'solved'), SURVEY.md 8b error convention"""
+    N = 10
+    pe = E.default_params()
+    d = synth.tron1_batch(2, 2, N, 0.005)
+    c = O.contact_schedule(int(d["iter"][0]), N)
+    for bad in (np.nan, np.inf):
+        x0 = d["x0"][0].copy(); x0[9] = bad
+        xr = d["x_ref"][0].copy(); xr[:, 9] = bad
+        F, st, it = E.solve(pe, N, x0, xr, d["feet"][0], c)
+        assert st == 2

@@ -317,3 +317,23 @@ def test_host_paths_packed_and_pipelined(torch_cuda):
         # the device reference generator may differ from numpy's x_ref in the last bit (FMA) -> tiny tolerance
         assert np.abs(u0 - F[:, 0, :]).max() / max(1.0, np.abs(F).max()) < 1e-9
         eng.close()
+
+
+def test_non_finite_instance_is_isolated(torch_cuda):
+    """a NaN state poisons only its own instance: status 2 there, neighbours (same CTA) still certified"""
+    torch = torch_cuda
+    N, B, Ts = 10, 16, 0.005
+    d = synth.tron1_batch(4, B, N, Ts)
+    d["x0"][5, 9] = np.nan; d["x_ref"][5, :, 9] = np.nan
+    eng = make_engine(N, B, Ts=Ts)
+    t = to_dev(torch, d)
+    F, st, it = eng.solve(t["x0"], t["x_ref"], t["feet"], it=t["iter"])
+    torch.cuda.synchronize()
+    st = st.cpu().numpy(); F = F.cpu().numpy()
+    assert st[5] == 2 and (np.delete(st, 5) == 0).all()
+    po = O.tron1_defaults(Ts=Ts)
+    c_ref = np.stack([O.contact_schedule(int(i), N) for i in d["iter"]])
+    keep = [b for b in range(B) if b != 5]
+    Fo, so, _ = O.tron1_solve_batch(po, N, d["x0"][keep], d["x_ref"][keep], d["feet"][keep], c_ref[keep], nthreads=4)
+    assert np.abs(F[keep] - Fo).max() / max(1.0, np.abs(Fo).max()) < 1e-4
+    eng.close()
