@@ -129,3 +129,21 @@ def test_non_finite_input_reports_failure():
         xr = d["x_ref"][0].copy(); xr[:, 9] = bad
         F, st, it = E.solve(pe, N, x0, xr, d["feet"][0], c)
         assert st == 2
+
+
+def test_random_contact_patterns():
+    """arbitrary schedules: flight phases, mixed single/double support inside one horizon (n_c not 30/60)"""
+    N, Ts = 10, 0.01
+    rng = np.random.default_rng(5)
+    d = synth.tron1_batch(55, 12, N, Ts)
+    d["x0"][:, [0, 1, 6, 7, 8, 9, 10, 11]] *= 3
+    po = O.tron1_defaults(Ts=Ts); pe = E.default_params(Ts=Ts)
+    for b in range(12):
+        contact = (rng.random((N, 2)) < (0.3 + 0.05 * b)).astype(np.uint8)
+        c = O.tron1_condense(po, N, d["x0"][b], d["x_ref"][b], d["feet"][b], want_pred=False)
+        A, lbA, ubA, lb, ub = O.tron1_constraints(po, N, contact)
+        u, info = O.qp_solve(c["H"], c["f"], A, lbA, ubA, lb, ub)
+        F, st, it = E.solve(pe, N, d["x0"][b], d["x_ref"][b], d["feet"][b], contact)
+        assert st == 0 and info["status"] == 0
+        assert np.abs(F.reshape(-1) - u).max() / max(1.0, np.abs(u).max()) < 1e-6
+        assert np.all(F.reshape(N, 2, 3)[contact == 0] == 0.0)

@@ -337,3 +337,30 @@ def test_non_finite_instance_is_isolated(torch_cuda):
     Fo, so, _ = O.tron1_solve_batch(po, N, d["x0"][keep], d["x_ref"][keep], d["feet"][keep], c_ref[keep], nthreads=4)
     assert np.abs(F[keep] - Fo).max() / max(1.0, np.abs(Fo).max()) < 1e-4
     eng.close()
+
+
+@pytest.mark.parametrize("N", [10, 20])
+def test_random_contact_patterns(torch_cuda, N):
+    """arbitrary contact schedules (flight phases, mixed single/double support in one horizon): compact sizes
+    that are not the full 3N / 6N exercise the partial-size register paths and the capacity routing"""
+    torch = torch_cuda
+    B, Ts = 96, 0.01
+    rng = np.random.default_rng(6)
+    d = synth.tron1_batch(56, B, N, Ts)
+    d["x0"][:, [0, 1, 6, 7, 8, 9, 10, 11]] *= 3
+    contact = (rng.random((B, N, 2)) < rng.uniform(0.2, 0.95, (B, 1, 1))).astype(np.uint8)
+    contact[0] = 0; contact[1] = 1; contact[2, :, 0] = 1; contact[2, :, 1] = 0   # all swing / all stance / single stance
+    eng = make_engine(N, B, Ts=Ts)
+    t = to_dev(torch, d)
+    F, st, it = eng.solve(t["x0"], t["x_ref"], t["feet"], contact=torch.from_numpy(contact).cuda())
+    torch.cuda.synchronize()
+    F = F.cpu().numpy(); st = st.cpu().numpy()
+    assert (st == 0).all(), st
+    po = O.tron1_defaults(Ts=Ts)
+    Fo, so, _ = O.tron1_solve_batch(po, N, d["x0"], d["x_ref"], d["feet"], contact, nthreads=8)
+    assert (so == 0).all()
+    assert np.abs(F - Fo).max() / max(1.0, np.abs(Fo).max()) < 1e-4
+    assert np.all(F.reshape(B, N, 2, 3)[contact == 0] == 0.0)
+    nc = 3 * contact.reshape(B, -1).sum(1)
+    assert ((nc > 0) & (nc < 3 * N)).any() and ((nc > 3 * N) & (nc < 6 * N)).any()   # both partial classes present
+    eng.close()
