@@ -197,28 +197,30 @@ def run_gpu(args):
     sh = torch.empty(B, dtype=torch.int32).pin_memory()
     ih = torch.empty(B, dtype=torch.int32).pin_memory()
     Ke = min(500, max(10, K // 4))
+    from mpc_limx_control_b200.engine import bind_solve_host, bind_control_host
+    host_call = bind_solve_host(eng, pin["x0"], pin["x_ref"], pin["feet"], it=pin["iter"], forces=Fh, status=sh, iters=ih)
     for _ in range(max(3, W // 4)):
-        eng.solve_host(pin["x0"], pin["x_ref"], pin["feet"], it=pin["iter"], forces=Fh, status=sh, iters=ih)
+        host_call()
     barrier()
     t0 = time.perf_counter()
     for _ in range(Ke):
-        eng.solve_host(pin["x0"], pin["x_ref"], pin["feet"], it=pin["iter"], forces=Fh, status=sh, iters=ih)
+        host_call()      # one mpc_b200_tron1_solve_host: H2D, solve, D2H, sync (pinned host buffers)
     torch.cuda.synchronize()
     te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * B * Ke / float(te.item())
     # controller-shaped host call (command in, first-step force out: the reference mpcQP's own I/O)
-    from mpc_limx_control_b200.engine import control_host
     pin_c = {k: torch.from_numpy(d[k]).pin_memory() for k in ("omega_yaw", "velocity_x")}
     u0h = torch.empty((B, 6), dtype=torch.float64).pin_memory()
-    args_c = (pin["x0"].numpy(), pin_c["omega_yaw"].numpy(), pin_c["velocity_x"].numpy(), pin["feet"].numpy())
+    ctrl_call = bind_control_host(eng, pin["x0"], pin_c["omega_yaw"], pin_c["velocity_x"], pin["feet"], it=pin["iter"], u0=u0h,
+                                  status=sh, iters=ih)
     for _ in range(max(3, W // 4)):
-        control_host(eng, *args_c, it=pin["iter"].numpy(), u0=u0h.numpy(), status=sh.numpy(), iters=ih.numpy())
+        ctrl_call()
     barrier()
     t0 = time.perf_counter()
     for _ in range(Ke):
-        control_host(eng, *args_c, it=pin["iter"].numpy(), u0=u0h.numpy(), status=sh.numpy(), iters=ih.numpy())
+        ctrl_call()
     torch.cuda.synchronize()
     tc = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
@@ -236,10 +238,10 @@ def run_gpu(args):
     one = {k: torch.from_numpy(d[k][:1].copy()).pin_memory() for k in ("x0", "x_ref", "feet", "iter")}
     F1 = torch.empty((1, N, 6), dtype=torch.float64).pin_memory()
     s1 = torch.empty(1, dtype=torch.int32).pin_memory(); i1 = torch.empty(1, dtype=torch.int32).pin_memory()
-    a = [one["x0"].numpy(), one["x_ref"].numpy(), one["feet"].numpy(), one["iter"].numpy(), F1.numpy(), s1.numpy(), i1.numpy()]
+    one_call = bind_solve_host(eng, one["x0"], one["x_ref"], one["feet"], it=one["iter"], forces=F1, status=s1, iters=i1)
     for j in range(args.latency_calls + 200):
         t0 = time.perf_counter()
-        eng.solve_host(a[0], a[1], a[2], it=a[3], forces=a[4], status=a[5], iters=a[6])
+        one_call()       # host call -> forces on host
         if j >= 200:
             lat.append(time.perf_counter() - t0)
     lat = np.array(lat if lat else [float("nan")]) * 1e6
@@ -324,7 +326,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--latency-calls", type=int, default=2000)
+    ap.add_argument("--latency-calls", type=int, default=10000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -388,7 +388,7 @@ struct mpc_b200_engine {
     int32_t *d_iter = nullptr, *d_status = nullptr, *d_iters = nullptr;
     int32_t *d_ovf_list = nullptr, *d_ovf_count = nullptr;   // capacity-overflow routing: list, {length, readers} per slot
     double *d_oy = nullptr, *d_vx = nullptr, *d_u0 = nullptr; // controller-shaped entry: commands in, first-step force out
-    static constexpr int kPipe = 4;                          // chunks in flight in the host-buffer entry
+    static constexpr int kPipe = 8;                          // streams used by the host-buffer entry
     static constexpr int kSmallB = 64;                       // packed single-copy path below this batch size
     cudaStream_t pipe[kPipe] = {};
     unsigned char *h_small = nullptr, *d_small = nullptr;    // pinned / device staging of the packed path
@@ -683,9 +683,14 @@ static int solve_host_impl(mpc_b200_engine* e, int B, const double* x0, const do
         return MPC_B200_OK;
     }
     // ---- throughput path: chunks pipelined over kPipe streams (H2D / solve / D2H of different chunks overlap) --
-    // chunking pays only when the copies outweigh the per-call API overhead (~5 us per memcpy / launch)
+    // chunk so that each H2D is ~1.25 MB: on PCIe Gen5 hosts mid-size pinned copies (4-20 MB) were measured
+    // at half the rate of 1 MB copies (tools/pcie_probe.py), and copies of later chunks overlap the solve of
+    // earlier ones; never more chunks than streams, never chunks smaller than 512 instances
     const size_t bytes = (size_t)B * (cmd ? 172 + 56 : sizeof(double) * (13 + XR + fstride + 6 * (size_t)N));
-    const int nchunk = bytes >= (size_t)24 << 20 ? mpc_b200_engine::kPipe : (bytes >= (size_t)6 << 20 ? 2 : 1);
+    int nchunk = (int)((bytes + (size_t)1250000 - 1) / (size_t)1250000);
+    if (nchunk > mpc_b200_engine::kPipe) nchunk = mpc_b200_engine::kPipe;
+    if (nchunk > B / 512) nchunk = B / 512;
+    if (nchunk < 1) nchunk = 1;
     int chunk = (B + nchunk - 1) / nchunk;
     chunk = (chunk + 3) & ~3;   // chunk starts stay multiples of 4: CTA slices remain 16-byte aligned
     for (int c = 0, first = 0; first < B; ++c, first += chunk) {

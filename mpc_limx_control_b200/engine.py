@@ -206,6 +206,47 @@ def control_host(eng, x0, omega_yaw, velocity_x, feet, contact=None, it=None, u0
     return u0, status, iters
 
 
+def _host_ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, torch.Tensor):
+        assert a.device.type == "cpu" and a.is_contiguous()
+        return C.c_void_p(a.data_ptr())
+    assert a.flags["C_CONTIGUOUS"]
+    return C.c_void_p(a.ctypes.data)
+
+
+def bind_solve_host(eng, x0, x_ref, feet, contact=None, it=None, forces=None, status=None, iters=None):
+    """Pre-marshalled mpc_b200_tron1_solve_host call (buffers: contiguous float64/uint8/int32 numpy arrays or
+    CPU torch tensors, pinned recommended; they must stay alive and unmoved)."""
+    B = x0.shape[0]
+    args = (eng.h, B, _host_ptr(x0), _host_ptr(x_ref), _host_ptr(feet), _host_ptr(contact), _host_ptr(it), _host_ptr(forces),
+            _host_ptr(status), _host_ptr(iters))
+    fn = eng.lib.mpc_b200_tron1_solve_host
+    keep = (x0, x_ref, feet, contact, it, forces, status, iters)
+
+    def call(_fn=fn, _args=args, _keep=keep):
+        rc = _fn(*_args)
+        if rc:
+            _capi.check(rc, eng.h)
+    return call
+
+
+def bind_control_host(eng, x0, omega_yaw, velocity_x, feet, contact=None, it=None, u0=None, status=None, iters=None):
+    """Pre-marshalled mpc_b200_tron1_control_host call (see bind_solve_host)."""
+    B = x0.shape[0]
+    args = (eng.h, B, _host_ptr(x0), _host_ptr(omega_yaw), _host_ptr(velocity_x), _host_ptr(feet), _host_ptr(contact),
+            _host_ptr(it), _host_ptr(u0), _host_ptr(status), _host_ptr(iters))
+    fn = eng.lib.mpc_b200_tron1_control_host
+    keep = (x0, omega_yaw, velocity_x, feet, contact, it, u0, status, iters)
+
+    def call(_fn=fn, _args=args, _keep=keep):
+        rc = _fn(*_args)
+        if rc:
+            _capi.check(rc, eng.h)
+    return call
+
+
 def as_np_out(a):
     if isinstance(a, torch.Tensor):
         return a.numpy()

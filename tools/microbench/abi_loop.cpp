@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 #include "../../include/mpc_b200.h"
 int main(int argc, char** argv) {
@@ -43,6 +44,26 @@ int main(int argc, char** argv) {
     int bad = 0; for (int v : st) bad += v != 0;
     printf("B %6d: %.2f us/step on device (%.1f M solves/s), host enqueue %.2f us/step, uncertified %d\n", B, 1e3 * ms / steps,
            B * (double)steps / (ms * 1e-3) / 1e6, std::chrono::duration<double, std::micro>(t1 - t0).count() / steps, bad);
+    // host-buffer entry points with pinned memory (no Python in the loop)
+    double *hx0, *hxr, *hfeet, *hF, *hoy, *hvx, *hu0; int32_t *hit, *hst, *hits;
+    cudaHostAlloc((void**)&hx0, x0.size() * 8, 0); cudaHostAlloc((void**)&hxr, xr.size() * 8, 0); cudaHostAlloc((void**)&hfeet, feet.size() * 8, 0);
+    cudaHostAlloc((void**)&hF, 60 * 8 * (size_t)B, 0); cudaHostAlloc((void**)&hit, 4 * (size_t)B, 0); cudaHostAlloc((void**)&hst, 4 * (size_t)B, 0);
+    cudaHostAlloc((void**)&hits, 4 * (size_t)B, 0); cudaHostAlloc((void**)&hoy, 8 * (size_t)B, 0); cudaHostAlloc((void**)&hvx, 8 * (size_t)B, 0);
+    cudaHostAlloc((void**)&hu0, 48 * (size_t)B, 0);
+    memcpy(hx0, x0.data(), x0.size() * 8); memcpy(hxr, xr.data(), xr.size() * 8); memcpy(hfeet, feet.data(), feet.size() * 8);
+    memcpy(hit, it.data(), 4 * (size_t)B);
+    for (int b2 = 0; b2 < B; ++b2) { hoy[b2] = 0.1; hvx[b2] = 0.5; }
+    int hs = steps / 4 + 5;
+    for (int i = 0; i < 5; ++i) mpc_b200_tron1_solve_host(e, B, hx0, hxr, hfeet, nullptr, hit, hF, hst, hits);
+    t0 = std::chrono::steady_clock::now();
+    for (int i = 0; i < hs; ++i) mpc_b200_tron1_solve_host(e, B, hx0, hxr, hfeet, nullptr, hit, hF, hst, hits);
+    double us_full = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count() / hs;
+    for (int i = 0; i < 5; ++i) mpc_b200_tron1_control_host(e, B, hx0, hoy, hvx, hfeet, nullptr, hit, hu0, hst, hits);
+    t0 = std::chrono::steady_clock::now();
+    for (int i = 0; i < hs; ++i) mpc_b200_tron1_control_host(e, B, hx0, hoy, hvx, hfeet, nullptr, hit, hu0, hst, hits);
+    double us_ctl = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count() / hs;
+    printf("         solve_host %.1f us/call (%.1f M solves/s e2e)   control_host %.1f us/call (%.1f M solves/s e2e)\n", us_full,
+           B / us_full, us_ctl, B / us_ctl);
     mpc_b200_destroy(e);
     return 0;
 }
