@@ -93,7 +93,11 @@ tron1_solve_kernel(const __grid_constant__ Tron1Const P, int B, const double* __
                    const double* __restrict__ xref, const double* __restrict__ feet,
                    const uint8_t* __restrict__ contact, const int32_t* __restrict__ iter,
                    double* __restrict__ forces, int32_t* __restrict__ status, int32_t* __restrict__ iters,
-                   int32_t* __restrict__ ovf_list, int32_t* __restrict__ ovf_count, double* __restrict__ ext_A) {
+                   int32_t* __restrict__ ovf_list, int32_t* __restrict__ ovf_count, double* __restrict__ ext_A,
+                   const double* __restrict__ cmd_oy, const double* __restrict__ cmd_vx, int first_step_only) {
+    // cmd_oy/cmd_vx != nullptr: controller-shaped call -- x_ref is generated here from the staged state and
+    // the commanded yaw rate / forward velocity (include/mpcQP.h:74-97) instead of being read from HBM;
+    // first_step_only: write u_0 (6 doubles per instance, include/mpcQP.h:118) instead of the whole horizon
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using Stage = CtaStage<N, IPC>;
     using Work = Tron1Work<N, NC, AINL>;
@@ -131,6 +135,10 @@ tron1_solve_kernel(const __grid_constant__ Tron1Const P, int B, const double* __
     };
     auto finish = [&](int b) {
         int its = 0;
+        if (cmd_oy) {   // build the reference in shared memory (the staged x0 is already visible to this group)
+            make_reference(S.x0, cmd_oy[b], cmd_vx[b], P.Ts, N, const_cast<double*>(xr_s), g);
+            g.sync();
+        }
 #if defined(MPC_PHASE_TIMING)
         if (g.t == 0) { for (int i = 0; i < 16; ++i) S.prof[i] = 0; S.t_last = clock64(); }
         g.sync();
@@ -140,8 +148,12 @@ tron1_solve_kernel(const __grid_constant__ Tron1Const P, int B, const double* __
         MPC_TICK(S, g, 13);
         if (g.t == 0) for (int i = 0; i < 16; ++i) atomicAdd(&g_phase_cycles[i], (unsigned long long)S.prof[i]);
 #endif
-        double* out = forces + (size_t)b * 6 * N;
-        for (int i = g.t; i < 6 * N; i += g.size()) out[i] = S.u[i];
+        if (first_step_only) {
+            if (g.t < 6) forces[(size_t)b * 6 + g.t] = S.u[g.t];
+        } else {
+            double* out = forces + (size_t)b * 6 * N;
+            for (int i = g.t; i < 6 * N; i += g.size()) out[i] = S.u[i];
+        }
         if (g.t == 0) {
             if (status) status[b] = code;
             if (iters) iters[b] = its;
@@ -155,20 +167,20 @@ tron1_solve_kernel(const __grid_constant__ Tron1Const P, int B, const double* __
         const double* gx = xref + (size_t)first * XR;
         const double* g0 = x0 + (size_t)first * 13;
         const double* gf = feet + (size_t)first * fstride;
-        const uint32_t bx = (uint32_t)(valid * XR * sizeof(double));
+        const uint32_t bx = cmd_oy ? 0u : (uint32_t)(valid * XR * sizeof(double));
         const uint32_t b0 = (uint32_t)(valid * 13 * sizeof(double));
         const uint32_t bf = (uint32_t)(valid * fstride * sizeof(double));
-        const bool bulk = (((uintptr_t)gx | (uintptr_t)g0 | (uintptr_t)gf | bx | b0 | bf) & 15) == 0;
+        const bool bulk = (((cmd_oy ? (uintptr_t)0 : (uintptr_t)gx) | (uintptr_t)g0 | (uintptr_t)gf | bx | b0 | bf) & 15) == 0;
         if (bulk) {
             if (threadIdx.x == 0) {
                 mbar_init(&st.bar, 1);
                 mbar_expect_tx(&st.bar, bx + b0 + bf);
-                bulk_g2s(st.xr, gx, bx, &st.bar);
+                if (bx) bulk_g2s(st.xr, gx, bx, &st.bar);
                 bulk_g2s(st.x0, g0, b0, &st.bar);
                 bulk_g2s(st.feet, gf, bf, &st.bar);
             }
         } else {
-            for (int i = threadIdx.x; i < valid * XR; i += blockDim.x) st.xr[i] = gx[i];
+            if (!cmd_oy) for (int i = threadIdx.x; i < valid * XR; i += blockDim.x) st.xr[i] = gx[i];
             for (int i = threadIdx.x; i < valid * 13; i += blockDim.x) st.x0[i] = g0[i];
             for (int i = threadIdx.x; i < valid * fstride; i += blockDim.x) st.feet[i] = gf[i];
         }
@@ -207,7 +219,7 @@ tron1_solve_kernel(const __grid_constant__ Tron1Const P, int B, const double* __
             double* sx = st.xr + g.gid * XR;
             double* s0 = st.x0 + g.gid * 13;
             double* sf = st.feet + g.gid * fstride;
-            for (int i = g.t; i < XR; i += g.size()) sx[i] = xref[(size_t)b * XR + i];
+            if (!cmd_oy) for (int i = g.t; i < XR; i += g.size()) sx[i] = xref[(size_t)b * XR + i];
             for (int i = g.t; i < 13; i += g.size()) s0[i] = x0[(size_t)b * 13 + i];
             for (int i = g.t; i < fstride; i += g.size()) sf[i] = feet[(size_t)b * fstride + i];
             load_contact(b);
@@ -390,6 +402,7 @@ struct mpc_b200_engine {
     double *d_oy = nullptr, *d_vx = nullptr, *d_u0 = nullptr; // controller-shaped entry: commands in, first-step force out
     static constexpr int kPipe = 8;                          // streams used by the host-buffer entry
     static constexpr int kSmallB = 64;                       // packed single-copy path below this batch size
+    static constexpr int kZeroCopyB = 8;                     // below this the kernels read/write the pinned staging directly
     cudaStream_t pipe[kPipe] = {};
     unsigned char *h_small = nullptr, *d_small = nullptr;    // pinned / device staging of the packed path
     double* d_extA = nullptr;                                // global-memory factor slabs (N = 50 double support)
@@ -422,7 +435,8 @@ static size_t solve_smem_bytes() {
 template <int N, int WPI_S, int IPC_S, int MINB_S, int WPI_L, int IPC_L, bool AINL_L = true>
 static int launch_solve(mpc_b200_engine* e, int B, const double* x0, const double* xref, const double* feet,
                         const uint8_t* contact, const int32_t* iter, double* forces, int32_t* status,
-                        int32_t* iters, cudaStream_t s, int32_t* ovf_list, int32_t* ovf_count) {
+                        int32_t* iters, cudaStream_t s, int32_t* ovf_list, int32_t* ovf_count,
+                        const double* cmd_oy, const double* cmd_vx, int first_only) {
     auto ks = tron1_solve_kernel<N, 3 * N, WPI_S, IPC_S, MINB_S, false, true>;
     auto kl = tron1_solve_kernel<N, 6 * N, WPI_L, IPC_L, 1, true, AINL_L>;
     const size_t smem_s = ((sizeof(CtaStage<N, IPC_S>) + 15) & ~size_t(15)) + sizeof(Tron1Work<N, 3 * N, true>) * IPC_S;
@@ -434,7 +448,7 @@ static int launch_solve(mpc_b200_engine* e, int B, const double* x0, const doubl
         configured[e->device & 63] = true;
     }
     ks<<<(B + IPC_S - 1) / IPC_S, 32 * WPI_S * IPC_S, smem_s, s>>>(e->C, B, x0, xref, feet, contact, iter, forces, status,
-                                                                 iters, ovf_list, ovf_count, nullptr);
+                                                                 iters, ovf_list, ovf_count, nullptr, cmd_oy, cmd_vx, first_only);
     CU(e, cudaGetLastError());
     int grid_l = (B + IPC_L - 1) / IPC_L;
     if (grid_l > e->num_sms * 2) grid_l = e->num_sms * 2;
@@ -447,7 +461,8 @@ static int launch_solve(mpc_b200_engine* e, int B, const double* x0, const doubl
         at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
         double* ext = AINL_L ? nullptr : e->d_extA;
-        CU(e, cudaLaunchKernelEx(&cfg, kl, e->C, B, x0, xref, feet, contact, iter, forces, status, iters, ovf_list, ovf_count, ext));
+        CU(e, cudaLaunchKernelEx(&cfg, kl, e->C, B, x0, xref, feet, contact, iter, forces, status, iters, ovf_list, ovf_count, ext,
+                                 cmd_oy, cmd_vx, first_only));
     }
     CU(e, cudaGetLastError());
     e->launches += 2;
@@ -457,14 +472,15 @@ static int launch_solve(mpc_b200_engine* e, int B, const double* x0, const doubl
 // compiled configurations per horizon
 static int dispatch_solve(mpc_b200_engine* e, int B, const double* x0, const double* xref, const double* feet,
                           const uint8_t* contact, const int32_t* iter, double* forces, int32_t* status,
-                          int32_t* iters, cudaStream_t s, int slot = 0, int list_offset = 0) {
+                          int32_t* iters, cudaStream_t s, int slot = 0, int list_offset = 0,
+                          const double* cmd_oy = nullptr, const double* cmd_vx = nullptr, int first_only = 0) {
     if (B + list_offset > e->max_batch) return set_err(e, MPC_B200_ECAPACITY, "solve: B > max_batch");
     int32_t* ol = e->d_ovf_list + list_offset;
     int32_t* oc = e->d_ovf_count + 2 * slot;
     switch (e->N) {
-        case 10: return launch_solve<10, 1, 4, 4, 2, 2>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc);
-        case 20: return launch_solve<20, 2, 2, 2, 2, 2>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc);
-        case 50: return launch_solve<50, 8, 1, 1, 8, 1, false>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc);
+        case 10: return launch_solve<10, 1, 4, 4, 2, 2>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only);
+        case 20: return launch_solve<20, 2, 2, 2, 2, 2>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only);
+        case 50: return launch_solve<50, 8, 1, 1, 8, 1, false>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only);
         default: return set_err(e, MPC_B200_EINVAL, "unsupported horizon");
     }
 }
@@ -545,7 +561,7 @@ int mpc_b200_create(const mpc_b200_tron1_params* p, int horizon, int max_batch, 
         ok = cudaStreamCreateWithFlags(&e->pipe[i], cudaStreamNonBlocking) == cudaSuccess;
     // packed staging of the small-batch path: inputs and outputs of kSmallB instances, 16-byte aligned segments
     e->small_bytes = (size_t)mpc_b200_engine::kSmallB * (sizeof(double) * (13 + 13 * (N + 1) + fstride + 2 + 6 * N) + 2 * N + 16) + 1024;
-    ok = ok && cudaHostAlloc((void**)&e->h_small, e->small_bytes, cudaHostAllocDefault) == cudaSuccess &&
+    ok = ok && cudaHostAlloc((void**)&e->h_small, e->small_bytes, cudaHostAllocMapped) == cudaSuccess &&
          cudaMalloc((void**)&e->d_small, e->small_bytes) == cudaSuccess;
     e->num_sms = prop.multiProcessorCount;
     if (ok && horizon == 50) {   // double-support factor (301*302/2 doubles = 364 KB) does not fit shared memory
@@ -602,12 +618,6 @@ int mpc_b200_tron1_solve_device(mpc_b200_engine* e, int B, const double* d_x0, c
     return dispatch_solve(e, B, d_x0, d_x_ref, d_feet, d_contact, d_iter, d_forces, d_status, d_iters, (cudaStream_t)stream);
 }
 
-// first-step forces u_0 of every instance, packed [B][6]
-__global__ void gather_u0_kernel(int B, int N, const double* __restrict__ forces, double* __restrict__ u0) {
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx < B * 6) u0[idx] = forces[(size_t)(idx / 6) * 6 * N + idx % 6];
-}
-
 namespace {
 // packed layout of the small-batch path: every segment starts 16-byte aligned (TMA bulk copies)
 struct SmallLayout {
@@ -647,34 +657,25 @@ static int solve_host_impl(mpc_b200_engine* e, int B, const double* x0, const do
         // ---- latency path: pack on the host, ONE H2D, kernels, ONE D2H ------------------------------------
         const SmallLayout L = small_layout(B, N, fstride, contact != nullptr, cmd);
         unsigned char* h = e->h_small;
-        unsigned char* d = e->d_small;
+        // tiny batches: zero-copy -- the kernels read the inputs from, and write the results to, the mapped
+        // pinned staging buffer over PCIe (UVA: same pointer on both sides), which removes two memcpy launches
+        // from the single-solve latency path
+        const bool zc = B <= mpc_b200_engine::kZeroCopyB;
+        unsigned char* d = zc ? h : e->d_small;
         cudaStream_t s = e->stream;
         memcpy(h + L.x0, x0, sizeof(double) * 13 * B);
         if (!cmd) memcpy(h + L.xref, x_ref, sizeof(double) * XR * B);
         memcpy(h + L.feet, feet, sizeof(double) * fstride * B);
         if (cmd) { memcpy(h + L.oy, oy, sizeof(double) * B); memcpy(h + L.vx, vx, sizeof(double) * B); }
         if (contact) memcpy(h + L.sched, contact, (size_t)2 * N * B); else memcpy(h + L.sched, iter, sizeof(int32_t) * B);
-        CU(e, cudaMemcpyAsync(d, h, L.in_bytes, cudaMemcpyHostToDevice, s));
-        const double* dxr = (const double*)(d + L.xref);
-        double* dforces = (double*)(d + L.forces);
-        if (cmd) {
-            tron1_reference_kernel<<<(int)((XR * B + 255) / 256), 256, 0, s>>>(e->C, B, N, (const double*)(d + L.x0), (const double*)(d + L.oy),
-                                                                              (const double*)(d + L.vx), e->d_xref);
-            CU(e, cudaGetLastError());
-            e->launches++;
-            dxr = e->d_xref;
-            dforces = e->d_forces;
-        }
-        int rc = dispatch_solve(e, B, (const double*)(d + L.x0), dxr, (const double*)(d + L.feet),
+        if (!zc) CU(e, cudaMemcpyAsync(d, h, L.in_bytes, cudaMemcpyHostToDevice, s));
+        // controller-shaped call: the solve kernel builds x_ref itself and writes u_0 only (no extra launches)
+        int rc = dispatch_solve(e, B, (const double*)(d + L.x0), cmd ? nullptr : (const double*)(d + L.xref), (const double*)(d + L.feet),
                                 contact ? (const uint8_t*)(d + L.sched) : nullptr, contact ? nullptr : (const int32_t*)(d + L.sched),
-                                dforces, (int32_t*)(d + L.status), (int32_t*)(d + L.iters), s);
+                                cmd ? (double*)(d + L.u0) : (double*)(d + L.forces), (int32_t*)(d + L.status), (int32_t*)(d + L.iters), s,
+                                0, 0, cmd ? (const double*)(d + L.oy) : nullptr, cmd ? (const double*)(d + L.vx) : nullptr, cmd ? 1 : 0);
         if (rc) return rc;
-        if (cmd) {
-            gather_u0_kernel<<<(B * 6 + 127) / 128, 128, 0, s>>>(B, N, e->d_forces, (double*)(d + L.u0));
-            CU(e, cudaGetLastError());
-            e->launches++;
-        }
-        CU(e, cudaMemcpyAsync(h + L.in_bytes, d + L.in_bytes, L.total - L.in_bytes, cudaMemcpyDeviceToHost, s));
+        if (!zc) CU(e, cudaMemcpyAsync(h + L.in_bytes, d + L.in_bytes, L.total - L.in_bytes, cudaMemcpyDeviceToHost, s));
         CU(e, cudaStreamSynchronize(s));
         if (cmd) memcpy(forces_out, h + L.u0, sizeof(double) * 6 * B);
         else memcpy(forces_out, h + L.forces, sizeof(double) * 6 * N * B);
@@ -688,6 +689,7 @@ static int solve_host_impl(mpc_b200_engine* e, int B, const double* x0, const do
     // earlier ones; never more chunks than streams, never chunks smaller than 512 instances
     const size_t bytes = (size_t)B * (cmd ? 172 + 56 : sizeof(double) * (13 + XR + fstride + 6 * (size_t)N));
     int nchunk = (int)((bytes + (size_t)1250000 - 1) / (size_t)1250000);
+    if (cmd) nchunk = B >= 16384 ? 4 : (B >= 2048 ? 2 : 1);   // tiny transfers: split only to overlap copies with the solve
     if (nchunk > mpc_b200_engine::kPipe) nchunk = mpc_b200_engine::kPipe;
     if (nchunk > B / 512) nchunk = B / 512;
     if (nchunk < 1) nchunk = 1;
@@ -705,20 +707,13 @@ static int solve_host_impl(mpc_b200_engine* e, int B, const double* x0, const do
         if (cmd) {
             CU(e, cudaMemcpyAsync(e->d_oy + f, oy + f, sizeof(double) * nb, cudaMemcpyHostToDevice, s));
             CU(e, cudaMemcpyAsync(e->d_vx + f, vx + f, sizeof(double) * nb, cudaMemcpyHostToDevice, s));
-            int grid = (int)((XR * nb + 255) / 256);
-            if (grid > e->num_sms * 16) grid = e->num_sms * 16;
-            tron1_reference_kernel<<<grid, 256, 0, s>>>(e->C, nb, N, e->d_x0 + 13 * f, e->d_oy + f, e->d_vx + f, e->d_xref + XR * f);
-            CU(e, cudaGetLastError());
-            e->launches++;
         }
-        int rc = dispatch_solve(e, nb, e->d_x0 + 13 * f, e->d_xref + XR * f, e->d_feet + fstride * f,
+        int rc = dispatch_solve(e, nb, e->d_x0 + 13 * f, cmd ? nullptr : e->d_xref + XR * f, e->d_feet + fstride * f,
                                 contact ? e->d_contact + 2 * N * f : nullptr, contact ? nullptr : e->d_iter + f,
-                                e->d_forces + 6 * N * f, e->d_status + f, e->d_iters + f, s, 1 + c % mpc_b200_engine::kPipe, first);
+                                cmd ? e->d_u0 + 6 * f : e->d_forces + 6 * N * f, e->d_status + f, e->d_iters + f, s,
+                                1 + c % mpc_b200_engine::kPipe, first, cmd ? e->d_oy + f : nullptr, cmd ? e->d_vx + f : nullptr, cmd ? 1 : 0);
         if (rc) return rc;
         if (cmd) {
-            gather_u0_kernel<<<(nb * 6 + 255) / 256, 256, 0, s>>>(nb, N, e->d_forces + 6 * N * f, e->d_u0 + 6 * f);
-            CU(e, cudaGetLastError());
-            e->launches++;
             CU(e, cudaMemcpyAsync(forces_out + 6 * f, e->d_u0 + 6 * f, sizeof(double) * 6 * nb, cudaMemcpyDeviceToHost, s));
         } else {
             CU(e, cudaMemcpyAsync(forces_out + 6 * N * f, e->d_forces + 6 * N * f, sizeof(double) * 6 * N * nb, cudaMemcpyDeviceToHost, s));
