@@ -432,13 +432,13 @@ static size_t solve_smem_bytes() {
 }
 
 // small class (direct, TMA-staged) followed by the large class (indirect, overflow list)
-template <int N, int WPI_S, int IPC_S, int MINB_S, int WPI_L, int IPC_L, bool AINL_L = true>
+template <int N, int WPI_S, int IPC_S, int MINB_S, int WPI_L, int IPC_L, bool AINL_L = true, int MINB_L = 1>
 static int launch_solve(mpc_b200_engine* e, int B, const double* x0, const double* xref, const double* feet,
                         const uint8_t* contact, const int32_t* iter, double* forces, int32_t* status,
                         int32_t* iters, cudaStream_t s, int32_t* ovf_list, int32_t* ovf_count,
                         const double* cmd_oy, const double* cmd_vx, int first_only) {
     auto ks = tron1_solve_kernel<N, 3 * N, WPI_S, IPC_S, MINB_S, false, true>;
-    auto kl = tron1_solve_kernel<N, 6 * N, WPI_L, IPC_L, 1, true, AINL_L>;
+    auto kl = tron1_solve_kernel<N, 6 * N, WPI_L, IPC_L, MINB_L, true, AINL_L>;
     const size_t smem_s = ((sizeof(CtaStage<N, IPC_S>) + 15) & ~size_t(15)) + sizeof(Tron1Work<N, 3 * N, true>) * IPC_S;
     const size_t smem_l = ((sizeof(CtaStage<N, IPC_L>) + 15) & ~size_t(15)) + sizeof(Tron1Work<N, 6 * N, AINL_L>) * IPC_L;
     static bool configured[64] = {};
@@ -451,7 +451,7 @@ static int launch_solve(mpc_b200_engine* e, int B, const double* x0, const doubl
                                                                  iters, ovf_list, ovf_count, nullptr, cmd_oy, cmd_vx, first_only);
     CU(e, cudaGetLastError());
     int grid_l = (B + IPC_L - 1) / IPC_L;
-    if (grid_l > e->num_sms * 2) grid_l = e->num_sms * 2;
+    if (grid_l > e->num_sms * (MINB_L > 2 ? MINB_L : 2)) grid_l = e->num_sms * (MINB_L > 2 ? MINB_L : 2);
     if (!AINL_L && grid_l * IPC_L > e->extA_slabs) grid_l = e->extA_slabs / IPC_L;
     {
         cudaLaunchConfig_t cfg = {};
@@ -478,7 +478,7 @@ static int dispatch_solve(mpc_b200_engine* e, int B, const double* x0, const dou
     int32_t* ol = e->d_ovf_list + list_offset;
     int32_t* oc = e->d_ovf_count + 2 * slot;
     switch (e->N) {
-        case 10: return launch_solve<10, 1, 4, 4, 2, 2>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only);
+        case 10: return launch_solve<10, 1, 4, 4, 2, 2, true, 3>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only);
         case 20: return launch_solve<20, 2, 2, 2, 2, 2>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only);
         case 50: return launch_solve<50, 8, 1, 1, 8, 1, false>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only);
         default: return set_err(e, MPC_B200_EINVAL, "unsupported horizon");
