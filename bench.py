@@ -210,6 +210,21 @@ def run_gpu(args):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * B * Ke / float(te.item())
+    e2e_path = "zero-copy (kernel reads/writes the pinned host buffers over PCIe)" if eng.last_host_path() else "staged copies"
+    # the same call forced onto the staged-copy path (what a caller with pageable buffers gets), for comparison
+    eng.set_host_mode(Engine.HOST_STAGED)
+    for _ in range(3):
+        host_call()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(max(5, Ke // 4)):
+        host_call()
+    torch.cuda.synchronize()
+    ts_ = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ts_, op=dist.ReduceOp.MAX)
+    e2e_staged_value = world * B * max(5, Ke // 4) / float(ts_.item())
+    eng.set_host_mode(Engine.HOST_AUTO)
     # controller-shaped host call (command in, first-step force out: the reference mpcQP's own I/O)
     pin_c = {k: torch.from_numpy(d[k]).pin_memory() for k in ("omega_yaw", "velocity_x")}
     u0h = torch.empty((B, 6), dtype=torch.float64).pin_memory()
@@ -290,7 +305,8 @@ def run_gpu(args):
                    "parallelism": f"instance-sharded x{world}, no collective", "mean_iters": mean_iters, "unsolved": n_bad},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": B * (104 + 104 * (N + 1) + 48 + 4),
-                "d2h_bytes_per_step": B * (48 * N + 8), "steps": Ke},
+                "d2h_bytes_per_step": B * (48 * N + 8), "steps": Ke, "path": e2e_path,
+                "staged_copies_value": e2e_staged_value},
         "e2e_controller": {"value": e2e_ctrl_value, "unit": "solves/s", "h2d_bytes_per_step": B * (104 + 16 + 48 + 4),
                            "d2h_bytes_per_step": B * (48 + 8), "steps": Ke,
                            "what": "mpc_b200_tron1_control_host: state + (yaw-rate, vx) command + feet + gait clock in, "

@@ -99,10 +99,19 @@ int mpc_b200_tron1_solve_device(mpc_b200_engine *e, int B, const double *d_x0, c
                                 const double *d_feet, const uint8_t *d_contact, const int32_t *d_iter,
                                 double *d_forces, int32_t *d_status, int32_t *d_iters, void *stream);
 
-/* Same with HOST buffers (pinned recommended): H2D copies, solve, D2H copies, stream sync.
- * Large transfers (>= 6 MB per call) are split into chunks pipelined over several streams (copies overlap
- * the solve);
- * batches <= 64 take a packed single-copy path (one H2D, one D2H). */
+/* Same with HOST buffers.  Two data paths:
+ *   zero-copy  every buffer is pinned / registered (device-addressable under UVA): the solve kernel reads its
+ *              inputs from, and writes its results to, host memory directly (TMA bulk copies over PCIe per CTA,
+ *              overlapped with the solves of the other resident CTAs); no cudaMemcpy, one stream sync.
+ *   staged     pageable buffers: H2D copies, solve, D2H copies; large transfers are split into chunks
+ *              pipelined over several streams, batches <= 64 take a packed single-copy path.
+ * MPC_B200_HOST_AUTO (default) picks zero-copy whenever all buffers qualify. */
+#define MPC_B200_HOST_AUTO 0
+#define MPC_B200_HOST_STAGED 1
+#define MPC_B200_HOST_ZEROCOPY 2   /* fail with MPC_B200_EINVAL instead of falling back to staged copies */
+int mpc_b200_set_host_mode(mpc_b200_engine *e, int mode);
+/* data path the last host-buffer call took: 1 zero-copy, 0 staged */
+int mpc_b200_last_host_path(const mpc_b200_engine *e);
 int mpc_b200_tron1_solve_host(mpc_b200_engine *e, int B, const double *x0, const double *x_ref,
                               const double *feet, const uint8_t *contact, const int32_t *iter,
                               double *forces, int32_t *status, int32_t *iters);

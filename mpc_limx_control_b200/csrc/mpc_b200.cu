@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -63,6 +64,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 #if defined(MPC_PHASE_TIMING)
+__device__ unsigned long long g_cta_trace[3 * 16384];   // per CTA: start ns, end ns, SM id (profiling build only)
+extern "C" int mpc_b200_debug_cta_trace(unsigned long long* out, int n) {
+    return cudaMemcpyFromSymbol(out, g_cta_trace, sizeof(unsigned long long) * 3 * n) == cudaSuccess ? 0 : -3;
+}
+__device__ __forceinline__ unsigned long long gtime_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 __device__ unsigned long long g_phase_cycles[16];
 extern "C" int mpc_b200_debug_phase_cycles(unsigned long long* out, int reset) {
     if (out && cudaMemcpyFromSymbol(out, g_phase_cycles, sizeof(unsigned long long) * 16) != cudaSuccess) return -3;
@@ -107,6 +113,12 @@ tron1_solve_kernel(const __grid_constant__ Tron1Const P, int B, const double* __
     const int fstride = (P.per_step_feet && P.ltv) ? 6 * N : 6;
     constexpr int XR = Stage::XR;
 
+#if defined(MPC_PHASE_TIMING)
+    if (!INDIRECT && threadIdx.x == 0 && blockIdx.x < 16384) {
+        unsigned smid; asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+        g_cta_trace[3 * blockIdx.x] = gtime_ns(); g_cta_trace[3 * blockIdx.x + 2] = smid;
+    }
+#endif
     GrpCuda<WPI> g;
     g.t = threadIdx.x % (32 * WPI);
     g.gid = threadIdx.x / (32 * WPI);
@@ -158,6 +170,9 @@ tron1_solve_kernel(const __grid_constant__ Tron1Const P, int B, const double* __
             if (status) status[b] = code;
             if (iters) iters[b] = its;
         }
+#if defined(MPC_PHASE_TIMING)
+        if (!INDIRECT && g.t == 0 && blockIdx.x < 16384) atomicMax(&g_cta_trace[3 * blockIdx.x + 1], gtime_ns());
+#endif
     };
 
     if (!INDIRECT) {
@@ -408,6 +423,8 @@ struct mpc_b200_engine {
     double* d_extA = nullptr;                                // global-memory factor slabs (N = 50 double support)
     int extA_slabs = 0;
     size_t small_bytes = 0;
+    int host_mode = MPC_B200_HOST_AUTO;                      // how the host-buffer entry points move data
+    int last_host_path = 0;                                  // 1 = zero-copy, 0 = staged (for tests / bench)
     int num_sms = 148;
     int64_t launches = 0;
     std::string err;
@@ -478,7 +495,11 @@ static int dispatch_solve(mpc_b200_engine* e, int B, const double* x0, const dou
     int32_t* ol = e->d_ovf_list + list_offset;
     int32_t* oc = e->d_ovf_count + 2 * slot;
     switch (e->N) {
-        case 10: return launch_solve<10, 1, 4, 4, 2, 2, true, 3>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only);
+        case 10: {
+            static const int ipc = getenv("MPC_B200_IPC") ? atoi(getenv("MPC_B200_IPC")) : 4;
+            if (ipc == 2) return launch_solve<10, 1, 2, 8, 2, 2, true, 3>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only);
+            return launch_solve<10, 1, 4, 4, 2, 2, true, 3>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only);
+        }
         case 20: return launch_solve<20, 2, 2, 2, 2, 2>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only);
         case 50: return launch_solve<50, 8, 1, 1, 8, 1, false>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only);
         default: return set_err(e, MPC_B200_EINVAL, "unsupported horizon");
@@ -595,6 +616,12 @@ int mpc_b200_destroy(mpc_b200_engine* e) {
 }
 
 const char* mpc_b200_last_error(const mpc_b200_engine* e) { return e ? e->err.c_str() : ""; }
+int mpc_b200_set_host_mode(mpc_b200_engine* e, int mode) {
+    if (!e || mode < MPC_B200_HOST_AUTO || mode > MPC_B200_HOST_ZEROCOPY) return set_err(e, MPC_B200_EINVAL, "set_host_mode: bad mode");
+    e->host_mode = mode;
+    return MPC_B200_OK;
+}
+int mpc_b200_last_host_path(const mpc_b200_engine* e) { return e ? e->last_host_path : 0; }
 int64_t mpc_b200_launch_count(const mpc_b200_engine* e) { return e ? e->launches : 0; }
 
 int mpc_b200_contact_schedule_device(mpc_b200_engine* e, int B, const int32_t* d_iter, uint8_t* d_contact, void* stream) {
@@ -643,6 +670,15 @@ SmallLayout small_layout(int B, int N, size_t fstride, bool has_contact, bool cm
 }
 }  // namespace
 
+// Device view of a host pointer the GPU can address directly (cudaHostAlloc / cudaHostRegister / managed
+// memory under UVA); nullptr for pageable memory.
+static void* device_view(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (a.type != cudaMemoryTypeHost && a.type != cudaMemoryTypeManaged) return nullptr;
+    return a.devicePointer;
+}
+
 // shared implementation of the two host-buffer entry points.
 //   cmd == false: x_ref in, full horizon forces out (forces_out [B][N][6])
 //   cmd == true : (omega_yaw, velocity_x) in -> reference generated on the device (include/mpcQP.h:74-97),
@@ -653,6 +689,35 @@ static int solve_host_impl(mpc_b200_engine* e, int B, const double* x0, const do
     const int N = e->N;
     const size_t fstride = (e->C.per_step_feet && e->C.ltv) ? 6 * (size_t)N : 6;
     const size_t XR = 13 * (size_t)(N + 1);
+    e->last_host_path = 0;
+    if (e->host_mode != MPC_B200_HOST_STAGED) {
+        // ---- zero-copy path: when every caller buffer is pinned (device-addressable), the solve kernel
+        // reads its inputs straight from host memory (each CTA's slice arrives by TMA bulk copies over
+        // PCIe, exactly once) and writes forces / status straight back: the H2D and D2H transfers happen
+        // inside the kernel, CTA by CTA, overlapped with the solves of the other resident CTAs; no
+        // cudaMemcpy calls, no staging, one stream synchronise.
+        const void* a0 = device_view(x0);
+        const void* a1 = cmd ? device_view(oy) : device_view(x_ref);
+        const void* a2 = cmd ? device_view(vx) : a1;
+        const void* a3 = device_view(feet);
+        const void* a4 = contact ? device_view(contact) : device_view(iter);
+        void* o0 = device_view(forces_out);
+        void* o1 = status ? device_view(status) : nullptr;
+        void* o2 = iters ? device_view(iters) : nullptr;
+        if (a0 && a1 && a2 && a3 && a4 && o0 && (!status || o1) && (!iters || o2)) {
+            cudaStream_t s = e->stream;
+            int rc = dispatch_solve(e, B, (const double*)a0, cmd ? nullptr : (const double*)a1, (const double*)a3,
+                                    contact ? (const uint8_t*)a4 : nullptr, contact ? nullptr : (const int32_t*)a4,
+                                    (double*)o0, (int32_t*)o1, (int32_t*)o2, s, 0, 0,
+                                    cmd ? (const double*)a1 : nullptr, cmd ? (const double*)a2 : nullptr, cmd ? 1 : 0);
+            if (rc) return rc;
+            CU(e, cudaStreamSynchronize(s));
+            e->last_host_path = 1;
+            return MPC_B200_OK;
+        }
+        if (e->host_mode == MPC_B200_HOST_ZEROCOPY)
+            return set_err(e, MPC_B200_EINVAL, "host buffers are not device-addressable (pin them, or use MPC_B200_HOST_AUTO/STAGED)");
+    }
     if (B <= mpc_b200_engine::kSmallB) {
         // ---- latency path: pack on the host, ONE H2D, kernels, ONE D2H ------------------------------------
         const SmallLayout L = small_layout(B, N, fstride, contact != nullptr, cmd);

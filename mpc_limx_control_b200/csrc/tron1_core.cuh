@@ -91,7 +91,8 @@ struct Tron1Work {
     double* Aext;           // external packed factor storage (only used when !AINL)
     double Astore[AINL ? PKN : 2];   // packed reduced Hessian / Cholesky factor; row nc holds the rhs
     double dinv[NC];        // 1 / L_kk
-    alignas(16) double colbuf[2 * (NC + 2)];   // double-buffered broadcast copy of the current factor column
+    static constexpr int CBS = (NC + 4) & ~1;   // stride of one broadcast buffer (even: 16-byte aligned halves)
+    alignas(16) double colbuf[2 * CBS];   // double-buffered broadcast copy of the current pivot column
     double w[NC], z[NC], y[NC];   // compact solve vector, ADMM iterates
     double W[N * 18];       // W[k][foot] 3x3 row-major:  Iw_k^-1 [r]x
     double cs[N * 2];       // cos, sin of yaw_k
@@ -502,6 +503,117 @@ __device__ __noinline__ bool cholesky_regs(WK& S, const G& g) {
     return cholesky_regs_body<WK, G, false>(S, g);
 }
 
+// ---- device fast path of the active-face solve: Gauss-Jordan elimination of [A | b], ONE ROW PER THREAD ----
+// A (nc x nc, symmetric positive definite) arrives as the packed lower triangle, b as its row nc.  Thread t
+// keeps row t of the symmetric matrix in registers as a SLIDING WINDOW: at column k, w[p] = A[t][k + p].
+// Column k: every row publishes its column entry w[0] (by symmetry these are the pivot row's entries to the
+// right of the diagonal) at the RELATIVE index t - k of a double-buffered broadcast array, the pivot comes
+// from its owner by warp shuffle, and every row except the pivot row does  w[p-1] = w[p] - m c[p],
+// b -= m b_k  with m = w[0] / d_k.  Rows above the pivot are updated too (the Jordan half), so the solution
+// is simply x_t = b_t / d_t: no backward substitution and no stored factor.  Per-thread work equals the
+// trailing update of a row-per-thread Cholesky (lanes above the pivot would otherwise idle).
+// The shift makes the loop body independent of k, so the columns run in ROLLED loops (5 stages whose window
+// shrinks by NC/5 each): ~12x less code than the unrolled register Cholesky + backward solve it replaces --
+// the unrolled version spent 40 % of its time in instruction-cache misses (profiles/r1d).
+// Rows/columns >= nc are padded with the identity, so one code path serves every compact size.
+__device__ __forceinline__ double fast_rcp(double d) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));   // MUFU.RCP64H, relative error ~2^-23
+    // one third-order step: y (1 + e + e^2), e = 1 - d y  ->  relative error ~e^3 = 2^-69 (three dependent DFMAs)
+    const double e = fma(-d, y, 1.0);
+    const double p = fma(e, e, e);
+    return fma(y, p, y);
+}
+
+#ifndef MPC_GJ_STAGES
+#define MPC_GJ_STAGES 5
+#endif
+template <int W, int KS, class WK, class G>
+__device__ __forceinline__ void gj_stage(double (&w)[WK::NC], double& b, double& inv, double& myinv, bool& ok,
+                                         WK& S, const G& g, const int k0) {
+    // `inv` = 1 / d_k of the column about to be eliminated.  The loop is ROTATED: the reciprocal of the next
+    // pivot is started as soon as its candidate exists (own registers, before the barrier), so that its
+    // SHFL -> MUFU -> Newton chain overlaps the barrier, the broadcast loads and the W-1 row updates of the
+    // current column (the warp issues in order: without the rotation the chain and the updates serialise).
+    const int t = g.tid();
+#pragma unroll 1
+    for (int k = k0; k < k0 + KS; ++k) {
+        // pivot-to-pivot chain: inv_k -> next pivot candidate (one DFMA) -> SHFL -> MUFU -> 3 DFMA; everything else
+        // (the multiplier, the pivot-row select, the positivity test) is formed off that chain
+        const double w0m = (t == k) ? 0.0 : w[0];          // the pivot row only shifts
+        const double q = w0m * w[0];
+        const double piv = fma(-q, inv, w[W > 1 ? 1 : 0]);  // next pivot candidate (c[1] of row k+1 is its own w[0])
+        const double m = w0m * inv;
+        if (t == k) myinv = inv;
+        double* cb = S.colbuf + (k & 1) * WK::CBS;
+        if (t > k) cb[t - k] = w[0];
+        if (t == k) cb[0] = b;
+        if (G::kThreads != 32 && t == k + 1 && k + 1 < WK::NC) S.w[k + 1] = piv;
+        g.sync();
+        double d;
+        if (G::kThreads == 32) d = __shfl_sync(0xffffffffu, piv, (k + 1) & 31);
+        else d = S.w[k + 1 < WK::NC ? k + 1 : k];
+        if (k + 1 < WK::NC && !(d > 0.0)) ok = false;       // reported as a failed solve; the garbage that follows is discarded
+        inv = fast_rcp(d);
+        b -= m * cb[0];
+        if (W > 1) w[0] = w[W > 1 ? 1 : 0] - m * cb[1];
+#pragma unroll
+        for (int p = 2; p + 1 < W; p += 2) {
+            const double2 c2 = *reinterpret_cast<const double2*>(cb + p);
+            w[p - 1] = w[p] - m * c2.x;
+            w[p] = w[p + 1] - m * c2.y;
+        }
+        if (W > 2 && (W & 1)) w[W - 2] = w[W - 1] - m * cb[W - 1];
+    }
+}
+
+template <int K0, class WK, class G>
+__device__ __forceinline__ void gj_stages(double (&w)[WK::NC], double& b, double& inv, double& myinv, bool& ok,
+                                          WK& S, const G& g) {
+    constexpr int NC = WK::NC, KS = NC / MPC_GJ_STAGES;
+    static_assert(NC % MPC_GJ_STAGES == 0, "stage split");
+    if constexpr (K0 < NC) {
+        gj_stage<NC - K0, KS, WK, G>(w, b, inv, myinv, ok, S, g, K0);
+        gj_stages<K0 + KS, WK, G>(w, b, inv, myinv, ok, S, g);
+    }
+}
+
+// solves A x = b for the packed system of face_solve; x goes to S.w[0..nc).  false = not positive definite.
+template <class WK, class G>
+__device__ __noinline__ bool gj_solve_regs(WK& S, const G& g) {
+    constexpr int NC = WK::NC;
+    static_assert(G::kThreads >= NC, "one row per thread");
+    const int n = S.nc, t = g.tid();
+    const double* A = S.Ap();
+    double w[NC];
+    const bool row = t < n;
+    const double* rowp = A + MPC_PK(row ? t : 0, 0);    // A[t][j], j <= t
+    const double* colp = A + (row ? t : 0);             // A[j][t] = colp[j (j + 1) / 2], j > t
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+        const double* q = (j <= t) ? rowp + j : colp + j * (j + 1) / 2;
+        w[j] = (row && j < n) ? *q : ((j == t) ? 1.0 : 0.0);
+    }
+    double b = row ? A[MPC_PK(n, t)] : 0.0;
+    double myinv = 0.0;
+    bool ok = true;
+    double d0;
+    if (G::kThreads != 32) {   // multi-warp groups exchange the pivot through shared memory
+        if (t == 0) S.w[0] = w[0];
+        g.sync();
+        d0 = S.w[0];
+    } else {
+        d0 = __shfl_sync(0xffffffffu, w[0], 0);
+    }
+    if (!(d0 > 0.0)) ok = false;
+    double inv = fast_rcp(d0);
+    gj_stages<0, WK, G>(w, b, inv, myinv, ok, S, g);
+    g.sync();                  // every pivot read of S.w is done before it is overwritten with the solution
+    if (row) S.w[t] = b * myinv;
+    g.sync();
+    return ok;
+}
+
 // forward solve L y = b (b in S.w) for one-warp groups; y goes to row nc of the packed factor, which is
 // where backward_regs expects it.  Column access A[PK(i,k)] over i is bank-conflict free.
 // The L entries each lane needs do not depend on the recurrence, so they are loaded up front and the
@@ -708,10 +820,9 @@ MPC_HD bool face_solve(const Tron1Const& P, WK& S, const G& g) {
     MPC_TICK(S, g, 6);
     bool ok;
 #if defined(__CUDA_ARCH__)
-    if constexpr (G::kThreads >= WK::NC + 1 && WK::NC <= 60) {
-        ok = cholesky_regs<WK>(S, g);
+    if constexpr (G::kThreads >= WK::NC && WK::NC <= 60) {
+        ok = gj_solve_regs<WK>(S, g);
         MPC_TICK(S, g, 7);
-        backward_regs<WK>(S, g);
     } else
 #endif
     {

@@ -56,6 +56,17 @@ class Engine:
     def launch_count(self):
         return int(self.lib.mpc_b200_launch_count(self.h))
 
+    HOST_AUTO, HOST_STAGED, HOST_ZEROCOPY = 0, 1, 2
+
+    def set_host_mode(self, mode):
+        """Data path of the host-buffer calls: HOST_AUTO (zero-copy when every buffer is pinned, else staged
+        copies), HOST_STAGED, HOST_ZEROCOPY (error instead of falling back)."""
+        _capi.check(self.lib.mpc_b200_set_host_mode(self.h, int(mode)), self.h)
+
+    def last_host_path(self):
+        """1 if the last host-buffer call ran zero-copy, 0 if it staged its copies."""
+        return int(self.lib.mpc_b200_last_host_path(self.h))
+
     # -- device-resident entry points ------------------------------------------------------------
     def contact_schedule(self, it):
         """it: int32 [B] on device -> uint8 [B,N,2] (MPC::calculateGait over the horizon)."""

@@ -319,6 +319,57 @@ def test_host_paths_packed_and_pipelined(torch_cuda):
         eng.close()
 
 
+def test_host_zero_copy_and_staged_paths_agree(torch_cuda):
+    """Pinned buffers take the zero-copy path (kernel reads/writes host memory directly), pageable ones the
+    staged path; HOST_ZEROCOPY refuses pageable buffers; both paths are bit-identical to the device entry point.
+    Covers a standing instance (overflow class reading host memory through the list-driven kernel) and an
+    8-byte-aligned (not 16) slice so that the plain-load staging fallback runs against host memory too."""
+    torch = torch_cuda
+    from mpc_limx_control_b200.engine import Engine, control_host
+    from mpc_limx_control_b200 import _capi
+    N, Ts = 10, 0.005
+    for B in (1, 5, 300, 4100):
+        d = synth.tron1_batch(33, B + 1, N, Ts)
+        d["iter"][min(2, B - 1)] = -1
+        eng = make_engine(N, B + 1, Ts=Ts)
+        t = to_dev(torch, {k: v[:B] for k, v in d.items()})
+        F, st, it = eng.solve(t["x0"], t["x_ref"], t["feet"], it=t["iter"])
+        torch.cuda.synchronize()
+        F = F.cpu().numpy(); st = st.cpu().numpy(); it = it.cpu().numpy()
+        pin = {k: torch.from_numpy(np.ascontiguousarray(d[k])).pin_memory() for k in ("x0", "x_ref", "feet", "iter", "omega_yaw", "velocity_x")}
+        Fh = torch.zeros((B, N, 6), dtype=torch.float64).pin_memory()
+        sh = torch.full((B,), -7, dtype=torch.int32).pin_memory(); ih = torch.zeros(B, dtype=torch.int32).pin_memory()
+        for off in (0, 1):            # off = 1: instance slices start 8-byte aligned only
+            Fh.zero_(); sh.fill_(-7)
+            sl = {k: v[off:off + B] for k, v in pin.items()}
+            eng.set_host_mode(Engine.HOST_ZEROCOPY)
+            eng.solve_host(sl["x0"], sl["x_ref"], sl["feet"], it=sl["iter"], forces=Fh, status=sh, iters=ih)
+            assert eng.last_host_path() == 1
+            t2 = to_dev(torch, {k: d[k][off:off + B] for k in ("x0", "x_ref", "feet", "iter")})
+            F2, st2, it2 = eng.solve(t2["x0"], t2["x_ref"], t2["feet"], it=t2["iter"])
+            torch.cuda.synchronize()
+            assert np.array_equal(Fh.numpy(), F2.cpu().numpy()) and np.array_equal(sh.numpy(), st2.cpu().numpy())
+            assert np.array_equal(ih.numpy(), it2.cpu().numpy())
+        # pageable buffers: AUTO falls back to staged copies, ZEROCOPY refuses
+        eng.set_host_mode(Engine.HOST_AUTO)
+        Fp, sp, ip = eng.solve_host(d["x0"][:B], d["x_ref"][:B], d["feet"][:B], it=d["iter"][:B])
+        assert eng.last_host_path() == 0 and np.array_equal(Fp, F) and np.array_equal(sp, st) and np.array_equal(ip, it)
+        eng.set_host_mode(Engine.HOST_ZEROCOPY)
+        with pytest.raises(_capi.MpcB200Error):
+            eng.solve_host(d["x0"][:B], d["x_ref"][:B], d["feet"][:B], it=d["iter"][:B])
+        # pinned + forced staging == zero-copy, and the controller-shaped entry agrees across paths
+        eng.set_host_mode(Engine.HOST_STAGED)
+        Fs = torch.zeros((B, N, 6), dtype=torch.float64).pin_memory()
+        eng.solve_host(pin["x0"][:B], pin["x_ref"][:B], pin["feet"][:B], it=pin["iter"][:B], forces=Fs, status=sh, iters=ih)
+        assert eng.last_host_path() == 0 and np.array_equal(Fs.numpy(), F)
+        u_s = torch.zeros((B, 6), dtype=torch.float64).pin_memory(); u_z = torch.zeros((B, 6), dtype=torch.float64).pin_memory()
+        control_host(eng, pin["x0"][:B], pin["omega_yaw"][:B], pin["velocity_x"][:B], pin["feet"][:B], it=pin["iter"][:B], u0=u_s, status=sh, iters=ih)
+        eng.set_host_mode(Engine.HOST_ZEROCOPY)
+        control_host(eng, pin["x0"][:B], pin["omega_yaw"][:B], pin["velocity_x"][:B], pin["feet"][:B], it=pin["iter"][:B], u0=u_z, status=sh, iters=ih)
+        assert eng.last_host_path() == 1 and np.array_equal(u_s.numpy(), u_z.numpy())
+        eng.close()
+
+
 def test_non_finite_instance_is_isolated(torch_cuda):
     """a NaN state poisons only its own instance: status 2 there, neighbours (same CTA) still certified"""
     torch = torch_cuda

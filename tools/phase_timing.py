@@ -14,8 +14,9 @@ from mpc_limx_control_b200 import _capi, synth
 _capi.LIB_PATH = out
 import torch
 from mpc_limx_control_b200.engine import Engine
-standing = len(sys.argv) > 1 and sys.argv[1] == "standing"
-N, B = 10, 4096
+standing = "standing" in sys.argv[1:]
+N = 10
+B = next((int(a) for a in sys.argv[1:] if a.isdigit()), 4096)
 d = synth.tron1_batch(1001, B, N, 0.005, standing=standing)
 eng = Engine(horizon=N, max_batch=B)
 t = {k: torch.from_numpy(d[k]).cuda() for k in ("x0", "x_ref", "feet", "iter")}
@@ -31,7 +32,22 @@ L.mpc_b200_debug_phase_cycles(buf, 0)
 names = ["model", "horizon_sums", "free_response", "adjoint(f)", "ufix/grad0", "build_hessian", "rhs", "cholesky", "backward",
          "recover_u", "input_response", "adjoint(g)", "project/check", "tail"]
 v = np.array(list(buf), dtype=np.float64)[:14] / B
-print(f"standing={standing} mean iters {it.float().mean().item():.2f}; cycles per instance (thread-0 wall, includes stalls):")
+print(f"B={B} standing={standing} mean iters {it.float().mean().item():.2f}; cycles per instance (thread-0 wall, includes stalls):")
 for n_, c in zip(names, v):
     print(f"  {n_:15s} {c:9.0f}  {100 * c / v.sum():5.1f}%")
 print(f"  {'total':15s} {v.sum():9.0f}")
+
+# per-CTA timeline of the same launch (globaltimer): how the two rounds of CTAs overlap
+nb = (B + 3) // 4
+tr = (C.c_ulonglong * (3 * nb))()
+L.mpc_b200_debug_cta_trace(tr, nb)
+tr = np.array(list(tr), dtype=np.float64).reshape(nb, 3)
+t0 = tr[:, 0].min()
+st_, en_ = (tr[:, 0] - t0) / 1e3, (tr[:, 1] - t0) / 1e3
+dur = en_ - st_
+print(f"CTAs {nb}: kernel span {en_.max():.1f} us; CTA duration mean {dur.mean():.1f} min {dur.min():.1f} max {dur.max():.1f} us")
+first = st_ < 2.0
+print(f"  first wave: {first.sum()} CTAs, duration mean {dur[first].mean():.1f} us, end mean {en_[first].mean():.1f} us")
+if (~first).any(): print(f"  later CTAs: {(~first).sum()}, start mean {st_[~first].mean():.1f} us, duration mean {dur[~first].mean():.1f} us, end mean {en_[~first].mean():.1f} max {en_[~first].max():.1f} us")
+per_sm = np.bincount(tr[:, 2].astype(int), minlength=148)
+print(f"  CTAs per SM: min {per_sm.min()} max {per_sm.max()}; SMs with 8+: {(per_sm >= 8).sum()}, with <=6: {(per_sm <= 6).sum()}")
