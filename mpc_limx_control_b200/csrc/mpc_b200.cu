@@ -64,9 +64,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 #if defined(MPC_PHASE_TIMING)
-__device__ unsigned long long g_cta_trace[3 * 16384];   // per CTA: start ns, end ns, SM id (profiling build only)
+__device__ unsigned long long g_cta_trace[4 * 16384];   // per CTA: start ns, end ns, SM id, inputs-arrived ns (profiling build only)
 extern "C" int mpc_b200_debug_cta_trace(unsigned long long* out, int n) {
-    return cudaMemcpyFromSymbol(out, g_cta_trace, sizeof(unsigned long long) * 3 * n) == cudaSuccess ? 0 : -3;
+    return cudaMemcpyFromSymbol(out, g_cta_trace, sizeof(unsigned long long) * 4 * n) == cudaSuccess ? 0 : -3;
 }
 __device__ __forceinline__ unsigned long long gtime_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 __device__ unsigned long long g_phase_cycles[16];
@@ -116,7 +116,7 @@ tron1_solve_kernel(const __grid_constant__ Tron1Const P, int B, const double* __
 #if defined(MPC_PHASE_TIMING)
     if (!INDIRECT && threadIdx.x == 0 && blockIdx.x < 16384) {
         unsigned smid; asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
-        g_cta_trace[3 * blockIdx.x] = gtime_ns(); g_cta_trace[3 * blockIdx.x + 2] = smid;
+        g_cta_trace[4 * blockIdx.x] = gtime_ns(); g_cta_trace[4 * blockIdx.x + 2] = smid; g_cta_trace[4 * blockIdx.x + 1] = 0;
     }
 #endif
     GrpCuda<WPI> g;
@@ -171,7 +171,7 @@ tron1_solve_kernel(const __grid_constant__ Tron1Const P, int B, const double* __
             if (iters) iters[b] = its;
         }
 #if defined(MPC_PHASE_TIMING)
-        if (!INDIRECT && g.t == 0 && blockIdx.x < 16384) atomicMax(&g_cta_trace[3 * blockIdx.x + 1], gtime_ns());
+        if (!INDIRECT && g.t == 0 && blockIdx.x < 16384) atomicMax(&g_cta_trace[4 * blockIdx.x + 1], gtime_ns());
 #endif
     };
 
@@ -207,6 +207,9 @@ tron1_solve_kernel(const __grid_constant__ Tron1Const P, int B, const double* __
         if (mine) nc = load_contact(b);
         __syncthreads();   // barrier init / plain stores visible
         if (bulk) mbar_wait(&st.bar, 0);
+#if defined(MPC_PHASE_TIMING)
+        if (threadIdx.x == 0 && blockIdx.x < 16384) g_cta_trace[4 * blockIdx.x + 3] = gtime_ns();
+#endif
         if (!mine) return;
         if (nc > NC) {     // does not fit this capacity class: hand over to the large instantiation
             if (g.t == 0) {
@@ -495,11 +498,7 @@ static int dispatch_solve(mpc_b200_engine* e, int B, const double* x0, const dou
     int32_t* ol = e->d_ovf_list + list_offset;
     int32_t* oc = e->d_ovf_count + 2 * slot;
     switch (e->N) {
-        case 10: {
-            static const int ipc = getenv("MPC_B200_IPC") ? atoi(getenv("MPC_B200_IPC")) : 4;
-            if (ipc == 2) return launch_solve<10, 1, 2, 8, 2, 2, true, 3>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only);
-            return launch_solve<10, 1, 4, 4, 2, 2, true, 3>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only);
-        }
+        case 10: return launch_solve<10, 1, 4, 4, 2, 2, true, 3>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only);
         case 20: return launch_solve<20, 2, 2, 2, 2, 2>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only);
         case 50: return launch_solve<50, 8, 1, 1, 8, 1, false>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only);
         default: return set_err(e, MPC_B200_EINVAL, "unsupported horizon");

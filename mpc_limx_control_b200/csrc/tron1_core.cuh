@@ -48,6 +48,7 @@ struct Tron1Const {
     int max_newton, max_admm;
     float gait_dt, gait_swing, gait_stance;
     int gait_mpc_step;
+    double gait_cycle, gait_inv_cycle;     // (double)(swing + stance) with the float add of the reference, and its reciprocal
     double foot_off_l[3], foot_off_r[3];   // nominal base->foot offsets (include/MPCParam.h:64-73)
 };
 
@@ -61,13 +62,21 @@ MPC_HD void gait_contact(const Tron1Const& P, int iter, int& left_stance, int& r
     if (iter < 0) { left_stance = 1; right_stance = 1; return; }   // standing
 #if defined(__CUDA_ARCH__)
     float ct = __fmul_rn((float)iter, P.gait_dt);
-    float cy = __fadd_rn(P.gait_swing, P.gait_stance);
 #else
     volatile float ctv = (float)iter * P.gait_dt;
-    volatile float cyv = P.gait_swing + P.gait_stance;
-    float ct = ctv, cy = cyv;
+    float ct = ctv;
 #endif
-    double phase = fmod((double)ct, (double)cy);
+    // phase = fmod((double)ct, (double)cycle), evaluated EXACTLY without the library's iterative fmod:
+    // x = (double)ct and y = (double)cycle carry 24-bit significands and q = trunc(x / y) < 2^29, so q y is
+    // exact in double, r = fma(-q, y, x) is exact, and a quotient that is off by one (x * (1/y) is rounded)
+    // is repaired by one correction step.  The result is the mathematically exact remainder, which is
+    // what fmod returns (checked against the C library on the reference's disagreement cases in the tests).
+    const double x = (double)ct, y = P.gait_cycle;
+    double q = trunc(x * P.gait_inv_cycle);
+    double phase = fma(-q, y, x);
+    if (phase < 0.0) phase += y;
+    else if (phase >= y) phase -= y;
+    if (!(y > 0.0) || !(x >= 0.0)) phase = fmod(x, y);   // degenerate parameters: defer to the library
     int left_swing = phase < (double)P.gait_swing;
     left_stance = !left_swing;
     right_stance = left_swing;
@@ -106,7 +115,8 @@ struct Tron1Work {
     const double* x0;       // 13 doubles (staged by the caller)
     const double* feet;     // 6 or 6N doubles
     int8_t contact[NS], ax[NS], ay[NS], zt[NS], nax[NS], nay[NS], nzt[NS];
-    int16_t cidx[NS];
+    int16_t cidx[NS];       // foot-step -> compact stance index
+    int8_t cinv[NS];        // compact stance index -> foot-step (2 step + foot)
     int nc;         // compact variable count (3 * stance foot-steps)
     int flag;       // group-uniform scratch flag
 #if defined(MPC_PHASE_TIMING)
@@ -352,14 +362,18 @@ MPC_HD void build_hessian(const Tron1Const& P, WK& S, double rho, bool use_face,
     [[maybe_unused]] constexpr int N = WK::N;
     const double Ts2 = P.Ts * P.Ts, Ts4 = Ts2 * Ts2, im2 = P.inv_m * P.inv_m;
     const double* q = P.q;
-    for (int pr = g.tid(); pr < N * (N + 1) / 2; pr += g.size()) {
-        // unrank pr -> (j, l), j >= l
-        int j = (int)((sqrtf(8.0f * (float)pr + 1.0f) - 1.0f) * 0.5f);
-        while (j * (j + 1) / 2 > pr) --j;
-        while ((j + 1) * (j + 2) / 2 <= pr) ++j;
-        int l = pr - j * (j + 1) / 2;
-        bool cj0 = S.contact[2 * j], cj1 = S.contact[2 * j + 1], cl0 = S.contact[2 * l], cl1 = S.contact[2 * l + 1];
-        if (!((cj0 || cj1) && (cl0 || cl1))) continue;
+    // work item = one pair of STANCE foot-steps (compact indices ia >= ib) = one 3x3 block of the reduced
+    // Hessian: every lane runs the same straight-line code whatever the contact pattern (a loop over step
+    // pairs with inner loops over the feet in contact made the lanes of a warp diverge four ways)
+    const int m = S.nc / 3;
+    for (int pr = g.tid(); pr < m * (m + 1) / 2; pr += g.size()) {
+        // unrank pr -> (ia, ib), ia >= ib
+        int ia = (int)((sqrtf(8.0f * (float)pr + 1.0f) - 1.0f) * 0.5f);
+        while (ia * (ia + 1) / 2 > pr) --ia;
+        while ((ia + 1) * (ia + 2) / 2 <= pr) ++ia;
+        const int ib = pr - ia * (ia + 1) / 2;
+        const int sa = S.cinv[ia], sb = S.cinv[ib];       // foot-steps (2 step + foot), sa >= sb
+        const int j = sa >> 1, l = sb >> 1;               // horizon steps, j >= l
         const double* sw = S.SW + 8 * j;   // suffix sums over i > j  (j >= l so i > l too)
         double dcj = S.dc[j], dsj = S.ds[j], dcl = S.dc[l], dsl = S.ds[l];
         double Saa = sw[3] + (dcj + dcl) * sw[1] + dcj * dcl * sw[0];
@@ -376,59 +390,51 @@ MPC_HD void build_hessian(const Tron1Const& P, WK& S, double rho, bool use_face,
         double M22 = Ts4 * q[2] * Szz + Ts2 * q[8] * sw[0];
         double Dp[3];
         for (int c = 0; c < 3; ++c) Dp[c] = im2 * (Ts4 * q[3 + c] * Szz + Ts2 * q[9 + c] * sw[0]);
-        for (int a = 0; a < 2; ++a) {
-            if (!S.contact[2 * j + a]) continue;
-            const int sa = 2 * j + a;
-            const double* Wa = S.W + 9 * sa;
-            // MW' = M' * Wa  ->  we need Wa' M Wb = (M' Wa)' Wb ; compute L = Wa' M (3x3)
-            double L[9];
-            for (int r = 0; r < 3; ++r) {   // row r of Wa' = column r of Wa
-                double w0 = Wa[0 * 3 + r], w1 = Wa[1 * 3 + r], w2 = Wa[2 * 3 + r];
-                L[r * 3 + 0] = w0 * M00 + w1 * M10;
-                L[r * 3 + 1] = w0 * M01 + w1 * M11;
-                L[r * 3 + 2] = w2 * M22;
+        const double* Wa = S.W + 9 * sa;
+        const double* Wb = S.W + 9 * sb;
+        // block = Wa' M Wb + D: first L = Wa' M (3x3), then T = L Wb
+        double L[9];
+        for (int r = 0; r < 3; ++r) {   // row r of Wa' = column r of Wa
+            double w0 = Wa[0 * 3 + r], w1 = Wa[1 * 3 + r], w2 = Wa[2 * 3 + r];
+            L[r * 3 + 0] = w0 * M00 + w1 * M10;
+            L[r * 3 + 1] = w0 * M01 + w1 * M11;
+            L[r * 3 + 2] = w2 * M22;
+        }
+        double T[9];
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c)
+                T[r * 3 + c] = L[r * 3 + 0] * Wb[0 * 3 + c] + L[r * 3 + 1] * Wb[1 * 3 + c] + L[r * 3 + 2] * Wb[2 * 3 + c];
+        for (int c = 0; c < 3; ++c) T[c * 3 + c] += Dp[c];
+        if (sa == sb) for (int c = 0; c < 3; ++c) T[c * 3 + c] += P.r + 0.5 * rho;
+        for (int i = 0; i < 9; ++i) T[i] *= 2.0;
+        if (use_face) {
+            FaceZ Za = face_basis(P.mu, S.ax[sa], S.ay[sa], S.zt[sa]);
+            FaceZ Zb = face_basis(P.mu, S.ax[sb], S.ay[sb], S.zt[sb]);
+            for (int r = 0; r < 3; ++r) {   // columns:  T <- T Zb
+                double t0 = T[r * 3], t1 = T[r * 3 + 1], t2 = T[r * 3 + 2];
+                T[r * 3 + 2] = Zb.fz * (Zb.mx * t0 + Zb.my * t1 + t2);
+                T[r * 3 + 0] = Zb.fx * t0;
+                T[r * 3 + 1] = Zb.fy * t1;
             }
-            FaceZ Za = use_face ? face_basis(P.mu, S.ax[sa], S.ay[sa], S.zt[sa]) : face_basis(P.mu, 0, 0, 0);
-            for (int b = 0; b < 2; ++b) {
-                if (!S.contact[2 * l + b]) continue;
-                if (j == l && b > a) continue;
-                const int sb = 2 * l + b;
-                const double* Wb = S.W + 9 * sb;
-                double T[9];
-                for (int r = 0; r < 3; ++r)
-                    for (int c = 0; c < 3; ++c)
-                        T[r * 3 + c] = L[r * 3 + 0] * Wb[0 * 3 + c] + L[r * 3 + 1] * Wb[1 * 3 + c] + L[r * 3 + 2] * Wb[2 * 3 + c];
-                for (int c = 0; c < 3; ++c) T[c * 3 + c] += Dp[c];
-                if (sa == sb) for (int c = 0; c < 3; ++c) T[c * 3 + c] += P.r + 0.5 * rho;
-                for (int i = 0; i < 9; ++i) T[i] *= 2.0;
-                if (use_face) {
-                    FaceZ Zb = face_basis(P.mu, S.ax[sb], S.ay[sb], S.zt[sb]);
-                    for (int r = 0; r < 3; ++r) {   // columns:  T <- T Zb
-                        double t0 = T[r * 3], t1 = T[r * 3 + 1], t2 = T[r * 3 + 2];
-                        T[r * 3 + 2] = Zb.fz * (Zb.mx * t0 + Zb.my * t1 + t2);
-                        T[r * 3 + 0] = Zb.fx * t0;
-                        T[r * 3 + 1] = Zb.fy * t1;
-                    }
-                    for (int c = 0; c < 3; ++c) {   // rows:  T <- Za' T
-                        double t0 = T[c], t1 = T[3 + c], t2 = T[6 + c];
-                        T[6 + c] = Za.fz * (Za.mx * t0 + Za.my * t1 + t2);
-                        T[c] = Za.fx * t0;
-                        T[3 + c] = Za.fy * t1;
-                    }
-                    if (sa == sb) {
-                        if (Za.fx == 0.0) T[0] = 1.0;
-                        if (Za.fy == 0.0) T[4] = 1.0;
-                        if (Za.fz == 0.0) T[8] = 1.0;
-                    }
-                }
-                const int ra = 3 * S.cidx[sa], cb = 3 * S.cidx[sb];
-                for (int r = 0; r < 3; ++r)
-                    for (int c = 0; c < 3; ++c) {
-                        if (sa == sb && c > r) continue;
-                        S.Ap()[MPC_PK(ra + r, cb + c)] = T[r * 3 + c];
-                    }
+            for (int c = 0; c < 3; ++c) {   // rows:  T <- Za' T
+                double t0 = T[c], t1 = T[3 + c], t2 = T[6 + c];
+                T[6 + c] = Za.fz * (Za.mx * t0 + Za.my * t1 + t2);
+                T[c] = Za.fx * t0;
+                T[3 + c] = Za.fy * t1;
+            }
+            if (sa == sb) {
+                if (Za.fx == 0.0) T[0] = 1.0;
+                if (Za.fy == 0.0) T[4] = 1.0;
+                if (Za.fz == 0.0) T[8] = 1.0;
             }
         }
+        const int ra = 3 * ia, cb = 3 * ib;
+        double* Ap = S.Ap();
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) {
+                if (sa == sb && c > r) continue;
+                Ap[MPC_PK(ra + r, cb + c)] = T[r * 3 + c];
+            }
     }
     g.sync();
 }
@@ -793,6 +799,12 @@ MPC_HD bool face_solve(const Tron1Const& P, WK& S, const G& g) {
     [[maybe_unused]] constexpr int N = WK::N;
     // fixed part: z = fmax on zt==1 foot-steps
     bool any_fixed = false;
+#if defined(__CUDA_ARCH__)
+    if constexpr (G::kThreads == 32 && 2 * N <= 32) {
+        const int s = g.tid();
+        any_fixed = __any_sync(0xffffffffu, s < 2 * N && S.contact[s] && S.zt[s] == 1);
+    } else
+#endif
     for (int s = 0; s < 2 * N; ++s) any_fixed |= (S.contact[s] && S.zt[s] == 1);
     for (int s = g.tid(); s < 2 * N; s += g.size()) {
         double fz = (S.contact[s] && S.zt[s] == 1) ? P.f_max : 0.0;
@@ -930,9 +942,24 @@ MPC_HD void adopt_predicted_face(WK& S, const G& g) {
 template <class WK, class G>
 MPC_HD void setup_instance(const Tron1Const& P, WK& S, const double* xref, const G& g, bool warm = false) {
     [[maybe_unused]] constexpr int N = WK::N;
+#if defined(__CUDA_ARCH__)
+    if constexpr (G::kThreads == 32 && 2 * N <= 32) {
+        // one foot-step per lane: ranks from a ballot instead of a serial scan by one thread
+        const int s = g.tid();
+        const bool in = s < 2 * N && S.contact[s];
+        const unsigned mask = __ballot_sync(0xffffffffu, in);
+        const int rank = __popc(mask & ((1u << s) - 1u));
+        if (s < 2 * N) S.cidx[s] = (int16_t)rank;
+        if (in) S.cinv[rank] = (int8_t)s;
+        if (s == 0) S.nc = 3 * __popc(mask);
+    } else
+#endif
     if (g.tid() == 0) {
         int c = 0;
-        for (int s = 0; s < 2 * N; ++s) { S.cidx[s] = (int16_t)c; c += S.contact[s] ? 1 : 0; }
+        for (int s = 0; s < 2 * N; ++s) {
+            S.cidx[s] = (int16_t)c;
+            if (S.contact[s]) { S.cinv[c] = (int8_t)s; ++c; }
+        }
         S.nc = 3 * c;
     }
     if (!warm) {

@@ -70,6 +70,11 @@ inline int make_tron1_const(const mpc_b200_tron1_params& p, Tron1Const& c) {
     c.gait_swing = p.gait_swing_time;
     c.gait_stance = p.gait_stance_time;
     c.gait_mpc_step = p.gait_mpc_step;
+    {   // cycle = swing + stance as ONE float add (reference include/MPCController.h:63 with include/MPCParam.h:48-49)
+        volatile float cyc = p.gait_swing_time + p.gait_stance_time;
+        c.gait_cycle = (double)cyc;
+        c.gait_inv_cycle = 1.0 / c.gait_cycle;
+    }
     for (int k = 0; k < 3; ++k) { c.foot_off_l[k] = p.foot_offset_left[k]; c.foot_off_r[k] = p.foot_offset_right[k]; }
     return 0;
 }

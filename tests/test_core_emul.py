@@ -103,6 +103,22 @@ def test_gait_matches_golden(golden):
     assert np.all(E.gait_contact(pe, -1, 5) == 1)   # standing
 
 
+def test_gait_exact_remainder_vs_library_fmod():
+    """gait_contact evaluates fmod((double)(iter*dt), (double)(swing+stance)) by an exact quotient/remainder
+    instead of the library routine: compare with the oracle (C fmod) on random and adversarial loop counters,
+    for the reference timing and for cycle lengths that are not powers of two (inexact reciprocal)."""
+    rng = np.random.default_rng(12)
+    its = np.concatenate([rng.integers(0, 2**31 - 64, 4000), np.arange(0, 3000), np.arange(10_773_900, 10_774_100),
+                          500 * np.arange(1, 2000), 500 * np.arange(1, 2000) - 1, [2**31 - 64, 16_777_216, 16_777_217]])
+    for dt, sw, stc in ((0.001, 0.5, 0.5), (0.001, 0.3, 0.4), (0.002, 0.35, 0.15), (0.0005, 0.7, 0.1)):
+        pe = E.default_params(gait_dt=dt, gait_swing_time=sw, gait_stance_time=stc)
+        g = O.gait_defaults(); g.dt = dt; g.swing_time = sw; g.stance_time = stc
+        for it in its:
+            a = E.gait_contact(pe, int(it), 1)
+            b = O.contact_schedule(int(it), 1, g)
+            assert np.array_equal(a, b), (dt, sw, stc, int(it))
+
+
 def test_rollout_vs_oracle():
     """closed loop (BASELINE configs[4] shape, short): emulated device source vs the oracle loop"""
     N, Ts, steps = 10, 0.005, 40

@@ -38,16 +38,32 @@ for n_, c in zip(names, v):
 print(f"  {'total':15s} {v.sum():9.0f}")
 
 # per-CTA timeline of the same launch (globaltimer): how the two rounds of CTAs overlap
-nb = (B + 3) // 4
-tr = (C.c_ulonglong * (3 * nb))()
-L.mpc_b200_debug_cta_trace(tr, nb)
-tr = np.array(list(tr), dtype=np.float64).reshape(nb, 3)
-t0 = tr[:, 0].min()
-st_, en_ = (tr[:, 0] - t0) / 1e3, (tr[:, 1] - t0) / 1e3
-dur = en_ - st_
-print(f"CTAs {nb}: kernel span {en_.max():.1f} us; CTA duration mean {dur.mean():.1f} min {dur.min():.1f} max {dur.max():.1f} us")
-first = st_ < 2.0
-print(f"  first wave: {first.sum()} CTAs, duration mean {dur[first].mean():.1f} us, end mean {en_[first].mean():.1f} us")
-if (~first).any(): print(f"  later CTAs: {(~first).sum()}, start mean {st_[~first].mean():.1f} us, duration mean {dur[~first].mean():.1f} us, end mean {en_[~first].mean():.1f} max {en_[~first].max():.1f} us")
-per_sm = np.bincount(tr[:, 2].astype(int), minlength=148)
-print(f"  CTAs per SM: min {per_sm.min()} max {per_sm.max()}; SMs with 8+: {(per_sm >= 8).sum()}, with <=6: {(per_sm <= 6).sum()}")
+def cta_trace(label):
+    nb = (B + 3) // 4
+    tr = (C.c_ulonglong * (4 * nb))()
+    L.mpc_b200_debug_cta_trace(tr, nb)
+    tr = np.array(list(tr), dtype=np.float64).reshape(nb, 4)
+    t0 = tr[:, 0].min()
+    st_, en_, arr = (tr[:, 0] - t0) / 1e3, (tr[:, 1] - t0) / 1e3, (tr[:, 3] - t0) / 1e3
+    dur = en_ - st_
+    print(f"[{label}] CTAs {nb}: kernel span {en_.max():.1f} us; CTA duration mean {dur.mean():.1f} min {dur.min():.1f} max {dur.max():.1f} us")
+    first = st_ < 2.0
+    w = arr - st_
+    print(f"  first wave: {first.sum()} CTAs, input wait mean {w[first].mean():.1f} max {w[first].max():.1f} us, duration mean {dur[first].mean():.1f} us, end mean {en_[first].mean():.1f} us")
+    if (~first).any():
+        print(f"  later CTAs: {(~first).sum()}, start mean {st_[~first].mean():.1f} us, input wait mean {w[~first].mean():.1f} max {w[~first].max():.1f}, duration mean {dur[~first].mean():.1f} us, end mean {en_[~first].mean():.1f} max {en_[~first].max():.1f} us")
+    q = np.argsort(st_)
+    print("  input-arrival time by CTA start order (deciles):", np.round(np.percentile(arr[q][:first.sum()], [0, 10, 25, 50, 75, 90, 100]), 1))
+    per_sm = np.bincount(tr[:, 2].astype(int), minlength=148)
+    print(f"  CTAs per SM: min {per_sm.min()} max {per_sm.max()}")
+
+cta_trace("device-resident inputs")
+# the same batch through the zero-copy host path (inputs read from pinned host memory by the kernel)
+from mpc_limx_control_b200.engine import bind_solve_host
+pin = {k: torch.from_numpy(d[k]).pin_memory() for k in ("x0", "x_ref", "feet", "iter")}
+Fh = torch.empty((B, N, 6), dtype=torch.float64).pin_memory()
+sh = torch.empty(B, dtype=torch.int32).pin_memory(); ih = torch.empty(B, dtype=torch.int32).pin_memory()
+hc = bind_solve_host(eng, pin["x0"], pin["x_ref"], pin["feet"], it=pin["iter"], forces=Fh, status=sh, iters=ih)
+for _ in range(3):
+    hc()
+cta_trace("zero-copy host buffers")
