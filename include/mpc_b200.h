@@ -149,6 +149,65 @@ int mpc_b200_tron1_rollout_device(mpc_b200_engine *e, int B, int steps, double *
                                   int32_t *d_uncertified, int32_t *d_iters, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Leg kinematics around the force MPC: the rest of MPC::run (include/MPCController.h:183-196).
+ *   include/pinocchio_kinematics.h:30-43,153-157  forwardKinematics / getLinkPosition / setBaseLinkPose  -> leg_fk
+ *   include/MPCController.h:61-75,106-175         calculateGait, computeFootPlacement, computeSwingFootDesiredPosition
+ *   include/pinocchio_kinematics.h:61-149         inverseKinematics                                       -> swing_step
+ *   include/MPCController.h:178-180               computeSupportFootForce (empty stub): tau = -J' f       -> grf_to_torque
+ * Layouts (instance-major, FP64): base_pos [B][3]; base_quat [B][4] stored [x,y,z,w]
+ * (include/state_estimator_fake.h:22); q / q_cmd / tau [B][6] = left abad,hip,knee, right abad,hip,knee
+ * (RobotCmd order, include/MPCController.h:164-174); feet [B][2][3] world (the `feet` input of the solve);
+ * jac [B][2][3][3] row-major world-aligned d(foot)/d(q_leg); des_vel [B][3]; u0 [B][6] first-step forces.
+ * The joint axes are NOT in the reference (its URDF lives in an external repository): they are model
+ * parameters, default abad = x, hip = knee = y; the link offsets are include/MPCParam.h:13-38. */
+typedef struct mpc_b200_leg_model {
+    double offset[2][5][3];  /* leg (0 left, 1 right) x {base->abad, abad->hip, hip->knee, knee->foot, foot->contact} */
+    double axis[2][3][3];    /* leg x joint: unit axis in the parent frame */
+} mpc_b200_leg_model;
+
+typedef struct mpc_b200_swing_params {
+    float dt, swing_time, stance_time, gait_height;   /* include/MPCParam.h:44-51 */
+    double p_rel_max;                                  /* 0.3, include/MPCController.h:111 */
+    double foot_offset_left[3], foot_offset_right[3];  /* include/MPCParam.h:64-73 */
+    double ik_tol, ik_dt, ik_damp;                     /* 1e-3, 1e-1, 1e-6: include/pinocchio_kinematics.h:61,76-77 */
+    int32_t ik_max_iter;                               /* 10 */
+} mpc_b200_swing_params;
+
+int mpc_b200_leg_default_model(mpc_b200_leg_model *m);
+int mpc_b200_swing_default_params(mpc_b200_swing_params *p);
+
+/* World positions of contact_L_Link / contact_R_Link (and, if d_jac != NULL, the leg Jacobians). Device pointers,
+ * launched on `stream` on the current device. */
+int mpc_b200_leg_fk_device(const mpc_b200_leg_model *m, int B, const double *d_base_pos, const double *d_base_quat,
+                           const double *d_q, double *d_feet, double *d_jac, void *stream);
+
+/* Swing-leg step: gait state of iter[b] -> landing point from the desired velocity -> next swing-foot position
+ * (linear xy, sine height) -> damped least-squares IK from the current joint angles -> the swing leg's three
+ * entries of q_cmd (the stance leg's entries are left untouched, as in the reference).  Optional outputs (may be
+ * NULL): feet [B][2][3] (FK at the current q: feed it to the solve), next_foot [B][3], swing_leg [B] (0 left,
+ * 1 right), ik_err [B] (last position error norm), ik_iters [B]. */
+int mpc_b200_swing_step_device(const mpc_b200_leg_model *m, const mpc_b200_swing_params *p, int B,
+                               const double *d_base_pos, const double *d_base_quat, const double *d_q,
+                               const double *d_des_vel, const int32_t *d_iter, double *d_q_cmd, double *d_feet,
+                               double *d_next_foot, int32_t *d_swing_leg, double *d_ik_err, int32_t *d_ik_iters,
+                               void *stream);
+
+/* tau = -J(q)' f for both legs from the first-step forces u0 (a swing foot has f = 0, hence tau = 0). */
+int mpc_b200_grf_to_torque_device(const mpc_b200_leg_model *m, int B, const double *d_base_quat, const double *d_q,
+                                  const double *d_u0, double *d_tau, void *stream);
+
+/* The same three calls with HOST buffers (copies in, kernel, copies out, synchronise) on `device`; used by the
+ * single-robot C++ facade.  One caller per device. */
+int mpc_b200_leg_fk_host(int device, const mpc_b200_leg_model *m, int B, const double *base_pos, const double *base_quat,
+                         const double *q, double *feet, double *jac);
+int mpc_b200_swing_step_host(int device, const mpc_b200_leg_model *m, const mpc_b200_swing_params *p, int B,
+                             const double *base_pos, const double *base_quat, const double *q, const double *des_vel,
+                             const int32_t *iter, double *q_cmd, double *feet, double *next_foot, int32_t *swing_leg,
+                             double *ik_err, int32_t *ik_iters);
+int mpc_b200_grf_to_torque_host(int device, const mpc_b200_leg_model *m, int B, const double *base_quat, const double *q,
+                                const double *u0, double *tau);
+
+/* ------------------------------------------------------------------------------------------------
  * Generic condensed-MPC path: the reference class QPSolver (include/QPSolver.h:13-37), any NX/NU/N.
  * HOST pointers, column-major (Eigen layout), B independent instances per call (B = 1 for the
  * facade).  Copies in, runs one CTA per instance on the device, copies out, synchronises. */

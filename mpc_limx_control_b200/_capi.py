@@ -19,6 +19,8 @@ SYMBOLS = [
     "mpc_b200_launch_count", "mpc_b200_set_host_mode", "mpc_b200_last_host_path", "mpc_b200_contact_schedule_device", "mpc_b200_tron1_solve_device",
     "mpc_b200_tron1_solve_host", "mpc_b200_tron1_condense_device",
     "mpc_b200_tron1_reference_device", "mpc_b200_tron1_rollout_device", "mpc_b200_tron1_control_host",
+    "mpc_b200_leg_default_model", "mpc_b200_swing_default_params", "mpc_b200_leg_fk_device", "mpc_b200_swing_step_device",
+    "mpc_b200_grf_to_torque_device", "mpc_b200_leg_fk_host", "mpc_b200_swing_step_host", "mpc_b200_grf_to_torque_host",
     "mpc_b200_lti_create", "mpc_b200_lti_destroy", "mpc_b200_lti_last_error", "mpc_b200_lti_launch_count",
     "mpc_b200_lti_discretize", "mpc_b200_lti_build_qp", "mpc_b200_qp_solve_dense", "mpc_b200_lti_update_state",
 ]
@@ -34,6 +36,17 @@ class Tron1Params(C.Structure):
         ("max_newton", C.c_int32), ("max_admm", C.c_int32), ("tol", C.c_double),
         ("foot_offset_left", C.c_double * 3), ("foot_offset_right", C.c_double * 3),
     ]
+
+
+class LegModel(C.Structure):
+    """mpc_b200_leg_model: offset[leg][link][xyz], axis[leg][joint][xyz] (flattened)."""
+    _fields_ = [("offset", C.c_double * 30), ("axis", C.c_double * 18)]
+
+
+class SwingParams(C.Structure):
+    _fields_ = [("dt", C.c_float), ("swing_time", C.c_float), ("stance_time", C.c_float), ("gait_height", C.c_float),
+                ("p_rel_max", C.c_double), ("foot_offset_left", C.c_double * 3), ("foot_offset_right", C.c_double * 3),
+                ("ik_tol", C.c_double), ("ik_dt", C.c_double), ("ik_damp", C.c_double), ("ik_max_iter", C.c_int32)]
 
 
 class MpcB200Error(RuntimeError):
@@ -76,6 +89,14 @@ def lib():
         L.mpc_b200_tron1_reference_device.argtypes = [vp, ip, vp, vp, vp, vp, vp]
         L.mpc_b200_tron1_rollout_device.argtypes = [vp, ip, ip, vp, vp, vp, vp, vp, vp, vp, vp]
         L.mpc_b200_tron1_control_host.argtypes = [vp, ip] + [vp] * 9
+        L.mpc_b200_leg_default_model.argtypes = [C.POINTER(LegModel)]
+        L.mpc_b200_swing_default_params.argtypes = [C.POINTER(SwingParams)]
+        L.mpc_b200_leg_fk_device.argtypes = [C.POINTER(LegModel), ip] + [vp] * 6
+        L.mpc_b200_swing_step_device.argtypes = [C.POINTER(LegModel), C.POINTER(SwingParams), ip] + [vp] * 12
+        L.mpc_b200_grf_to_torque_device.argtypes = [C.POINTER(LegModel), ip] + [vp] * 5
+        L.mpc_b200_leg_fk_host.argtypes = [ip, C.POINTER(LegModel), ip] + [vp] * 5
+        L.mpc_b200_swing_step_host.argtypes = [ip, C.POINTER(LegModel), C.POINTER(SwingParams), ip] + [vp] * 11
+        L.mpc_b200_grf_to_torque_host.argtypes = [ip, C.POINTER(LegModel), ip] + [vp] * 4
         dd = C.c_double
         L.mpc_b200_lti_create.argtypes = [ip, C.POINTER(vp)]
         L.mpc_b200_lti_destroy.argtypes = [vp]

@@ -3,14 +3,18 @@
 // for the limxsdk types and an injectable state source instead of the ROS StateEstimatorFake
 // (include/state_estimator_fake.h:118-143).
 //
-// In scope: update_odom_state (a1), calculateGait (a2) and
-// computeSupportFootForce -- the reference's empty stub (include/MPCController.h:178-180) -- which
-// here runs the force MPC on the device and keeps the optimal ground-reaction forces.
-// Out of scope this round: foot placement and the swing-leg IK (section 8f rank 2).
+// run() performs the reference's four calls (include/MPCController.h:183-196) plus the force MPC the reference
+// left as an empty stub:
+//   update_odom_state (a1) -> calculateGait (a2) -> computeFootPlacement -> computeSwingFootDesiredPosition
+//   (FK + swing profile + IK on the device, csrc/leg_b200.cu; writes the swing leg's cmd.q) ->
+//   computeSupportFootForce (include/MPCController.h:178-180: force MPC on the device, then tau = -J'f into the
+//   stance leg's cmd.tau).
+// The leg model's joint axes are parameters (external URDF, see include/mpc_b200.h).
 #pragma once
 #include <array>
 #include <cmath>
 #include <functional>
+#include <string>
 
 #include "MPCParam.h"
 #include "limxsdk_stub.h"
@@ -33,19 +37,31 @@ public:
     using FootSource = std::function<void(const limxsdk::RobotState&, const RobotOdomState&, Vector3d& left, Vector3d& right)>;
 
     explicit MPC(StateSource src = StateSource(), int horizon = 10, int device = 0)
-        : estimates(src ? src : StateSource([] { return RobotOdomState(); })), qp(horizon, 1, device) {
+        : estimates(src ? src : StateSource([] { return RobotOdomState(); })), qp(horizon, 1, device), device_(device) {
+        mpc_b200_leg_default_model(&leg_model);
+        mpc_b200_swing_default_params(&swing_params);
+        for (int i = 0; i < 3; ++i) finalPosition(i) = 0.0;
         odom_state = estimates();
     }
 
     // reference include/MPCController.h:183-196
     void run(limxsdk::RobotState state, limxsdk::ImuData imu, limxsdk::RobotCmd& cmd, int iter) {
-        (void)imu; (void)cmd;
+        (void)imu;
         update_odom_state();
         calculateGait(iter);
+        if (enable_leg_pipeline && iter >= 0) {
+            computeFootPlacement(finalPosition);
+            computeSwingFootDesiredPosition(state, cmd, iter);
+        }
         computeSupportFootForce(state, iter);
+        if (enable_leg_pipeline) supportForceToTorque(state, cmd);
     }
 
     MPCParam param;
+    mpc_b200_leg_model leg_model;        // link offsets of include/MPCParam.h:13-38, joint axes (parameters)
+    mpc_b200_swing_params swing_params;  // gait / swing / IK constants of the reference
+    bool enable_leg_pipeline = true;     // false: force MPC only (BASELINE config 1b latency measurement)
+    bool kinematic_feet = false;         // true: the MPC's foot positions come from FK at state.q instead of the nominal offsets
     StateSource estimates;
     FootSource feet_from_kinematics;   // FK hook; default = nominal offsets under the base
     Vector3d desieredV_pos = make3(1.0, 0.0, 0.0);   // reference include/MPCController.h:16-17
@@ -57,6 +73,12 @@ public:
     double gaitPhase() const { return phase; }
     double remainingSwingTime() const { return remainSwingTime; }
     std::array<double, 6> supportFootForce() const { return qp.optimalForce(); }
+    std::array<double, 6> jointTorque() const { return tau_cmd; }            // tau = -J' f, [left 3, right 3]
+    std::array<double, 3> swingFootLanding() const { return {finalPosition(0), finalPosition(1), finalPosition(2)}; }
+    std::array<double, 3> swingFootNext() const { return next_foot; }
+    std::array<double, 6> footPositions() const { return fk_feet; }          // FK of both contact points at state.q
+    double ikError() const { return ik_err; }
+    int ikIterations() const { return ik_iters; }
     bool lastSolveCertified() const { return qp.lastStatus() == 0; }
 
     // reference include/MPCController.h:61-75, float members of MPCParam widened exactly as there
@@ -68,8 +90,53 @@ public:
         else { left_leg_state = 0; right_leg_state = 1; remainSwingTime = cycleTime - phase; }
     }
 
+    // reference include/MPCController.h:106-132 (host restatement; the device step recomputes it per robot)
+    void computeFootPlacement(Vector3d& fin) {
+        double px = currentPosition(0) + desieredV_pos(0) * remainSwingTime;
+        double py = currentPosition(1) + desieredV_pos(1) * remainSwingTime;
+        const double p_rel_max = 0.3;
+        double pfx_rel = desieredV_pos(0) * 0.5 * param.stance_time;
+        double pfy_rel = desieredV_pos(1) * 0.5 * param.stance_time;
+        pfx_rel = std::fmin(std::fmax(pfx_rel, -p_rel_max), p_rel_max);
+        pfy_rel = std::fmin(std::fmax(pfy_rel, -p_rel_max), p_rel_max);
+        px += pfx_rel; py += pfy_rel;
+        const auto& off = (left_leg_state == 1) ? param.static_foot_offset_left : param.static_foot_offset_right;
+        fin(0) = px + off[0]; fin(1) = py + off[1]; fin(2) = 0.0;
+    }
+
 private:
     static Vector3d make3(double a, double b, double c) { Vector3d v; v(0) = a; v(1) = b; v(2) = c; return v; }
+
+    void joint_angles(const limxsdk::RobotState& state, double q[6]) const {
+        for (int i = 0; i < 6; ++i) q[i] = i < (int)state.q.size() ? (double)state.q[i] : 0.0;
+    }
+
+    // reference include/MPCController.h:134-175: FK of the swing foot, interpolation towards the landing point,
+    // sine height profile, IK, and the write of the swing leg's joint targets into cmd.q
+    void computeSwingFootDesiredPosition(const limxsdk::RobotState& state, limxsdk::RobotCmd& cmd, int iter) {
+        double q[6], q_cmd[6], des_v[3] = {desieredV_pos(0), desieredV_pos(1), desieredV_pos(2)};
+        joint_angles(state, q);
+        for (int i = 0; i < 6; ++i) q_cmd[i] = i < (int)cmd.q.size() ? (double)cmd.q[i] : 0.0;
+        int32_t it = iter, leg = 0, its = 0;
+        const int rc = mpc_b200_swing_step_host(device_, &leg_model, &swing_params, 1, odom_state.pos, odom_state.quat, q, des_v, &it,
+                                                q_cmd, fk_feet.data(), next_foot.data(), &leg, &ik_err, &its);
+        if (rc != MPC_B200_OK) throw DeviceError(rc, std::string("mpc_b200_swing_step_host: ") + mpc_b200_strerror(rc));
+        ik_iters = its;
+        have_fk = true;
+        if (cmd.q.size() < 6) cmd.q.resize(6, 0.f);
+        for (int i = 3 * leg; i < 3 * leg + 3; ++i) cmd.q[i] = (float)q_cmd[i];
+    }
+
+    // tau = -J' f of the stance leg(s) into cmd.tau (the force half of the reference's empty stub)
+    void supportForceToTorque(const limxsdk::RobotState& state, limxsdk::RobotCmd& cmd) {
+        double q[6];
+        joint_angles(state, q);
+        const auto f = qp.optimalForce();
+        const int rc = mpc_b200_grf_to_torque_host(device_, &leg_model, 1, odom_state.quat, q, f.data(), tau_cmd.data());
+        if (rc != MPC_B200_OK) throw DeviceError(rc, std::string("mpc_b200_grf_to_torque_host: ") + mpc_b200_strerror(rc));
+        if (cmd.tau.size() < 6) cmd.tau.resize(6, 0.f);
+        for (int i = 0; i < 6; ++i) cmd.tau[i] = (float)tau_cmd[i];
+    }
 
     // reference include/MPCController.h:45-58
     void update_odom_state() {
@@ -87,7 +154,15 @@ private:
     void computeSupportFootForce(const limxsdk::RobotState& state, int iter) {
         Vector3d left, right;
         if (feet_from_kinematics) feet_from_kinematics(state, odom_state, left, right);
-        else {
+        else if (kinematic_feet) {
+            if (!have_fk) {
+                double q[6];
+                joint_angles(state, q);
+                const int rc = mpc_b200_leg_fk_host(device_, &leg_model, 1, odom_state.pos, odom_state.quat, q, fk_feet.data(), nullptr);
+                if (rc != MPC_B200_OK) throw DeviceError(rc, std::string("mpc_b200_leg_fk_host: ") + mpc_b200_strerror(rc));
+            }
+            for (int i = 0; i < 3; ++i) { left(i) = fk_feet[i]; right(i) = fk_feet[3 + i]; }
+        } else {
             const double c = std::cos(currentOrientation(2)), s = std::sin(currentOrientation(2));
             const auto& L = param.static_foot_offset_left; const auto& R = param.static_foot_offset_right;
             left(0) = currentPosition(0) + c * L[0] - s * L[1]; left(1) = currentPosition(1) + s * L[0] + c * L[1]; left(2) = currentPosition(2) + L[2];
@@ -98,10 +173,18 @@ private:
         qp.setReference(desieredV_ori(2), desieredV_pos(0));
         qp.setGaitIteration(iter);
         qp.solve();
+        have_fk = false;
     }
 
     RobotOdomState odom_state;
     mpcQP qp;
+    int device_ = 0;
+    bool have_fk = false;
+    Vector3d finalPosition;
+    std::array<double, 3> next_foot{{0, 0, 0}};
+    std::array<double, 6> fk_feet{{0, 0, 0, 0, 0, 0}}, tau_cmd{{0, 0, 0, 0, 0, 0}};
+    double ik_err = 0.0;
+    int ik_iters = 0;
     int left_leg_state = 0, right_leg_state = 0;
     double phase = 0, remainSwingTime = 0;
     Vector3d currentPosition, currentVelocity, currentOrientation, currentAngularVelocity;

@@ -22,10 +22,18 @@ int main(int argc, char** argv) {
         auto f = mpc.supportFootForce();
         printf("forces %.17g %.17g %.17g %.17g %.17g %.17g certified %d\n", f[0], f[1], f[2], f[3], f[4], f[5],
                (int)mpc.lastSolveCertified());
+        st.q = {0.0f, 0.4f, -0.8f, 0.0f, 0.4f, -0.8f};   // bent knees
         mpc.run(st, imu, cmd, 250);   // left swing / right stance per calculateGait
         f = mpc.supportFootForce();
         printf("gait250 left_state %d right_state %d forces %.17g %.17g %.17g %.17g %.17g %.17g\n", mpc.leftLegState(),
                mpc.rightLegState(), f[0], f[1], f[2], f[3], f[4], f[5]);
+        auto tq = mpc.jointTorque(); auto nf = mpc.swingFootNext(); auto fk = mpc.footPositions();
+        printf("gait250 tau %.17g %.17g %.17g %.17g %.17g %.17g\n", tq[0], tq[1], tq[2], tq[3], tq[4], tq[5]);
+        printf("gait250 fk_feet %.17g %.17g %.17g %.17g %.17g %.17g\n", fk[0], fk[1], fk[2], fk[3], fk[4], fk[5]);
+        printf("gait250 swing_next %.17g %.17g %.17g cmd_q %.9g %.9g %.9g %.9g %.9g %.9g ik_err %.6g ik_iters %d\n", nf[0], nf[1], nf[2],
+               cmd.q[0], cmd.q[1], cmd.q[2], cmd.q[3], cmd.q[4], cmd.q[5], mpc.ikError(), mpc.ikIterations());
+        st.q = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        mpc.enable_leg_pipeline = false;   // the latency figure below is the force MPC alone (BASELINE config 1b)
         std::vector<double> us;
         for (int i = 0; i < calls + 100; ++i) {
             auto t0 = std::chrono::steady_clock::now();

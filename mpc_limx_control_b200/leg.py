@@ -1,0 +1,82 @@
+"""Host-side plumbing of the leg kinematics kernels (csrc/leg_b200.cu) over the C ABI: the rest of the
+reference's MPC::run around the force MPC (include/MPCController.h:183-196) for a batch of robots.
+torch owns the device memory and the stream; nothing here computes."""
+import ctypes as C
+
+import torch
+
+from . import _capi
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class LegKinematics:
+    """Batched FK / swing-leg step / GRF->torque on one GPU (device tensors in, device tensors out)."""
+
+    def __init__(self, device=0, model=None, swing=None):
+        self.lib = _capi.lib()
+        self.model = model or default_model()
+        self.swing = swing or default_swing()
+        self.tdev = torch.device("cuda", int(device))
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.tdev).cuda_stream)
+
+    def _chk(self, t, dtype, numel, name):
+        if t.device != self.tdev or t.dtype != dtype or not t.is_contiguous() or t.numel() != numel:
+            raise ValueError(f"{name}: expected contiguous {dtype} tensor of {numel} elements on {self.tdev}")
+
+    def fk(self, base_pos, base_quat, q, want_jac=False):
+        """base_pos [B,3], base_quat [B,4] ([x,y,z,w]), q [B,6] -> feet [B,2,3] (and jac [B,2,3,3])."""
+        B = q.shape[0]
+        self._chk(base_pos, torch.float64, 3 * B, "base_pos"); self._chk(base_quat, torch.float64, 4 * B, "base_quat")
+        self._chk(q, torch.float64, 6 * B, "q")
+        feet = torch.empty((B, 2, 3), dtype=torch.float64, device=self.tdev)
+        jac = torch.empty((B, 2, 3, 3), dtype=torch.float64, device=self.tdev) if want_jac else None
+        with torch.cuda.device(self.tdev):
+            _capi.check(self.lib.mpc_b200_leg_fk_device(C.byref(self.model), B, _ptr(base_pos), _ptr(base_quat), _ptr(q), _ptr(feet),
+                                                        _ptr(jac), self._stream()))
+        return (feet, jac) if want_jac else feet
+
+    def swing_step(self, base_pos, base_quat, q, des_vel, it, q_cmd):
+        """One swing-leg step per robot; q_cmd [B,6] is updated in place (swing leg entries only).
+        Returns dict(feet [B,2,3], next_foot [B,3], swing_leg [B], ik_err [B], ik_iters [B])."""
+        B = q.shape[0]
+        for t, n, nm in ((base_pos, 3, "base_pos"), (base_quat, 4, "base_quat"), (q, 6, "q"), (des_vel, 3, "des_vel"), (q_cmd, 6, "q_cmd")):
+            self._chk(t, torch.float64, n * B, nm)
+        self._chk(it, torch.int32, B, "iter")
+        feet = torch.empty((B, 2, 3), dtype=torch.float64, device=self.tdev)
+        nxt = torch.empty((B, 3), dtype=torch.float64, device=self.tdev)
+        leg = torch.empty(B, dtype=torch.int32, device=self.tdev)
+        err = torch.empty(B, dtype=torch.float64, device=self.tdev)
+        its = torch.empty(B, dtype=torch.int32, device=self.tdev)
+        with torch.cuda.device(self.tdev):
+            _capi.check(self.lib.mpc_b200_swing_step_device(C.byref(self.model), C.byref(self.swing), B, _ptr(base_pos), _ptr(base_quat),
+                                                            _ptr(q), _ptr(des_vel), _ptr(it), _ptr(q_cmd), _ptr(feet), _ptr(nxt), _ptr(leg),
+                                                            _ptr(err), _ptr(its), self._stream()))
+        return dict(feet=feet, next_foot=nxt, swing_leg=leg, ik_err=err, ik_iters=its)
+
+    def grf_to_torque(self, base_quat, q, u0, tau=None):
+        """tau [B,6] = -J(q)' f per leg from the first-step forces u0 [B,6]."""
+        B = q.shape[0]
+        self._chk(base_quat, torch.float64, 4 * B, "base_quat"); self._chk(q, torch.float64, 6 * B, "q"); self._chk(u0, torch.float64, 6 * B, "u0")
+        if tau is None:
+            tau = torch.empty((B, 6), dtype=torch.float64, device=self.tdev)
+        with torch.cuda.device(self.tdev):
+            _capi.check(self.lib.mpc_b200_grf_to_torque_device(C.byref(self.model), B, _ptr(base_quat), _ptr(q), _ptr(u0), _ptr(tau),
+                                                               self._stream()))
+        return tau
+
+
+def default_model():
+    m = _capi.LegModel()
+    _capi.check(_capi.lib().mpc_b200_leg_default_model(C.byref(m)))
+    return m
+
+
+def default_swing():
+    p = _capi.SwingParams()
+    _capi.check(_capi.lib().mpc_b200_swing_default_params(C.byref(p)))
+    return p

@@ -139,3 +139,41 @@ def lti_update(Ad, Bd, xi, u):
     xi = np.array(xi, dtype=np.float64); u = np.array(u, dtype=np.float64)
     lti().emul_lti_update(NX, NU, _pp(Ad), _pp(Bd), _pp(xi), _pp(u))
     return xi
+
+
+# ---- leg kinematics (csrc/leg_core.cuh) -----------------------------------------------------------------
+_leg = None
+
+
+def leg_lib():
+    global _leg
+    if _leg is None:
+        subprocess.check_call(["make", "-s", "-C", os.path.join(_ROOT, "tests", "emul")])
+        _leg = C.CDLL(os.path.join(_ROOT, "tests", "emul", "libemul_leg.so"))
+    return _leg
+
+
+def leg_fk(m, pos, quat, q6):
+    pos = np.ascontiguousarray(pos, np.float64); quat = np.ascontiguousarray(quat, np.float64); q6 = np.ascontiguousarray(q6, np.float64)
+    feet = np.zeros((2, 3)); jac = np.zeros((2, 3, 3))
+    leg_lib().emul_leg_fk(C.byref(m), pos.ctypes.data_as(_dp), quat.ctypes.data_as(_dp), q6.ctypes.data_as(_dp),
+                          feet.ctypes.data_as(_dp), jac.ctypes.data_as(_dp))
+    return feet, jac
+
+
+def swing_step(m, sp, pos, quat, q6, des_v, it, q_cmd):
+    a = lambda x: np.ascontiguousarray(x, np.float64)
+    pos, quat, q6, des_v = a(pos), a(quat), a(q6), a(des_v)
+    q_cmd = a(q_cmd).copy(); feet = np.zeros(6); nxt = np.zeros(3); err = C.c_double(); its = C.c_int()
+    leg = leg_lib().emul_swing_step(C.byref(m), C.byref(sp), pos.ctypes.data_as(_dp), quat.ctypes.data_as(_dp), q6.ctypes.data_as(_dp),
+                                    des_v.ctypes.data_as(_dp), int(it), q_cmd.ctypes.data_as(_dp), feet.ctypes.data_as(_dp),
+                                    nxt.ctypes.data_as(_dp), C.byref(err), C.byref(its))
+    return dict(leg=leg, q_cmd=q_cmd, feet=feet.reshape(2, 3), next_foot=nxt, ik_err=err.value, ik_iters=its.value)
+
+
+def grf_to_torque(m, quat, q6, u0):
+    a = lambda x: np.ascontiguousarray(x, np.float64)
+    quat, q6, u0 = a(quat), a(q6), a(u0)
+    tau = np.zeros(6)
+    leg_lib().emul_grf_to_torque(C.byref(m), quat.ctypes.data_as(_dp), q6.ctypes.data_as(_dp), u0.ctypes.data_as(_dp), tau.ctypes.data_as(_dp))
+    return tau

@@ -21,8 +21,8 @@ class Tron1Params(C.Structure):
 
 
 def build(force=False):
-    src = os.path.join(_ROOT, "oracle", "mpc_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(_ROOT, "oracle", f) for f in ("mpc_oracle.c", "leg_oracle.c", "mpc_oracle.h", "leg_oracle.h")]
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-s", "-C", os.path.join(_ROOT, "oracle")])
     return _SO
 
@@ -201,3 +201,46 @@ def tron1_rollout(p, N, steps, x, omega_yaw, velocity_x, iter0, off_l, off_r, g=
     bad = lib().orc_tron1_rollout(C.byref(p), C.byref(g), N, int(steps), _p(x), C.c_double(omega_yaw), C.c_double(velocity_x),
                                   int(iter0), _p(off_l), _p(off_r), _p(U))
     return x, U, bad
+
+
+# ---- leg kinematics oracle (oracle/leg_oracle.c) -----------------------------------------------------
+class LegModel(C.Structure):
+    _fields_ = [("offset", C.c_double * 30), ("axis", C.c_double * 18)]
+
+
+class SwingParams(C.Structure):
+    _fields_ = [("dt", C.c_float), ("swing_time", C.c_float), ("stance_time", C.c_float), ("gait_height", C.c_float),
+                ("p_rel_max", C.c_double), ("foot_offset_left", C.c_double * 3), ("foot_offset_right", C.c_double * 3),
+                ("ik_tol", C.c_double), ("ik_dt", C.c_double), ("ik_damp", C.c_double), ("ik_max_iter", C.c_int32)]
+
+
+def leg_defaults():
+    m, p = LegModel(), SwingParams()
+    lib().orc_leg_defaults(C.byref(m), C.byref(p))
+    return m, p
+
+
+def _v(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def leg_fk(m, leg, pos, quat, q3, want_jac=True):
+    pos, quat, q3 = _v(pos), _v(quat), _v(q3)
+    p = np.zeros(3); J = np.zeros((3, 3))
+    lib().orc_leg_fk(C.byref(m), int(leg), _p(pos), _p(quat), _p(q3), _p(p), _p(J) if want_jac else None)
+    return (p, J) if want_jac else p
+
+
+def swing_step(m, sp, pos, quat, q6, des_v, it, q_cmd):
+    pos, quat, q6, des_v = _v(pos), _v(quat), _v(q6), _v(des_v)
+    q_cmd = _v(q_cmd).copy(); feet = np.zeros(6); nxt = np.zeros(3); err = C.c_double(); its = C.c_int()
+    leg = lib().orc_swing_step(C.byref(m), C.byref(sp), _p(pos), _p(quat), _p(q6), _p(des_v), int(it), _p(q_cmd), _p(feet), _p(nxt),
+                               C.byref(err), C.byref(its))
+    return dict(leg=leg, q_cmd=q_cmd, feet=feet.reshape(2, 3), next_foot=nxt, ik_err=err.value, ik_iters=its.value)
+
+
+def grf_to_torque(m, quat, q6, u0):
+    quat, q6, u0 = _v(quat), _v(q6), _v(u0)
+    tau = np.zeros(6)
+    lib().orc_grf_to_torque(C.byref(m), _p(quat), _p(q6), _p(u0), _p(tau))
+    return tau

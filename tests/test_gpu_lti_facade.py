@@ -111,4 +111,18 @@ def test_facade_tron1_single_binary(golden):
     assert g[2] == "1" and g[4] == "0"           # iter 250: left swing, right stance (calculateGait)
     fg = np.array([float(x) for x in g[6:12]])
     assert np.all(fg[:3] == 0.0) and fg[5] > 0.0  # swing foot carries no force
-    assert lines[2].startswith("latency_us")
+    # the rest of MPC::run: FK, swing-leg targets and stance torques (csrc/leg_b200.cu) against the oracle
+    import oracle_lib as O
+    mo, po = O.leg_defaults()
+    q = np.array([0.0, 0.4, -0.8, 0.0, 0.4, -0.8], np.float32).astype(np.float64)
+    pos, quat = np.array([0.0, 0.0, 0.81181]), np.array([0.0, 0.0, 0.0, 1.0])
+    ref = O.swing_step(mo, po, pos, quat, q, [0.0, 0.0, 0.0], 250, np.zeros(6))
+    tau = np.array([float(x) for x in lines[2].split()[2:8]])
+    fk = np.array([float(x) for x in lines[3].split()[2:8]])
+    sw = lines[4].split()
+    nxt = np.array([float(x) for x in sw[2:5]]); cq = np.array([float(x) for x in sw[6:12]])
+    assert ref["leg"] == 0 and np.abs(fk - ref["feet"].reshape(-1)).max() < 1e-12 and np.abs(nxt - ref["next_foot"]).max() < 1e-12
+    assert np.abs(cq[:3] - ref["q_cmd"][:3].astype(np.float32)).max() < 1e-6 and np.all(cq[3:] == 0.0)    # cmd.q is float
+    assert int(sw[-1]) == ref["ik_iters"] and abs(float(sw[-3]) - ref["ik_err"]) < 1e-6 * max(1.0, ref["ik_err"])
+    assert np.abs(tau - O.grf_to_torque(mo, quat, q, fg)).max() < 1e-9 and np.all(tau[:3] == 0.0) and np.abs(tau[3:]).max() > 0.1
+    assert lines[5].startswith("latency_us")
