@@ -181,17 +181,47 @@ MPC_HD void model_step(const Tron1Const& P, WK& S, const double* xref, int k) {
 template <int N>
 MPC_HD double step_weight(const Tron1Const& P, int i) { return i == N ? P.p_scale : 1.0; }
 
+// ---- serial scans over the horizon, one lane per component ------------------------------------------------
+// The values are first pulled into registers (independent loads, pipelined), scanned there (one dependent add
+// per step) and written back: an in-place `acc += a[j]; a[j] = acc` loop serialises a shared-memory load, an
+// add and a store per step (~50 cycles each).  Same order of additions as the plain loop, so bit-identical.
+template <int N, int STRIDE>
+MPC_HD void suffix_scan_inplace(double* a) {          // a[j * STRIDE] <- sum_{i >= j} a[i * STRIDE]
+    constexpr int CH = (N % 10 == 0) ? 10 : N;
+    double acc = 0.0;
+    for (int c0 = N - CH; c0 >= 0; c0 -= CH) {
+        double v[CH];
+#pragma unroll
+        for (int j = 0; j < CH; ++j) v[j] = a[(c0 + j) * STRIDE];
+#pragma unroll
+        for (int j = CH - 1; j >= 0; --j) { acc += v[j]; v[j] = acc; }
+#pragma unroll
+        for (int j = 0; j < CH; ++j) a[(c0 + j) * STRIDE] = v[j];
+    }
+}
+// out[(k + 1) * OSTRIDE] = sum_{m <= k} scale * in[m * ISTRIDE], out[0] = 0   (exclusive prefix, N + 1 outputs)
+template <int N, int ISTRIDE, int OSTRIDE>
+MPC_HD void prefix_scan(const double* in, double* out, double scale, bool scaled) {
+    constexpr int CH = (N % 10 == 0) ? 10 : N;
+    double acc = 0.0;
+    out[0] = 0.0;
+    for (int c0 = 0; c0 < N; c0 += CH) {
+        double v[CH];
+#pragma unroll
+        for (int j = 0; j < CH; ++j) v[j] = in[(c0 + j) * ISTRIDE];
+#pragma unroll
+        for (int j = 0; j < CH; ++j) { acc += scaled ? scale * v[j] : v[j]; v[j] = acc; }
+#pragma unroll
+        for (int j = 0; j < CH; ++j) out[(c0 + j + 1) * OSTRIDE] = v[j];
+    }
+}
+
 // ---- phase: prefix / suffix sums that depend on the yaw sequence only ---------------------------
 template <class WK, class G>
 MPC_HD void horizon_sums(const Tron1Const& P, WK& S, const G& g) {
     [[maybe_unused]] constexpr int N = WK::N;
     // prefix cc_i, ss_i (two serial scans, one per thread)
-    for (int c = g.tid(); c < 2; c += g.size()) {
-        double* out = c ? S.ss : S.cc;
-        double acc = 0.0;
-        out[0] = 0.0;
-        for (int k = 0; k < N; ++k) { acc += S.cs[2 * k + c]; out[k + 1] = acc; }
-    }
+    for (int c = g.tid(); c < 2; c += g.size()) prefix_scan<N, 2, 1>(S.cs + c, c ? S.ss : S.cc, 1.0, false);
     g.sync();
     for (int j = g.tid(); j < N; j += g.size()) {
         S.dc[j] = 0.5 * S.cs[2 * j] - S.cc[j + 1];
@@ -206,10 +236,7 @@ MPC_HD void horizon_sums(const Tron1Const& P, WK& S, const G& g) {
     }
     g.sync();
     // ... then suffix sums over i > j, one component per thread (uniform code, no divergence)
-    for (int c = g.tid(); c < 8; c += g.size()) {
-        double acc = 0.0;
-        for (int j = N - 1; j >= 0; --j) { acc += S.SW[8 * j + c]; S.SW[8 * j + c] = acc; }
-    }
+    for (int c = g.tid(); c < 8; c += g.size()) suffix_scan_inplace<N, 8>(S.SW + c);
     g.sync();
 }
 
@@ -258,14 +285,7 @@ MPC_HD void input_response(const Tron1Const& P, WK& S, const double* u, const G&
     }
     g.sync();
     // level 1: omega_k = Ts sum_{m<k} tau_m, v_k = Ts sum_{m<k} phi_m  (one component per thread, uniform code)
-    for (int c = g.tid(); c < 6; c += g.size()) {
-        double acc = 0.0;
-        double* dst = S.ee + 6 + c;                      // omega -> 6..8, v -> 9..11
-        for (int k = 0; k <= N; ++k) {
-            dst[12 * k] = acc;
-            if (k < N) acc += Ts * S.tau()[6 * k + c];
-        }
-    }
+    for (int c = g.tid(); c < 6; c += g.size()) prefix_scan<N, 6, 12>(S.tau() + c, S.ee + 6 + c, Ts, true);   // omega -> 6..8, v -> 9..11
     g.sync();
     // level 2: per-step increments  dTheta_k = Ts Rz_k'(omega_k + Ts/2 tau_k),  dp_k = Ts (v_k + Ts/2 phi_k)
     for (int k = g.tid(); k < N; k += g.size()) {
@@ -281,14 +301,7 @@ MPC_HD void input_response(const Tron1Const& P, WK& S, const double* u, const G&
     }
     g.sync();
     // level 3: Theta_k, p_k = prefix sums of the increments
-    for (int c = g.tid(); c < 6; c += g.size()) {
-        double acc = 0.0;
-        double* dst = S.ee + c;                          // Theta -> 0..2, p -> 3..5
-        for (int k = 0; k <= N; ++k) {
-            dst[12 * k] = acc;
-            if (k < N) acc += S.tau()[6 * k + c];
-        }
-    }
+    for (int c = g.tid(); c < 6; c += g.size()) prefix_scan<N, 6, 12>(S.tau() + c, S.ee + c, 1.0, false);       // Theta -> 0..2, p -> 3..5
     g.sync();
 }
 
@@ -318,10 +331,7 @@ MPC_HD void adjoint(const Tron1Const& P, WK& S, const double* e, double* out, co
     }
     g.sync();
     // suffix sums over i > j, stored at row j  (row j currently holds step j+1)
-    for (int c = g.tid(); c < 18; c += g.size()) {
-        double acc = 0.0;
-        for (int j = N - 1; j >= 0; --j) { acc += S.adj[18 * j + c]; S.adj[18 * j + c] = acc; }
-    }
+    for (int c = g.tid(); c < 18; c += g.size()) suffix_scan_inplace<N, 18>(S.adj + c);
     g.sync();
     for (int s = g.tid(); s < 2 * N; s += g.size()) {
         int j = s >> 1;

@@ -1,0 +1,64 @@
+"""Throughput of the leg kinematics kernels (csrc/leg_b200.cu) against their HBM roofline, with the CPU oracle
+timed beside them.  One JSON line per kernel.  usage (GPU box): python tools/bench_leg.py [B]"""
+import json, os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch
+from scipy.spatial.transform import Rotation
+from mpc_limx_control_b200.leg import LegKinematics
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
+try:
+    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]; src = "MEASURED_PEAKS.json hbm_gbs"
+except Exception:
+    peak, src = 6650.0, "fallback 6650 GB/s"
+rng = np.random.default_rng(0)
+pos = rng.uniform(-1, 1, (B, 3)) + np.array([0, 0, 0.655])
+quat = Rotation.from_euler("xyz", rng.uniform([-0.05, -0.05, -np.pi], [0.05, 0.05, np.pi], (B, 3))).as_quat()
+q = rng.uniform(-0.05, 0.05, (B, 6)) + np.array([0.0, 0.4, -0.8, 0.0, 0.4, -0.8])
+dv = rng.uniform(-0.3, 0.3, (B, 3)); dv[:, 2] = 0
+it = rng.integers(0, 10_000_000, B).astype(np.int32)
+u0 = rng.uniform(-40, 160, (B, 6))
+t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+d = dict(pos=t(pos), quat=t(quat), q=t(q), dv=t(dv), it=t(it), u0=t(u0), qc=t(q.copy()))
+lk = LegKinematics()
+tau = torch.empty((B, 6), dtype=torch.float64, device="cuda")
+
+
+def timeit(fn, n=30):
+    for _ in range(5):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record()
+    for _ in range(n):
+        fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e-3 / n
+
+
+import oracle_lib as O
+mo, po = O.leg_defaults()
+ncpu = 20000
+
+
+def cpu_rate(fn):
+    t0 = time.perf_counter()
+    for b in range(ncpu):
+        fn(b)
+    return ncpu / (time.perf_counter() - t0)
+
+
+cases = [
+    ("leg_fk_kernel (feet)", 152, lambda: lk.fk(d["pos"], d["quat"], d["q"]), lambda b: [O.leg_fk(mo, l, pos[b], quat[b], q[b, 3 * l:3 * l + 3], want_jac=False) for l in (0, 1)]),
+    ("leg_fk_kernel (feet + Jacobians)", 296, lambda: lk.fk(d["pos"], d["quat"], d["q"], want_jac=True), lambda b: [O.leg_fk(mo, l, pos[b], quat[b], q[b, 3 * l:3 * l + 3]) for l in (0, 1)]),
+    ("swing_step_kernel", 244, lambda: lk.swing_step(d["pos"], d["quat"], d["q"], d["dv"], d["it"], d["qc"]), lambda b: O.swing_step(mo, po, pos[b], quat[b], q[b], dv[b], int(it[b]), q[b])),
+    ("grf_torque_kernel", 176, lambda: lk.grf_to_torque(d["quat"], d["q"], d["u0"], tau), lambda b: O.grf_to_torque(mo, quat[b], q[b], u0[b])),
+]
+for name, nbytes, fn, cfn in cases:
+    s = timeit(fn)
+    gbs = nbytes * B / s / 1e9
+    print(json.dumps({"kernel": name, "B": B, "us": s * 1e6, "robots_per_s": B / s, "bytes_per_robot": nbytes,
+                      "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "peak_source": src},
+                      "cpu_oracle": {"robots_per_s": cpu_rate(cfn), "cores": 1, "kind": "port (python ctypes call per robot)", "sample": ncpu},
+                      "note": "outputs allocated per call by the torch wrapper (cudaMalloc-free caching allocator)"}))
