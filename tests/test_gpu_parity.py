@@ -225,6 +225,68 @@ def test_full_size_properties_config2(torch_cuda):
     eng.close()
 
 
+def _check_force_properties(F, c_ref, mu=0.5, fmax=2 * 9.585 * 9.8):
+    B, N = F.shape[0], F.shape[1]
+    F4 = F.reshape(B, N, 2, 3)
+    assert np.all(F4[c_ref == 0] == 0.0)                              # swing feet: exactly zero force
+    assert (np.abs(F4[..., 0]) <= mu * F4[..., 2] + 1e-9).all()       # friction pyramid
+    assert (np.abs(F4[..., 1]) <= mu * F4[..., 2] + 1e-9).all()
+    assert (F4[..., 2] >= -1e-12).all() and (F4[..., 2] <= fmax + 1e-9).all()
+
+
+@pytest.mark.parametrize("name,N,B,seed,stride", [("config3", 20, 65536, 1002, 2048), ("config4", 50, 8192, 1003, 2048)])
+def test_full_size_properties_configs_3_4(torch_cuda, name, N, B, seed, stride):
+    """BASELINE configs[2] (B=65536, N=20) and configs[3] (B=8192, N=50) at full size on one GPU: every solve
+    certified, feasibility, exact zeros on swing feet, determinism, and oracle parity on a strided sample."""
+    torch = torch_cuda
+    Ts = 0.005
+    d = synth.tron1_batch(seed, B, N, Ts)
+    eng = make_engine(N, B, Ts=Ts)
+    t = to_dev(torch, d)
+    F, st, it = eng.solve(t["x0"], t["x_ref"], t["feet"], it=t["iter"])
+    Fb, _, _ = eng.solve(t["x0"], t["x_ref"], t["feet"], it=t["iter"])
+    torch.cuda.synchronize()
+    assert torch.equal(F, Fb) and int((st != 0).sum()) == 0
+    idx = np.arange(0, B, stride)
+    Fs = F[torch.from_numpy(idx).cuda()].cpu().numpy()
+    contact = eng.contact_schedule(t["iter"]).cpu().numpy()
+    c_ref = np.stack([O.contact_schedule(int(i), N) for i in d["iter"][idx]])
+    assert np.array_equal(contact[idx], c_ref)                        # mode indices bit-exact
+    _check_force_properties(F.cpu().numpy(), contact)
+    po = O.tron1_defaults(Ts=Ts)
+    Fo, so, _ = O.tron1_solve_batch(po, N, d["x0"][idx], d["x_ref"][idx], d["feet"][idx], c_ref, nthreads=8)
+    assert (so == 0).all()
+    assert np.abs(Fs - Fo).max() / max(1.0, np.abs(Fo).max()) < 1e-4
+    eng.close()
+
+
+def test_full_size_rollout_config5(torch_cuda):
+    """BASELINE configs[4]: 16384 robots x 1000 closed-loop control steps (one GPU holds the whole job here):
+    every step certified, states finite, forces feasible, and the first 25 steps of a strided sample equal the
+    oracle loop."""
+    torch = torch_cuda
+    N, Ts, steps, B = 10, 0.005, 1000, 16384
+    d = synth.tron1_batch(1004, B, N, Ts)
+    eng = make_engine(N, B, Ts=Ts)
+    x = torch.from_numpy(d["x0"].copy()).cuda()
+    args = (torch.from_numpy(d["omega_yaw"]).cuda(), torch.from_numpy(d["velocity_x"]).cuda(), torch.from_numpy(d["iter"]).cuda())
+    _, bad, its = eng.rollout(x, *args, steps)
+    torch.cuda.synchronize()
+    assert int(bad.sum()) == 0 and int(its.min()) >= steps and bool(torch.isfinite(x).all())
+    idx = np.arange(0, B, 4096)
+    xs = torch.from_numpy(d["x0"][idx].copy()).cuda()
+    traj, bad2, _ = eng.rollout(xs, args[0][idx].contiguous(), args[1][idx].contiguous(), args[2][idx].contiguous(), 25, want_traj=True)
+    torch.cuda.synchronize()
+    U = traj.cpu().numpy(); X = xs.cpu().numpy()
+    assert (U[..., 2] >= -1e-12).all() and (U[..., 5] >= -1e-12).all() and (np.abs(U[..., 0]) <= 0.5 * U[..., 2] + 1e-9).all()
+    po = O.tron1_defaults(Ts=Ts)
+    offl = list(eng.params.foot_offset_left); offr = list(eng.params.foot_offset_right)
+    for j, b in enumerate(idx):
+        xo, Uo, bo = O.tron1_rollout(po, N, 25, d["x0"][b], d["omega_yaw"][b], d["velocity_x"][b], int(d["iter"][b]), offl, offr)
+        assert bo == 0 and np.abs(U[j] - Uo).max() / max(1.0, np.abs(Uo).max()) < 1e-4 and np.abs(X[j] - xo).max() < 1e-6
+    eng.close()
+
+
 def test_fp64_peak_measurement(torch_cuda):
     from mpc_limx_control_b200.engine import measure_fp64_peak
     tf = measure_fp64_peak(0)
