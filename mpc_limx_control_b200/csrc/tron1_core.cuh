@@ -544,6 +544,38 @@ __device__ __forceinline__ double fast_rcp(double d) {
 #ifndef MPC_GJ_STAGES
 #define MPC_GJ_STAGES 5
 #endif
+template <int W, int BUF, class WK, class G>
+__device__ __forceinline__ void gj_column(double (&w)[WK::NC], double& b, double& inv, double& myinv, bool& ok,
+                                          WK& S, const G& g, const int k) {
+    const int t = g.tid();
+    // pivot-to-pivot chain: inv_k -> next pivot candidate (one DFMA) -> SHFL -> MUFU -> 3 DFMA; everything else
+    // (the multiplier, the pivot-row select, the positivity test) is formed off that chain
+    const double w0m = (t == k) ? 0.0 : w[0];          // the pivot row only shifts
+    const double q = w0m * w[0];
+    const double piv = fma(-q, inv, w[W > 1 ? 1 : 0]);  // next pivot candidate (c[1] of row k+1 is its own w[0])
+    const double m = w0m * inv;
+    if (t == k) myinv = inv;
+    double* cb = S.colbuf + BUF * WK::CBS;             // static toggle: the caller alternates BUF
+    if (t > k) cb[t - k] = w[0];
+    if (t == k) cb[0] = b;
+    if (G::kThreads != 32 && t == k + 1 && k + 1 < WK::NC) S.w[k + 1] = piv;
+    g.sync();
+    double d;
+    if (G::kThreads == 32) d = __shfl_sync(0xffffffffu, piv, (k + 1) & 31);
+    else d = S.w[k + 1 < WK::NC ? k + 1 : k];
+    if (k + 1 < WK::NC && !(d > 0.0)) ok = false;       // reported as a failed solve; the garbage that follows is discarded
+    inv = fast_rcp(d);
+    b -= m * cb[0];
+    if (W > 1) w[0] = w[W > 1 ? 1 : 0] - m * cb[1];
+#pragma unroll
+    for (int p = 2; p + 1 < W; p += 2) {
+        const double2 c2 = *reinterpret_cast<const double2*>(cb + p);
+        w[p - 1] = w[p] - m * c2.x;
+        w[p] = w[p + 1] - m * c2.y;
+    }
+    if (W > 2 && (W & 1)) w[W - 2] = w[W - 1] - m * cb[W - 1];
+}
+
 template <int W, int KS, class WK, class G>
 __device__ __forceinline__ void gj_stage(double (&w)[WK::NC], double& b, double& inv, double& myinv, bool& ok,
                                          WK& S, const G& g, const int k0) {
@@ -551,35 +583,12 @@ __device__ __forceinline__ void gj_stage(double (&w)[WK::NC], double& b, double&
     // pivot is started as soon as its candidate exists (own registers, before the barrier), so that its
     // SHFL -> MUFU -> Newton chain overlaps the barrier, the broadcast loads and the W-1 row updates of the
     // current column (the warp issues in order: without the rotation the chain and the updates serialise).
-    const int t = g.tid();
+    // Columns run in even/odd pairs so that the double-buffer toggle is static (k0 is even).
+    static_assert(KS % 2 == 0, "even/odd column pairs");
 #pragma unroll 1
-    for (int k = k0; k < k0 + KS; ++k) {
-        // pivot-to-pivot chain: inv_k -> next pivot candidate (one DFMA) -> SHFL -> MUFU -> 3 DFMA; everything else
-        // (the multiplier, the pivot-row select, the positivity test) is formed off that chain
-        const double w0m = (t == k) ? 0.0 : w[0];          // the pivot row only shifts
-        const double q = w0m * w[0];
-        const double piv = fma(-q, inv, w[W > 1 ? 1 : 0]);  // next pivot candidate (c[1] of row k+1 is its own w[0])
-        const double m = w0m * inv;
-        if (t == k) myinv = inv;
-        double* cb = S.colbuf + (k & 1) * WK::CBS;
-        if (t > k) cb[t - k] = w[0];
-        if (t == k) cb[0] = b;
-        if (G::kThreads != 32 && t == k + 1 && k + 1 < WK::NC) S.w[k + 1] = piv;
-        g.sync();
-        double d;
-        if (G::kThreads == 32) d = __shfl_sync(0xffffffffu, piv, (k + 1) & 31);
-        else d = S.w[k + 1 < WK::NC ? k + 1 : k];
-        if (k + 1 < WK::NC && !(d > 0.0)) ok = false;       // reported as a failed solve; the garbage that follows is discarded
-        inv = fast_rcp(d);
-        b -= m * cb[0];
-        if (W > 1) w[0] = w[W > 1 ? 1 : 0] - m * cb[1];
-#pragma unroll
-        for (int p = 2; p + 1 < W; p += 2) {
-            const double2 c2 = *reinterpret_cast<const double2*>(cb + p);
-            w[p - 1] = w[p] - m * c2.x;
-            w[p] = w[p + 1] - m * c2.y;
-        }
-        if (W > 2 && (W & 1)) w[W - 2] = w[W - 1] - m * cb[W - 1];
+    for (int k = k0; k < k0 + KS; k += 2) {
+        gj_column<W, 0, WK, G>(w, b, inv, myinv, ok, S, g, k);
+        gj_column<W, 1, WK, G>(w, b, inv, myinv, ok, S, g, k + 1);
     }
 }
 
