@@ -612,14 +612,31 @@ __device__ __noinline__ bool gj_solve_regs(WK& S, const G& g) {
     const double* A = S.Ap();
     double w[NC];
     const bool row = t < n;
-    const double* rowp = A + MPC_PK(row ? t : 0, 0);    // A[t][j], j <= t
-    const double* colp = A + (row ? t : 0);             // A[j][t] = colp[j (j + 1) / 2], j > t
+    double b;
+    if (n == NC) {
+        // full size (the common case): two predicated loads per entry, no padding logic.  Lanes beyond the matrix
+        // hold a copy of the last row: they are never pivots and everything they publish lands in window slots
+        // beyond column NC-1, which never feed a real slot.
+        const int tt = t < NC ? t : NC - 1;
+        const double* rowp = A + MPC_PK(tt, 0);         // A[t][j], j <= t
+        const double* colp = A + tt;                    // A[j][t] = colp[j (j + 1) / 2], j > t
 #pragma unroll
-    for (int j = 0; j < NC; ++j) {
-        const double* q = (j <= t) ? rowp + j : colp + j * (j + 1) / 2;
-        w[j] = (row && j < n) ? *q : ((j == t) ? 1.0 : 0.0);
+        for (int j = 0; j < NC; ++j) {
+            double v;
+            if (j <= tt) v = rowp[j]; else v = colp[j * (j + 1) / 2];
+            w[j] = v;
+        }
+        b = A[MPC_PK(NC, tt)];
+    } else {
+        const double* rowp = A + MPC_PK(row ? t : 0, 0);
+        const double* colp = A + (row ? t : 0);
+#pragma unroll
+        for (int j = 0; j < NC; ++j) {
+            const double* q = (j <= t) ? rowp + j : colp + j * (j + 1) / 2;
+            w[j] = (row && j < n) ? *q : ((j == t) ? 1.0 : 0.0);
+        }
+        b = row ? A[MPC_PK(n, t)] : 0.0;
     }
-    double b = row ? A[MPC_PK(n, t)] : 0.0;
     double myinv = 0.0;
     bool ok = true;
     double d0;
