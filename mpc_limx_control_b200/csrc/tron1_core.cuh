@@ -417,7 +417,8 @@ MPC_HD void build_hessian(const Tron1Const& P, WK& S, double rho, bool use_face,
         for (int c = 0; c < 3; ++c) T[c * 3 + c] += Dp[c];
         if (sa == sb) for (int c = 0; c < 3; ++c) T[c * 3 + c] += P.r + 0.5 * rho;
         for (int i = 0; i < 9; ++i) T[i] *= 2.0;
-        if (use_face) {
+        // interior faces have Z = I: the first active-face iteration of every instance skips the reduction
+        if (use_face && (S.ax[sa] | S.ay[sa] | S.zt[sa] | S.ax[sb] | S.ay[sb] | S.zt[sb]) != 0) {
             FaceZ Za = face_basis(P.mu, S.ax[sa], S.ay[sa], S.zt[sa]);
             FaceZ Zb = face_basis(P.mu, S.ax[sb], S.ay[sb], S.zt[sb]);
             for (int r = 0; r < 3; ++r) {   // columns:  T <- T Zb
