@@ -208,6 +208,36 @@ int mpc_b200_grf_to_torque_host(int device, const mpc_b200_leg_model *m, int B, 
                                 const double *u0, double *tau);
 
 /* ------------------------------------------------------------------------------------------------
+ * Base-state Kalman filter for a batch of robots: the reference's unbuilt, OCS2-derived
+ * stateEstimator::update (include/stateEstimator.h:217-337).  State xhat [B][12] = base position, base velocity,
+ * left and right foot position (world); covariance P [B][12 x 12] row-major (symmetric); one call = one update with
+ * time step dt from IMU orientation quat [B][4] ([x,y,z,w]), body-frame angular velocity gyro [B][3] and
+ * acceleration accel [B][3], joint angles/velocities q, dq [B][6] and contact flags contact [B][2] (uint8, 1 = in
+ * contact).  odom [B][13] (may be NULL) = RobotOdomState of include/state_estimator_fake.h:19-25 as filled at
+ * include/stateEstimator.h:319-333: pos 3, quat 4, v_pos 3 (body frame), v_ori 3.  Noise constants :124-130. */
+typedef struct mpc_b200_kf_params {
+    double foot_radius;                   /* 0.02 */
+    double imu_process_noise_position;    /* 0.02 */
+    double imu_process_noise_velocity;    /* 0.02 */
+    double foot_process_noise_position;   /* 0.002 */
+    double foot_sensor_noise_position;    /* 0.005 */
+    double foot_sensor_noise_velocity;    /* 0.1 */
+    double foot_height_sensor_noise;      /* 0.01 */
+    double high_suspect_number;           /* 100: noise inflation of a foot that is not in contact (:262) */
+    int32_t accel_transpose;              /* 1: accel = R' a_local + g as written at :281; 0: R a_local + g */
+} mpc_b200_kf_params;
+int mpc_b200_kf_default_params(mpc_b200_kf_params *p);
+/* xhat = 0, P = p0 I (the reference starts from 100 I, include/stateEstimator.h:206-207) */
+int mpc_b200_kf_reset_device(int B, double p0, double *d_xhat, double *d_P, void *stream);
+int mpc_b200_kf_update_device(const mpc_b200_kf_params *p, const mpc_b200_leg_model *m, int B, double dt,
+                              const double *d_quat, const double *d_gyro_local, const double *d_accel_local,
+                              const double *d_q, const double *d_dq, const uint8_t *d_contact, double *d_xhat,
+                              double *d_P, double *d_odom, void *stream);
+int mpc_b200_kf_update_host(int device, const mpc_b200_kf_params *p, const mpc_b200_leg_model *m, int B, double dt,
+                            const double *quat, const double *gyro_local, const double *accel_local, const double *q,
+                            const double *dq, const uint8_t *contact, double *xhat, double *P, double *odom);
+
+/* ------------------------------------------------------------------------------------------------
  * Generic condensed-MPC path: the reference class QPSolver (include/QPSolver.h:13-37), any NX/NU/N.
  * HOST pointers, column-major (Eigen layout), B independent instances per call (B = 1 for the
  * facade).  Copies in, runs one CTA per instance on the device, copies out, synchronises. */

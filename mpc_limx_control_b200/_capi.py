@@ -21,6 +21,7 @@ SYMBOLS = [
     "mpc_b200_tron1_reference_device", "mpc_b200_tron1_rollout_device", "mpc_b200_tron1_control_host",
     "mpc_b200_leg_default_model", "mpc_b200_swing_default_params", "mpc_b200_leg_fk_device", "mpc_b200_swing_step_device",
     "mpc_b200_grf_to_torque_device", "mpc_b200_leg_fk_host", "mpc_b200_swing_step_host", "mpc_b200_grf_to_torque_host",
+    "mpc_b200_kf_default_params", "mpc_b200_kf_reset_device", "mpc_b200_kf_update_device", "mpc_b200_kf_update_host",
     "mpc_b200_lti_create", "mpc_b200_lti_destroy", "mpc_b200_lti_last_error", "mpc_b200_lti_launch_count",
     "mpc_b200_lti_discretize", "mpc_b200_lti_build_qp", "mpc_b200_qp_solve_dense", "mpc_b200_lti_update_state",
 ]
@@ -47,6 +48,13 @@ class SwingParams(C.Structure):
     _fields_ = [("dt", C.c_float), ("swing_time", C.c_float), ("stance_time", C.c_float), ("gait_height", C.c_float),
                 ("p_rel_max", C.c_double), ("foot_offset_left", C.c_double * 3), ("foot_offset_right", C.c_double * 3),
                 ("ik_tol", C.c_double), ("ik_dt", C.c_double), ("ik_damp", C.c_double), ("ik_max_iter", C.c_int32)]
+
+
+class KfParams(C.Structure):
+    _fields_ = [("foot_radius", C.c_double), ("imu_process_noise_position", C.c_double), ("imu_process_noise_velocity", C.c_double),
+                ("foot_process_noise_position", C.c_double), ("foot_sensor_noise_position", C.c_double),
+                ("foot_sensor_noise_velocity", C.c_double), ("foot_height_sensor_noise", C.c_double),
+                ("high_suspect_number", C.c_double), ("accel_transpose", C.c_int32)]
 
 
 class MpcB200Error(RuntimeError):
@@ -97,6 +105,10 @@ def lib():
         L.mpc_b200_leg_fk_host.argtypes = [ip, C.POINTER(LegModel), ip] + [vp] * 5
         L.mpc_b200_swing_step_host.argtypes = [ip, C.POINTER(LegModel), C.POINTER(SwingParams), ip] + [vp] * 11
         L.mpc_b200_grf_to_torque_host.argtypes = [ip, C.POINTER(LegModel), ip] + [vp] * 4
+        L.mpc_b200_kf_default_params.argtypes = [C.POINTER(KfParams)]
+        L.mpc_b200_kf_reset_device.argtypes = [ip, C.c_double, vp, vp, vp]
+        L.mpc_b200_kf_update_device.argtypes = [C.POINTER(KfParams), C.POINTER(LegModel), ip, C.c_double] + [vp] * 10
+        L.mpc_b200_kf_update_host.argtypes = [ip, C.POINTER(KfParams), C.POINTER(LegModel), ip, C.c_double] + [vp] * 9
         dd = C.c_double
         L.mpc_b200_lti_create.argtypes = [ip, C.POINTER(vp)]
         L.mpc_b200_lti_destroy.argtypes = [vp]

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../MPCController.h"
+#include "../stateEstimator.h"
 
 using namespace mpcb200::host;
 
@@ -34,6 +35,24 @@ int main(int argc, char** argv) {
                cmd.q[0], cmd.q[1], cmd.q[2], cmd.q[3], cmd.q[4], cmd.q[5], mpc.ikError(), mpc.ikIterations());
         st.q = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         mpc.enable_leg_pipeline = false;   // the latency figure below is the force MPC alone (BASELINE config 1b)
+        // the Kalman state estimator as the controller's state source: a robot standing still on both feet
+        {
+            stateEstimator est;
+            est.updateJointStates({0.0, 0.4, -0.8, 0.0, 0.4, -0.8}, {0, 0, 0, 0, 0, 0});
+            est.updateContact(true, true);
+            est.updateImu({0, 0, 0, 1}, {0, 0, 0}, {0, 0, 9.81});
+            RobotOdomState o;
+            for (int i = 0; i < 400; ++i) o = est.update(0.002);
+            printf("estimator pos %.9g %.9g %.9g vel %.3g %.3g %.3g foot_L %.9g %.9g %.9g\n", o.pos[0], o.pos[1], o.pos[2], o.v_pos[0], o.v_pos[1],
+                   o.v_pos[2], est.state()[6], est.state()[7], est.state()[8]);
+            MPC mpc2([&] { return est.update(0.002); });
+            mpc2.desieredV_pos(0) = 0.0;
+            mpc2.enable_leg_pipeline = false;
+            mpc2.run(st, imu, cmd, -1);
+            auto f2 = mpc2.supportFootForce();
+            printf("estimator-driven forces %.9g %.9g %.9g %.9g %.9g %.9g certified %d\n", f2[0], f2[1], f2[2], f2[3], f2[4], f2[5],
+                   (int)mpc2.lastSolveCertified());
+        }
         std::vector<double> us;
         for (int i = 0; i < calls + 100; ++i) {
             auto t0 = std::chrono::steady_clock::now();

@@ -80,3 +80,47 @@ def default_swing():
     p = _capi.SwingParams()
     _capi.check(_capi.lib().mpc_b200_swing_default_params(C.byref(p)))
     return p
+
+
+class StateEstimator:
+    """Batched base-state Kalman filter (csrc/kf_b200.cu; reference include/stateEstimator.h:184-337): xhat [B,12] and
+    P [B,12,12] stay on the device between updates."""
+
+    def __init__(self, B, device=0, model=None, params=None, p0=100.0):
+        self.lib = _capi.lib()
+        self.B = int(B)
+        self.tdev = torch.device("cuda", int(device))
+        self.model = model or default_model()
+        self.params = params or default_kf_params()
+        self.xhat = torch.empty((self.B, 12), dtype=torch.float64, device=self.tdev)
+        self.P = torch.empty((self.B, 12, 12), dtype=torch.float64, device=self.tdev)
+        self.reset(p0)
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.tdev).cuda_stream)
+
+    def reset(self, p0=100.0):
+        with torch.cuda.device(self.tdev):
+            _capi.check(self.lib.mpc_b200_kf_reset_device(self.B, float(p0), _ptr(self.xhat), _ptr(self.P), self._stream()))
+
+    def update(self, dt, quat, gyro, accel, q, dq, contact, odom=None):
+        """One filter update for every robot; returns odom [B,13] = pos, quat, body-frame velocity, angular velocity."""
+        B = self.B
+        for t, n, nm in ((quat, 4, "quat"), (gyro, 3, "gyro"), (accel, 3, "accel"), (q, 6, "q"), (dq, 6, "dq")):
+            if t.device != self.tdev or t.dtype != torch.float64 or not t.is_contiguous() or t.numel() != n * B:
+                raise ValueError(f"{nm}: expected contiguous float64 tensor of {n * B} elements on {self.tdev}")
+        if contact.device != self.tdev or contact.dtype != torch.uint8 or not contact.is_contiguous() or contact.numel() != 2 * B:
+            raise ValueError("contact: expected contiguous uint8 [B,2] on the device")
+        if odom is None:
+            odom = torch.empty((B, 13), dtype=torch.float64, device=self.tdev)
+        with torch.cuda.device(self.tdev):
+            _capi.check(self.lib.mpc_b200_kf_update_device(C.byref(self.params), C.byref(self.model), B, float(dt), _ptr(quat), _ptr(gyro),
+                                                           _ptr(accel), _ptr(q), _ptr(dq), _ptr(contact), _ptr(self.xhat), _ptr(self.P),
+                                                           _ptr(odom), self._stream()))
+        return odom
+
+
+def default_kf_params():
+    k = _capi.KfParams()
+    _capi.check(_capi.lib().mpc_b200_kf_default_params(C.byref(k)))
+    return k

@@ -65,3 +65,23 @@ void emul_grf_to_torque(const mpc_b200_leg_model* m, const double* quat, const d
 }
 
 }  // extern "C"
+
+// ---- Kalman filter core (csrc/kf_core.cuh) with a one-thread group --------------------------------------------------
+#include "../../mpc_limx_control_b200/csrc/kf_core.cuh"
+struct GrpSerialKf {
+    int tid() const { return 0; }
+    int size() const { return 1; }
+    void sync() const {}
+};
+extern "C" void emul_kf_update(const mpc_b200_kf_params* p, const mpc_b200_leg_model* m, double dt, const double* quat, const double* gyro,
+                               const double* accel, const double* q, const double* dq, const uint8_t* contact, double* xhat, double* P,
+                               double* odom) {
+    KfParams K;
+    K.foot_radius = p->foot_radius; K.imu_noise_pos = p->imu_process_noise_position; K.imu_noise_vel = p->imu_process_noise_velocity;
+    K.foot_noise_pos = p->foot_process_noise_position; K.foot_sensor_pos = p->foot_sensor_noise_position;
+    K.foot_sensor_vel = p->foot_sensor_noise_velocity; K.foot_height_noise = p->foot_height_sensor_noise;
+    K.suspect = p->high_suspect_number; K.accel_transpose = p->accel_transpose;
+    LegModel M = to_model(m);
+    KfWork W;
+    kf_update(K, M, dt, quat, gyro, accel, q, dq, contact, xhat, P, odom, W, GrpSerialKf());
+}

@@ -177,3 +177,14 @@ def grf_to_torque(m, quat, q6, u0):
     tau = np.zeros(6)
     leg_lib().emul_grf_to_torque(C.byref(m), quat.ctypes.data_as(_dp), q6.ctypes.data_as(_dp), u0.ctypes.data_as(_dp), tau.ctypes.data_as(_dp))
     return tau
+
+
+def kf_update(k, m, dt, quat, gyro, accel, q, dq, contact, xhat, P):
+    a = lambda x: np.ascontiguousarray(x, np.float64)
+    quat, gyro, accel, q, dq = a(quat), a(gyro), a(accel), a(q), a(dq)
+    c = np.ascontiguousarray(contact, np.uint8)
+    x = a(xhat).copy(); Pn = a(P).reshape(144).copy(); od = np.zeros(13)
+    leg_lib().emul_kf_update(C.byref(k), C.byref(m), C.c_double(dt), quat.ctypes.data_as(_dp), gyro.ctypes.data_as(_dp),
+                             accel.ctypes.data_as(_dp), q.ctypes.data_as(_dp), dq.ctypes.data_as(_dp), c.ctypes.data_as(_u8),
+                             x.ctypes.data_as(_dp), Pn.ctypes.data_as(_dp), od.ctypes.data_as(_dp))
+    return x, Pn.reshape(12, 12), od

@@ -21,7 +21,7 @@ class Tron1Params(C.Structure):
 
 
 def build(force=False):
-    srcs = [os.path.join(_ROOT, "oracle", f) for f in ("mpc_oracle.c", "leg_oracle.c", "mpc_oracle.h", "leg_oracle.h")]
+    srcs = [os.path.join(_ROOT, "oracle", f) for f in ("mpc_oracle.c", "leg_oracle.c", "kf_oracle.c", "mpc_oracle.h", "leg_oracle.h")]
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-s", "-C", os.path.join(_ROOT, "oracle")])
     return _SO
@@ -244,3 +244,25 @@ def grf_to_torque(m, quat, q6, u0):
     tau = np.zeros(6)
     lib().orc_grf_to_torque(C.byref(m), _p(quat), _p(q6), _p(u0), _p(tau))
     return tau
+
+
+# ---- Kalman filter oracle (oracle/kf_oracle.c) ----------------------------------------------------------
+class KfParams(C.Structure):
+    _fields_ = [("foot_radius", C.c_double), ("imu_process_noise_position", C.c_double), ("imu_process_noise_velocity", C.c_double),
+                ("foot_process_noise_position", C.c_double), ("foot_sensor_noise_position", C.c_double),
+                ("foot_sensor_noise_velocity", C.c_double), ("foot_height_sensor_noise", C.c_double),
+                ("high_suspect_number", C.c_double), ("accel_transpose", C.c_int32)]
+
+
+def kf_defaults():
+    k = KfParams(); lib().orc_kf_defaults(C.byref(k)); return k
+
+
+def kf_update(k, m, dt, quat, gyro, accel, q, dq, contact, xhat, P):
+    """one update; returns (xhat, P, odom) as new arrays"""
+    quat, gyro, accel, q, dq = _v(quat), _v(gyro), _v(accel), _v(q), _v(dq)
+    c = np.ascontiguousarray(contact, np.uint8)
+    x = _v(xhat).copy(); Pn = _v(P).reshape(144).copy(); od = np.zeros(13)
+    lib().orc_kf_update(C.byref(k), C.byref(m), C.c_double(dt), _p(quat), _p(gyro), _p(accel), _p(q), _p(dq),
+                        c.ctypes.data_as(C.POINTER(C.c_uint8)), _p(x), _p(Pn), _p(od))
+    return x, Pn.reshape(12, 12), od

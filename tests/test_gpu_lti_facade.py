@@ -125,4 +125,13 @@ def test_facade_tron1_single_binary(golden):
     assert np.abs(cq[:3] - ref["q_cmd"][:3].astype(np.float32)).max() < 1e-6 and np.all(cq[3:] == 0.0)    # cmd.q is float
     assert int(sw[-1]) == ref["ik_iters"] and abs(float(sw[-3]) - ref["ik_err"]) < 1e-6 * max(1.0, ref["ik_err"])
     assert np.abs(tau - O.grf_to_torque(mo, quat, q, fg)).max() < 1e-9 and np.all(tau[:3] == 0.0) and np.abs(tau[3:]).max() > 0.1
-    assert lines[5].startswith("latency_us")
+    # the Kalman estimator shim (host/stateEstimator.h) standing still: height = leg length + foot radius, zero velocity,
+    # and the controller driven by it produces a certified, upward, near-symmetric standing force
+    est = lines[5].split()
+    assert lines[5].startswith("estimator pos")
+    feet0 = O.leg_fk(mo, 0, [0, 0, 0], quat, q[:3], want_jac=False)
+    assert abs(float(est[4]) - (-feet0[2] + 0.02)) < 2e-3 and max(abs(float(v)) for v in est[6:9]) < 1e-3
+    assert abs(float(est[12])) < 2e-3          # left foot on the ground plane
+    ef = lines[6].split()
+    assert lines[6].startswith("estimator-driven forces") and ef[-1] == "1" and float(ef[4]) > 1.0 and float(ef[7]) > 1.0
+    assert lines[7].startswith("latency_us")
