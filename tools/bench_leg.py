@@ -55,6 +55,27 @@ cases = [
     ("swing_step_kernel", 244, lambda: lk.swing_step(d["pos"], d["quat"], d["q"], d["dv"], d["it"], d["qc"]), lambda b: O.swing_step(mo, po, pos[b], quat[b], q[b], dv[b], int(it[b]), q[b])),
     ("grf_torque_kernel", 176, lambda: lk.grf_to_torque(d["quat"], d["q"], d["u0"], tau), lambda b: O.grf_to_torque(mo, quat[b], q[b], u0[b])),
 ]
+# Kalman filter: xhat/P resident on the device (read + written every update: 2 x 1248 B), inputs 176 B + 2, odom 104 B
+from mpc_limx_control_b200.leg import StateEstimator
+Bk = min(B, 1 << 18)
+est = StateEstimator(Bk)
+kd = dict(quat=d["quat"][:Bk].contiguous(), gyro=t(rng.normal(size=(Bk, 3)) * 0.3), accel=t(rng.normal(size=(Bk, 3)) * 0.5 + np.array([0, 0, 9.81])),
+          q=d["q"][:Bk].contiguous(), dq=t(rng.normal(size=(Bk, 6)) * 0.5), contact=t(rng.integers(0, 2, (Bk, 2)).astype(np.uint8)))
+odom = torch.empty((Bk, 13), dtype=torch.float64, device="cuda")
+ko = O.kf_defaults()
+xo = np.zeros(12); Po = 100.0 * np.eye(12)
+kin = {k: v.cpu().numpy() for k, v in kd.items()}
+
+
+def kf_cpu(b):
+    O.kf_update(ko, mo, 0.002, kin["quat"][b], kin["gyro"][b], kin["accel"][b], kin["q"][b], kin["dq"][b], kin["contact"][b], xo, Po)
+
+
+s_kf = timeit(lambda: est.update(0.002, kd["quat"], kd["gyro"], kd["accel"], kd["q"], kd["dq"], kd["contact"], odom))
+nb = 2 * 1248 + 176 + 2 + 104
+print(json.dumps({"kernel": "kf_update_kernel", "B": Bk, "us": s_kf * 1e6, "robots_per_s": Bk / s_kf, "bytes_per_robot": nb,
+                  "roofline": {"bound": "hbm", "achieved": nb * Bk / s_kf / 1e9, "peak": peak, "unit": "GB/s", "frac": nb * Bk / s_kf / 1e9 / peak, "peak_source": src},
+                  "cpu_oracle": {"robots_per_s": cpu_rate(kf_cpu), "cores": 1, "kind": "port (python ctypes call per robot)", "sample": ncpu}}))
 for name, nbytes, fn, cfn in cases:
     s = timeit(fn)
     gbs = nbytes * B / s / 1e9
