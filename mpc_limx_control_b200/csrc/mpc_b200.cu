@@ -428,6 +428,7 @@ struct mpc_b200_engine {
     size_t small_bytes = 0;
     int host_mode = MPC_B200_HOST_AUTO;                      // how the host-buffer entry points move data
     int last_host_path = 0;                                  // 1 = zero-copy, 0 = staged (for tests / bench)
+    bool skip_large = false;                                 // host entry points: the caller's schedule needs no large-class pass
     int num_sms = 148;
     int64_t launches = 0;
     std::string err;
@@ -470,6 +471,10 @@ static int launch_solve(mpc_b200_engine* e, int B, const double* x0, const doubl
     ks<<<(B + IPC_S - 1) / IPC_S, 32 * WPI_S * IPC_S, smem_s, s>>>(e->C, B, x0, xref, feet, contact, iter, forces, status,
                                                                  iters, ovf_list, ovf_count, nullptr, cmd_oy, cmd_vx, first_only);
     CU(e, cudaGetLastError());
+    if (e->skip_large) {   // the host entry point has looked at the schedule: no instance can overflow, the list stays empty
+        e->launches += 1;
+        return MPC_B200_OK;
+    }
     int grid_l = (B + IPC_L - 1) / IPC_L;
     if (grid_l > e->num_sms * (MINB_L > 2 ? MINB_L : 2)) grid_l = e->num_sms * (MINB_L > 2 ? MINB_L : 2);
     if (!AINL_L && grid_l * IPC_L > e->extA_slabs) grid_l = e->extA_slabs / IPC_L;
@@ -678,6 +683,25 @@ static void* device_view(const void* p) {
     return a.devicePointer;
 }
 
+// Host entry points see the schedule in host memory: when it is cheap to prove that no instance needs the large
+// capacity class (double support), the list-driven second kernel is not launched at all (2 us per call).
+// A gait clock >= 0 alternates single support (gait_contact); a negative one means standing on both feet.
+static bool schedule_needs_large_class(const mpc_b200_engine* e, int B, const uint8_t* contact, const int32_t* iter) {
+    const int N = e->N;
+    if (iter) {
+        if (B > 8192) return true;                       // not worth scanning: keep the general two-kernel launch
+        for (int b = 0; b < B; ++b) if (iter[b] < 0) return true;
+        return false;
+    }
+    if ((size_t)B * 2 * N > 32768) return true;
+    for (int b = 0; b < B; ++b) {
+        int c = 0;
+        for (int s = 0; s < 2 * N; ++s) c += contact[(size_t)b * 2 * N + s] ? 1 : 0;
+        if (c > N) return true;
+    }
+    return false;
+}
+
 // shared implementation of the two host-buffer entry points.
 //   cmd == false: x_ref in, full horizon forces out (forces_out [B][N][6])
 //   cmd == true : (omega_yaw, velocity_x) in -> reference generated on the device (include/mpcQP.h:74-97),
@@ -689,6 +713,11 @@ static int solve_host_impl(mpc_b200_engine* e, int B, const double* x0, const do
     const size_t fstride = (e->C.per_step_feet && e->C.ltv) ? 6 * (size_t)N : 6;
     const size_t XR = 13 * (size_t)(N + 1);
     e->last_host_path = 0;
+    struct SkipGuard {   // every dispatch of this call may skip the large-class kernel; always restored on return
+        mpc_b200_engine* e;
+        ~SkipGuard() { e->skip_large = false; }
+    } guard{e};
+    e->skip_large = !schedule_needs_large_class(e, B, contact, iter);
     if (e->host_mode != MPC_B200_HOST_STAGED) {
         // ---- zero-copy path: when every caller buffer is pinned (device-addressable), the solve kernel
         // reads its inputs straight from host memory (each CTA's slice arrives by TMA bulk copies over
