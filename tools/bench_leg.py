@@ -1,9 +1,10 @@
-"""Throughput of the leg kinematics kernels (csrc/leg_b200.cu) against their HBM roofline, with the CPU oracle
-timed beside them.  One JSON line per kernel.  usage (GPU box): python tools/bench_leg.py [B]"""
+"""Throughput of the leg kinematics and Kalman kernels (csrc/leg_b200.cu, csrc/kf_b200.cu) against their HBM
+roofline.  One JSON line per kernel.  usage (GPU box): python tools/bench_leg.py [B]
+(No CPU baseline here: only tests/, smoke() and bench.py may execute the oracle.)"""
 import json, os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT)
 import torch
 from scipy.spatial.transform import Rotation
 from mpc_limx_control_b200.leg import LegKinematics
@@ -37,23 +38,11 @@ def timeit(fn, n=30):
     return e0.elapsed_time(e1) * 1e-3 / n
 
 
-import oracle_lib as O
-mo, po = O.leg_defaults()
-ncpu = 20000
-
-
-def cpu_rate(fn):
-    t0 = time.perf_counter()
-    for b in range(ncpu):
-        fn(b)
-    return ncpu / (time.perf_counter() - t0)
-
-
 cases = [
-    ("leg_fk_kernel (feet)", 152, lambda: lk.fk(d["pos"], d["quat"], d["q"]), lambda b: [O.leg_fk(mo, l, pos[b], quat[b], q[b, 3 * l:3 * l + 3], want_jac=False) for l in (0, 1)]),
-    ("leg_fk_kernel (feet + Jacobians)", 296, lambda: lk.fk(d["pos"], d["quat"], d["q"], want_jac=True), lambda b: [O.leg_fk(mo, l, pos[b], quat[b], q[b, 3 * l:3 * l + 3]) for l in (0, 1)]),
-    ("swing_step_kernel", 244, lambda: lk.swing_step(d["pos"], d["quat"], d["q"], d["dv"], d["it"], d["qc"]), lambda b: O.swing_step(mo, po, pos[b], quat[b], q[b], dv[b], int(it[b]), q[b])),
-    ("grf_torque_kernel", 176, lambda: lk.grf_to_torque(d["quat"], d["q"], d["u0"], tau), lambda b: O.grf_to_torque(mo, quat[b], q[b], u0[b])),
+    ("leg_fk_kernel (feet)", 152, lambda: lk.fk(d["pos"], d["quat"], d["q"])),
+    ("leg_fk_kernel (feet + Jacobians)", 296, lambda: lk.fk(d["pos"], d["quat"], d["q"], want_jac=True)),
+    ("swing_step_kernel", 244, lambda: lk.swing_step(d["pos"], d["quat"], d["q"], d["dv"], d["it"], d["qc"])),
+    ("grf_torque_kernel", 176, lambda: lk.grf_to_torque(d["quat"], d["q"], d["u0"], tau)),
 ]
 # Kalman filter: xhat/P resident on the device (read + written every update: 2 x 1248 B), inputs 176 B + 2, odom 104 B
 from mpc_limx_control_b200.leg import StateEstimator
@@ -62,24 +51,13 @@ est = StateEstimator(Bk)
 kd = dict(quat=d["quat"][:Bk].contiguous(), gyro=t(rng.normal(size=(Bk, 3)) * 0.3), accel=t(rng.normal(size=(Bk, 3)) * 0.5 + np.array([0, 0, 9.81])),
           q=d["q"][:Bk].contiguous(), dq=t(rng.normal(size=(Bk, 6)) * 0.5), contact=t(rng.integers(0, 2, (Bk, 2)).astype(np.uint8)))
 odom = torch.empty((Bk, 13), dtype=torch.float64, device="cuda")
-ko = O.kf_defaults()
-xo = np.zeros(12); Po = 100.0 * np.eye(12)
-kin = {k: v.cpu().numpy() for k, v in kd.items()}
-
-
-def kf_cpu(b):
-    O.kf_update(ko, mo, 0.002, kin["quat"][b], kin["gyro"][b], kin["accel"][b], kin["q"][b], kin["dq"][b], kin["contact"][b], xo, Po)
-
-
 s_kf = timeit(lambda: est.update(0.002, kd["quat"], kd["gyro"], kd["accel"], kd["q"], kd["dq"], kd["contact"], odom))
 nb = 2 * 1248 + 176 + 2 + 104
 print(json.dumps({"kernel": "kf_update_kernel", "B": Bk, "us": s_kf * 1e6, "robots_per_s": Bk / s_kf, "bytes_per_robot": nb,
-                  "roofline": {"bound": "hbm", "achieved": nb * Bk / s_kf / 1e9, "peak": peak, "unit": "GB/s", "frac": nb * Bk / s_kf / 1e9 / peak, "peak_source": src},
-                  "cpu_oracle": {"robots_per_s": cpu_rate(kf_cpu), "cores": 1, "kind": "port (python ctypes call per robot)", "sample": ncpu}}))
-for name, nbytes, fn, cfn in cases:
+                  "roofline": {"bound": "hbm", "achieved": nb * Bk / s_kf / 1e9, "peak": peak, "unit": "GB/s", "frac": nb * Bk / s_kf / 1e9 / peak, "peak_source": src}}))
+for name, nbytes, fn in cases:
     s = timeit(fn)
     gbs = nbytes * B / s / 1e9
     print(json.dumps({"kernel": name, "B": B, "us": s * 1e6, "robots_per_s": B / s, "bytes_per_robot": nbytes,
                       "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "peak_source": src},
-                      "cpu_oracle": {"robots_per_s": cpu_rate(cfn), "cores": 1, "kind": "port (python ctypes call per robot)", "sample": ncpu},
                       "note": "outputs allocated per call by the torch wrapper (cudaMalloc-free caching allocator)"}))
