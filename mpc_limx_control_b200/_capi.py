@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libmpc_b200.so")
+LIB_PATH = os.environ.get("MPC_B200_LIB") or os.path.join(_HERE, "csrc", "libmpc_b200.so")   # override: A/B builds in tools/
 
 OK, EINVAL, ENODEV, ECUDA, ENOMEM, ECAPACITY = 0, -1, -2, -3, -4, -5
 INFTY = 1.0e20
