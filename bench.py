@@ -24,6 +24,17 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# stdout carries exactly one JSON line.  Libraries write there too (under torchrun NCCL prints a version banner on
+# file descriptor 1), so the real stdout is kept aside for the JSON line and descriptor 1 is pointed at stderr.
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line):
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
+
 SEED, HORIZON, TS = 1001, 10, 0.005
 METRIC = "batched MPC solves/sec (TRON1, N=10)"
 
@@ -116,7 +127,7 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     v = n * args.steps / dt
     sample = f"{n} of the {args.batch} config-2 instances per step (seed {SEED}), {cores} threads, one solve per thread at a time"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "solves/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -125,7 +136,7 @@ def run_reference(args):
         "cpu_baseline": {"value": v, "unit": "solves/s", "cores": cores, "kind": "port", "sample": sample,
                          "note": "restated reference CPU path (Eigen/qpOASES unavailable): dense condensing + cold-start active set"},
         "e2e": {"value": v, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 def run_gpu(args):
@@ -139,8 +150,6 @@ def run_gpu(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"     # the version banner goes to stdout, which carries the one JSON line
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     else:
@@ -332,7 +341,7 @@ def run_gpu(args):
                          "bytes_per_solve": algorithmic_bytes(N)},
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
