@@ -141,9 +141,13 @@ tron1_solve_kernel(const __grid_constant__ Tron1Const P, int B, const double* __
             }
         }
         g.sync();
-        int c = 0;
-        for (int s = 0; s < 2 * N; ++s) c += S.contact[s];
-        return 3 * c;
+        if constexpr (WPI == 1 && 2 * N <= 32) {   // one foot-step per lane: count by ballot
+            return 3 * __popc(__ballot_sync(0xffffffffu, g.t < 2 * N && S.contact[g.t]));
+        } else {
+            int c = 0;
+            for (int s = 0; s < 2 * N; ++s) c += S.contact[s];
+            return 3 * c;
+        }
     };
     auto finish = [&](int b) {
         int its = 0;
