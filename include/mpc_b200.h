@@ -29,6 +29,7 @@
 #ifndef MPC_B200_H
 #define MPC_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -112,6 +113,11 @@ int mpc_b200_tron1_solve_device(mpc_b200_engine *e, int B, const double *d_x0, c
 int mpc_b200_set_host_mode(mpc_b200_engine *e, int mode);
 /* data path the last host-buffer call took: 1 zero-copy, 0 staged */
 int mpc_b200_last_host_path(const mpc_b200_engine *e);
+/* Page-lock an existing host allocation (malloc, std::vector, Eigen, numpy ...) so that calls using it take the
+ * zero-copy path; for callers that do not link the CUDA runtime themselves.  Pin once at start-up (it costs about a
+ * millisecond per few MB), unpin before freeing the memory.  Pinning an already pinned range is not an error. */
+int mpc_b200_pin_host_buffer(void *ptr, size_t bytes);
+int mpc_b200_unpin_host_buffer(void *ptr);
 int mpc_b200_tron1_solve_host(mpc_b200_engine *e, int B, const double *x0, const double *x_ref,
                               const double *feet, const uint8_t *contact, const int32_t *iter,
                               double *forces, int32_t *status, int32_t *iters);

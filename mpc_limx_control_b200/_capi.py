@@ -16,7 +16,7 @@ INFTY = 1.0e20
 SYMBOLS = [
     "mpc_b200_version", "mpc_b200_strerror", "mpc_b200_device_count", "mpc_b200_measure_fp64_peak",
     "mpc_b200_tron1_default_params", "mpc_b200_create", "mpc_b200_destroy", "mpc_b200_last_error",
-    "mpc_b200_launch_count", "mpc_b200_set_host_mode", "mpc_b200_last_host_path", "mpc_b200_contact_schedule_device", "mpc_b200_tron1_solve_device",
+    "mpc_b200_launch_count", "mpc_b200_set_host_mode", "mpc_b200_last_host_path", "mpc_b200_pin_host_buffer", "mpc_b200_unpin_host_buffer", "mpc_b200_contact_schedule_device", "mpc_b200_tron1_solve_device",
     "mpc_b200_tron1_solve_host", "mpc_b200_tron1_condense_device",
     "mpc_b200_tron1_reference_device", "mpc_b200_tron1_rollout_device", "mpc_b200_tron1_control_host",
     "mpc_b200_leg_default_model", "mpc_b200_swing_default_params", "mpc_b200_leg_fk_device", "mpc_b200_swing_step_device",
@@ -90,6 +90,8 @@ def lib():
         L.mpc_b200_launch_count.argtypes = [vp]
         L.mpc_b200_set_host_mode.argtypes = [vp, ip]
         L.mpc_b200_last_host_path.argtypes = [vp]
+        L.mpc_b200_pin_host_buffer.argtypes = [vp, C.c_size_t]
+        L.mpc_b200_unpin_host_buffer.argtypes = [vp]
         L.mpc_b200_contact_schedule_device.argtypes = [vp, ip, vp, vp, vp]
         L.mpc_b200_tron1_solve_device.argtypes = [vp, ip, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         L.mpc_b200_tron1_solve_host.argtypes = [vp, ip, vp, vp, vp, vp, vp, vp, vp, vp]

@@ -12,6 +12,7 @@
 //   fp64_peak_kernel                DFMA-chain microbenchmark: the FP64 roofline denominator
 #include <cuda_runtime.h>
 
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -630,6 +631,19 @@ int mpc_b200_set_host_mode(mpc_b200_engine* e, int mode) {
     return MPC_B200_OK;
 }
 int mpc_b200_last_host_path(const mpc_b200_engine* e) { return e ? e->last_host_path : 0; }
+
+int mpc_b200_pin_host_buffer(void* ptr, size_t bytes) {
+    if (!ptr || bytes == 0) return MPC_B200_EINVAL;
+    cudaError_t ce = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
+    if (ce == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return MPC_B200_OK; }
+    if (ce != cudaSuccess) { cudaGetLastError(); return ce == cudaErrorMemoryAllocation ? MPC_B200_ENOMEM : MPC_B200_ECUDA; }
+    return MPC_B200_OK;
+}
+int mpc_b200_unpin_host_buffer(void* ptr) {
+    if (!ptr) return MPC_B200_EINVAL;
+    if (cudaHostUnregister(ptr) != cudaSuccess) { cudaGetLastError(); return MPC_B200_ECUDA; }
+    return MPC_B200_OK;
+}
 int64_t mpc_b200_launch_count(const mpc_b200_engine* e) { return e ? e->launches : 0; }
 
 int mpc_b200_contact_schedule_device(mpc_b200_engine* e, int B, const int32_t* d_iter, uint8_t* d_contact, void* stream) {

@@ -258,6 +258,16 @@ def bind_control_host(eng, x0, omega_yaw, velocity_x, feet, contact=None, it=Non
     return call
 
 
+def pin_host_buffer(a):
+    """Page-lock a numpy array in place (mpc_b200_pin_host_buffer) so that host calls using it run zero-copy."""
+    _capi.check(_capi.lib().mpc_b200_pin_host_buffer(C.c_void_p(a.ctypes.data), a.nbytes))
+    return a
+
+
+def unpin_host_buffer(a):
+    _capi.check(_capi.lib().mpc_b200_unpin_host_buffer(C.c_void_p(a.ctypes.data)))
+
+
 def as_np_out(a):
     if isinstance(a, torch.Tensor):
         return a.numpy()

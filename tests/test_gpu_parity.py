@@ -432,6 +432,31 @@ def test_host_zero_copy_and_staged_paths_agree(torch_cuda):
         eng.close()
 
 
+def test_pin_host_buffer_switches_numpy_arrays_to_zero_copy(torch_cuda):
+    """plain numpy arrays take the staged path; after mpc_b200_pin_host_buffer the same arrays run zero-copy, same bits"""
+    from mpc_limx_control_b200.engine import pin_host_buffer, unpin_host_buffer
+    N, B, Ts = 10, 700, 0.005
+    d = synth.tron1_batch(55, B, N, Ts)
+    eng = make_engine(N, B, Ts=Ts)
+    arrs = {k: np.ascontiguousarray(d[k]) for k in ("x0", "x_ref", "feet", "iter")}
+    F0 = np.zeros((B, N, 6)); s0 = np.zeros(B, np.int32); i0 = np.zeros(B, np.int32)
+    eng.solve_host(arrs["x0"], arrs["x_ref"], arrs["feet"], it=arrs["iter"], forces=F0, status=s0, iters=i0)
+    assert eng.last_host_path() == 0
+    F1 = np.zeros((B, N, 6)); s1 = np.zeros(B, np.int32); i1 = np.zeros(B, np.int32)
+    bufs = list(arrs.values()) + [F1, s1, i1]
+    for a in bufs:
+        pin_host_buffer(a)
+    pin_host_buffer(F1)        # pinning twice is not an error
+    eng.solve_host(arrs["x0"], arrs["x_ref"], arrs["feet"], it=arrs["iter"], forces=F1, status=s1, iters=i1)
+    assert eng.last_host_path() == 1
+    assert np.array_equal(F0, F1) and np.array_equal(s0, s1) and np.array_equal(i0, i1) and (s1 == 0).all()
+    for a in bufs:
+        unpin_host_buffer(a)
+    eng.solve_host(arrs["x0"], arrs["x_ref"], arrs["feet"], it=arrs["iter"], forces=F1, status=s1, iters=i1)
+    assert eng.last_host_path() == 0 and np.array_equal(F0, F1)
+    eng.close()
+
+
 def test_non_finite_instance_is_isolated(torch_cuda):
     """a NaN state poisons only its own instance: status 2 there, neighbours (same CTA) still certified"""
     torch = torch_cuda
