@@ -457,6 +457,34 @@ def test_pin_host_buffer_switches_numpy_arrays_to_zero_copy(torch_cuda):
     eng.close()
 
 
+def test_device_entry_point_is_cuda_graph_capturable(torch_cuda):
+    """the device entry point launches on the caller's stream and makes no synchronising call, so a control loop can
+    capture several solves (here: three batches into three output buffers) in one CUDA graph and replay it"""
+    torch = torch_cuda
+    N, B, Ts = 10, 512, 0.005
+    eng = make_engine(N, B, Ts=Ts)
+    batches = [to_dev(torch, synth.tron1_batch(70 + i, B, N, Ts)) for i in range(3)]
+    outs = [(torch.zeros((B, N, 6), dtype=torch.float64, device="cuda"), torch.zeros(B, dtype=torch.int32, device="cuda"),
+             torch.zeros(B, dtype=torch.int32, device="cuda")) for _ in range(3)]
+    ref = []
+    for t, o in zip(batches, outs):          # warm-up outside capture (first call configures the kernels)
+        F, st, it = eng.solve(t["x0"], t["x_ref"], t["feet"], it=t["iter"])
+        ref.append((F.clone(), st.clone()))
+    torch.cuda.synchronize()
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        for t, o in zip(batches, outs):
+            eng.solve(t["x0"], t["x_ref"], t["feet"], it=t["iter"], forces=o[0], status=o[1], iters=o[2])
+    for _ in range(3):
+        for o in outs:
+            o[0].zero_(); o[1].fill_(-1)
+        gr.replay()
+        torch.cuda.synchronize()
+        for o, r in zip(outs, ref):
+            assert torch.equal(o[0], r[0]) and torch.equal(o[1], r[1])
+    eng.close()
+
+
 def test_non_finite_instance_is_isolated(torch_cuda):
     """a NaN state poisons only its own instance: status 2 there, neighbours (same CTA) still certified"""
     torch = torch_cuda
