@@ -37,6 +37,14 @@ struct GrpCuda {
         if (WPI == 1) __syncwarp();
         else asm volatile("bar.sync %0, %1;" ::"r"(gid + 1), "n"(32 * WPI) : "memory");
     }
+    // group-wide OR of a predicate (a barrier as well): one vote for a warp, one reducing named barrier otherwise
+    __device__ __forceinline__ bool any(bool p) const {
+        if (WPI == 1) return __any_sync(0xffffffffu, p);
+        int r;
+        asm volatile("{\n.reg .pred p, q;\nsetp.ne.s32 q, %1, 0;\nbar.red.or.pred p, %2, %3, q;\nselp.s32 %0, 1, 0, p;\n}"
+                     : "=r"(r) : "r"((int)p), "r"(gid + 1), "n"(32 * WPI) : "memory");
+        return r != 0;
+    }
 };
 
 // ---- 1-D TMA bulk copy global -> shared, completion on an mbarrier --------------------------------

@@ -837,9 +837,9 @@ MPC_HD bool face_solve(const Tron1Const& P, WK& S, const G& g) {
     // fixed part: z = fmax on zt==1 foot-steps
     bool any_fixed = false;
 #if defined(__CUDA_ARCH__)
-    if constexpr (G::kThreads == 32 && 2 * N <= 32) {
+    if constexpr (G::kThreads >= 2 * N) {     // one foot-step per thread, group-wide vote
         const int s = g.tid();
-        any_fixed = __any_sync(0xffffffffu, s < 2 * N && S.contact[s] && S.zt[s] == 1);
+        any_fixed = g.any(s < 2 * N && S.contact[s] && S.zt[s] == 1);
     } else
 #endif
     for (int s = 0; s < 2 * N; ++s) any_fixed |= (S.contact[s] && S.zt[s] == 1);
@@ -931,6 +931,47 @@ MPC_HD bool check_optimality(const Tron1Const& P, WK& S, const G& g, bool& chang
         g.sync();
         MPC_TICK(S, g, 12);
         return r <= P.tol * um;
+    } else if constexpr (G::kThreads >= 2 * N && G::kThreads > 32) {
+        // multi-warp groups: one foot-step per thread, warp-shuffle reductions, the per-warp results combined through
+        // shared memory (S.res is free here), the face-change flag by a reducing barrier
+        const int s = g.tid();
+        double r = 0.0, um = 1.0;
+        bool ch = false;
+        if (s < 2 * N && S.contact[s]) {
+            double v[3], o[3];
+            int ax, ay, zt;
+            for (int c = 0; c < 3; ++c) v[c] = S.u[3 * s + c] - P.gamma * S.g[3 * s + c];
+            project_pyramid(P.mu, P.f_max, v, o, ax, ay, zt);
+            for (int c = 0; c < 3; ++c) {
+                double d = fabs(S.u[3 * s + c] - o[c]);
+                r = (!(d <= r) && r == r) ? d : r;   // NaN-propagating max
+                double a = fabs(S.u[3 * s + c]);
+                um = a > um ? a : um;
+            }
+            S.nax[s] = (int8_t)ax; S.nay[s] = (int8_t)ay; S.nzt[s] = (int8_t)zt;
+            ch = (ax != S.ax[s]) || (ay != S.ay[s]) || (zt != S.zt[s]);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            double r2 = __shfl_xor_sync(0xffffffffu, r, off), u2 = __shfl_xor_sync(0xffffffffu, um, off);
+            r = (!(r2 <= r) && r == r) ? r2 : r;
+            um = u2 > um ? u2 : um;
+        }
+        constexpr int NW = G::kThreads / 32;
+        static_assert(2 * NW <= 2 * N, "S.res holds the per-warp partial results");
+        if ((s & 31) == 0) { S.res[2 * (s >> 5)] = r; S.res[2 * (s >> 5) + 1] = um; }
+        changed = g.any(ch);                  // also the barrier that publishes S.res
+        r = S.res[0]; um = S.res[1];
+#pragma unroll
+        for (int w = 1; w < NW; ++w) {
+            const double r2 = S.res[2 * w], u2 = S.res[2 * w + 1];
+            r = (!(r2 <= r) && r == r) ? r2 : r;
+            um = u2 > um ? u2 : um;
+        }
+        resid = r;
+        g.sync();                             // S.res is reused by the next check
+        MPC_TICK(S, g, 12);
+        return r <= P.tol * um;
     } else
 #endif
     {
@@ -989,6 +1030,27 @@ MPC_HD void setup_instance(const Tron1Const& P, WK& S, const double* xref, const
         if (s < 2 * N) S.cidx[s] = (int16_t)rank;
         if (in) S.cinv[rank] = (int8_t)s;
         if (s == 0) S.nc = 3 * __popc(mask);
+    } else if constexpr (G::kThreads >= 2 * N && G::kThreads > 32) {
+        // multi-warp groups: per-warp ballots, warp offsets from the other warps' masks (through S.res as scratch)
+        const int s = g.tid(), wid = s >> 5, lane = s & 31;
+        const bool in = s < 2 * N && S.contact[s];
+        const unsigned mask = __ballot_sync(0xffffffffu, in);
+        unsigned* masks = reinterpret_cast<unsigned*>(S.res);
+        if (lane == 0) masks[wid] = mask;
+        g.sync();
+        int base = 0, total = 0;
+        constexpr int NW = G::kThreads / 32;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            const int c = __popc(masks[w]);
+            if (w < wid) base += c;
+            total += c;
+        }
+        const int rank = base + __popc(mask & ((1u << lane) - 1u));
+        if (s < 2 * N) S.cidx[s] = (int16_t)rank;
+        if (in) S.cinv[rank] = (int8_t)s;
+        if (s == 0) S.nc = 3 * total;
+        g.sync();                             // S.res is scratch again
     } else
 #endif
     if (g.tid() == 0) {

@@ -15,7 +15,7 @@ _capi.LIB_PATH = out
 import torch
 from mpc_limx_control_b200.engine import Engine
 standing = "standing" in sys.argv[1:]
-N = 10
+N = 20 if "n20" in sys.argv[1:] else 10
 B = next((int(a) for a in sys.argv[1:] if a.isdigit()), 4096)
 d = synth.tron1_batch(1001, B, N, 0.005, standing=standing)
 eng = Engine(horizon=N, max_batch=B)
@@ -57,6 +57,8 @@ def cta_trace(label):
     per_sm = np.bincount(tr[:, 2].astype(int), minlength=148)
     print(f"  CTAs per SM: min {per_sm.min()} max {per_sm.max()}")
 
+if N != 10:
+    sys.exit(0)
 cta_trace("device-resident inputs")
 # the same batch through the zero-copy host path (inputs read from pinned host memory by the kernel)
 from mpc_limx_control_b200.engine import bind_solve_host
