@@ -15,7 +15,7 @@ _capi.LIB_PATH = out
 import torch
 from mpc_limx_control_b200.engine import Engine
 standing = "standing" in sys.argv[1:]
-N = 20 if "n20" in sys.argv[1:] else 10
+N = 50 if "n50" in sys.argv[1:] else (20 if "n20" in sys.argv[1:] else 10)
 B = next((int(a) for a in sys.argv[1:] if a.isdigit()), 4096)
 d = synth.tron1_batch(1001, B, N, 0.005, standing=standing)
 eng = Engine(horizon=N, max_batch=B)
