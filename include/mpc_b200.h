@@ -79,7 +79,7 @@ int mpc_b200_device_count(void);
 /* measured FP64 FMA peak of `device` (register-resident DFMA chains), TFLOP/s */
 int mpc_b200_measure_fp64_peak(int device, double *tflops);
 
-/* engine lifetime.  horizon N must be one of the compiled horizons (10, 20). */
+/* engine lifetime.  horizon N must be one of the compiled horizons (10, 20, 50; closed-loop rollout: 10, 20). */
 int mpc_b200_tron1_default_params(mpc_b200_tron1_params *p);
 int mpc_b200_create(const mpc_b200_tron1_params *p, int horizon, int max_batch, int device,
                     mpc_b200_engine **out);

@@ -19,7 +19,7 @@ def _ptr(t):
 
 
 class Engine:
-    """One engine per GPU (single caller).  horizon in {10, 20}."""
+    """One engine per GPU (single caller).  horizon in {10, 20, 50} (rollout: 10, 20)."""
 
     def __init__(self, horizon=10, max_batch=4096, device=0, **param_overrides):
         self.lib = _capi.lib()

@@ -23,7 +23,7 @@ struct Vector4d { double v[4] = {0, 0, 0, 1}; double& operator()(int i) { return
 
 class mpcQP {
 public:
-    // horizon in {10, 20}; params default to the reference constants (include/mpcQP.h:18-22,54-56)
+    // horizon in {10, 20, 50}; params default to the reference constants (include/mpcQP.h:18-22,54-56)
     explicit mpcQP(int horizon = 10, int max_batch = 1, int device = 0, const mpc_b200_tron1_params* params = nullptr)
         : N(horizon), eng(nullptr) {
         if (params) prm = *params; else mpc_b200_tron1_default_params(&prm);
