@@ -770,14 +770,16 @@ MPC_HD void backward_solve(WK& S, const G& g) {
     double* A = S.Ap();
     for (int i = g.tid(); i < n; i += g.size()) S.w[i] = A[MPC_PK(n, i)];
     g.sync();
+    // w[k] is final once the steps above k are done and is never written again by the loop (only entries i < k are),
+    // so the scaling by 1/L_kk can wait until the end: one barrier per step instead of two
     for (int k = n - 1; k >= 0; --k) {
-        double xk = S.w[k] * S.dinv[k];
+        const double xk = S.w[k] * S.dinv[k];
         const double* rk = A + MPC_PK(k, 0);
-        g.sync();   // everyone has read w[k] before its owner rewrites it
         for (int i = g.tid(); i < k; i += g.size()) S.w[i] -= rk[i] * xk;
-        if (g.tid() == 0) S.w[k] = xk;
         g.sync();
     }
+    for (int i = g.tid(); i < n; i += g.size()) S.w[i] *= S.dinv[i];
+    g.sync();
 }
 
 // forward solve L y = b with b in S.w (used by ADMM where the factor is reused)
@@ -786,13 +788,13 @@ MPC_HD void forward_solve(WK& S, const G& g) {
     [[maybe_unused]] constexpr int N = WK::N;
     const int n = S.nc;
     double* A = S.Ap();
-    for (int k = 0; k < n; ++k) {
-        double yk = S.w[k] * S.dinv[k];
-        g.sync();
+    for (int k = 0; k < n; ++k) {       // same deferral of the 1/L_kk scaling as in backward_solve
+        const double yk = S.w[k] * S.dinv[k];
         for (int i = k + 1 + g.tid(); i < n; i += g.size()) S.w[i] -= A[MPC_PK(i, k)] * yk;
-        if (g.tid() == 0) S.w[k] = yk;
         g.sync();
     }
+    for (int i = g.tid(); i < n; i += g.size()) S.w[i] *= S.dinv[i];
+    g.sync();
 }
 
 // exact Euclidean projection onto {|x|<=mu z, |y|<=mu z, 0<=z<=fmax}; returns face codes
