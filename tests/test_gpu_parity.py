@@ -3,6 +3,8 @@ against the committed golden fixtures, and -- at BASELINE.json's full batch size
 size-independent properties.  Tolerances (BASELINE.json north_star): H, f, prediction matrices
 1e-9 relative in FP64; forces 1e-4 relative with KKT (natural) residual <= 1e-6; contact/mode
 indices bit-exact."""
+import os
+
 import numpy as np
 import pytest
 
@@ -284,6 +286,35 @@ def test_full_size_rollout_config5(torch_cuda):
     for j, b in enumerate(idx):
         xo, Uo, bo = O.tron1_rollout(po, N, 25, d["x0"][b], d["omega_yaw"][b], d["velocity_x"][b], int(d["iter"][b]), offl, offr)
         assert bo == 0 and np.abs(U[j] - Uo).max() / max(1.0, np.abs(Uo).max()) < 1e-4 and np.abs(X[j] - xo).max() < 1e-6
+    eng.close()
+
+
+@pytest.mark.parametrize("seed,Ts,scale,mu,standing_every", [(9001, 0.005, 1.0, 0.5, 0), (9002, 0.02, 4.0, 0.35, 7), (9003, 0.05, 2.0, 0.25, 0)])
+def test_fuzz_forces_vs_oracle(torch_cuda, seed, Ts, scale, mu, standing_every):
+    """16,384 random instances per setting, EVERY one compared with the oracle's active-set solution: nominal, a
+    stressed setting where most instances need several active-face iterations (and some the ADMM fallback), and the
+    ill-conditioned Ts = 0.05 (cond(H) ~ 3e4).  Tolerances of BASELINE.json: forces 1e-4 relative, natural residual 1e-6."""
+    torch = torch_cuda
+    N, B = 10, 16384
+    d = synth.tron1_batch(seed, B, N, Ts)
+    d["x0"][:, [0, 1, 6, 7, 8, 9, 10, 11]] *= scale
+    if standing_every:
+        d["iter"][::standing_every] = -1
+    eng = make_engine(N, B, Ts=Ts, mu=mu)
+    t = to_dev(torch, d)
+    F, st, it = eng.solve(t["x0"], t["x_ref"], t["feet"], it=t["iter"])
+    torch.cuda.synchronize()
+    F = F.cpu().numpy(); st = st.cpu().numpy(); it = it.cpu().numpy()
+    assert (st == 0).all(), np.bincount(st)
+    c_ref = np.stack([O.contact_schedule(int(i), N) for i in d["iter"]])
+    po = O.tron1_defaults(Ts=Ts, mu=mu)
+    Fo, so, _ = O.tron1_solve_batch(po, N, d["x0"], d["x_ref"], d["feet"], c_ref, nthreads=os.cpu_count() or 8)
+    assert (so == 0).all()
+    err = np.abs(F - Fo).reshape(B, -1).max(1) / np.maximum(1.0, np.abs(Fo).reshape(B, -1).max(1))
+    assert err.max() < 1e-4, (err.max(), int(err.argmax()), int(it[err.argmax()]))
+    _check_force_properties(F, c_ref, mu=mu)
+    if scale > 1.0:
+        assert it.max() >= 3 and (it > 1).mean() > 0.05        # the setting really exercises the iterations
     eng.close()
 
 
