@@ -25,6 +25,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <stddef.h>
 
 #if defined(__CUDACC__)
 #define MPC_HD __host__ __device__ __forceinline__
@@ -108,9 +109,12 @@ struct Tron1Work {
     double cc[N + 1], ss[N + 1];   // prefix sums  sum_{k<i} cos / sin
     double dc[N], ds[N];    // D_j = 1/2 Rz_j' - C_{j+1}  (cos-like / sin-like entries)
     double SW[N * 8];       // suffix sums over i>j of w_i * {1, cc, ss, cc^2, ss^2, cc ss, i, i^2}
+    double f[NV];             // full layout: linear term (live for the whole solve)
+    // ee | adj | g are contiguous and dead between the right-hand side of a face solve and the optimality check:
+    // the 3x3-block elimination uses them as its broadcast arrays (gj3_solve_regs); u must survive (swing feet stay 0)
     double ee[(N + 1) * 12];  // tracking error: free response during setup, input response later
     double adj[(N + 1) * 18]; // adjoint terms / suffix sums; first 6(N+1) doubles double as `tau`
-    double f[NV], g[NV], u[NV];   // full layout: linear term, gradient, solution
+    double g[NV], u[NV];      // full layout: gradient, solution
     double res[NS];
     const double* x0;       // 13 doubles (staged by the caller)
     const double* feet;     // 6 or 6N doubles
@@ -657,6 +661,120 @@ __device__ __noinline__ bool gj_solve_regs(WK& S, const G& g) {
     return ok;
 }
 
+// ---- 3x3-block variant of the elimination for the multi-warp classes: one step per stance foot-step ---------------------
+// The reduced Hessian is made of 3x3 blocks (one per stance foot-step), so the elimination can pivot on a whole block:
+// every row publishes its first three window entries (by symmetry: the three pivot rows to the right of the block), every
+// thread inverts the 3x3 pivot block (adjugate + one reciprocal), forms three multipliers and updates its window with
+// three FMAs per entry.  Same FMA count as three scalar columns, but ONE barrier, one reciprocal and one set of selects
+// per three columns, no pivot exchange through a separate array, and the pivot-to-pivot chain is walked NC/3 times.
+// Used where a column step is expensive (two-warp groups: a named barrier and a shared-memory pivot per column) and
+// registers are available (168-254 per thread); in the one-warp class, at its 128-register cap, it spills and loses 7 %
+// against the scalar columns, so that class keeps gj_solve_regs.  The broadcast arrays alias S.ee..S.g.
+template <int W, int BUF, class WK, class G>
+__device__ __forceinline__ void gj3_step(double (&w)[WK::NC], double& b, double (&minv)[3], bool& ok, double* buf,
+                                         const G& g, const int k) {
+    constexpr int L = WK::NC;                 // length of one broadcast array (threads beyond the matrix do not publish)
+    double* c0 = buf + BUF * (3 * L + 4);     // c0 | c1 | c2 | b of the three pivot rows
+    double* c1 = c0 + L;
+    double* c2 = c1 + L;
+    double* bq = c2 + L;
+    const int t = g.tid(), rel = t - k;
+    if (rel >= 0 && t < WK::NC) { c0[rel] = w[0]; c1[rel] = w[1]; c2[rel] = w[2]; }
+    if (rel >= 0 && rel < 3) bq[rel] = b;
+    g.sync();
+    // pivot block D[i][j] = c_j[i] (row k+i, column k+j), symmetric
+    const double d00 = c0[0], d01 = c1[0], d02 = c2[0], d11 = c1[1], d12 = c2[1], d22 = c2[2];
+    const double C00 = d11 * d22 - d12 * d12, C01 = d02 * d12 - d01 * d22, C02 = d01 * d12 - d02 * d11;
+    const double C11 = d00 * d22 - d02 * d02, C12 = d01 * d02 - d00 * d12, C22 = d00 * d11 - d01 * d01;
+    const double det = d00 * C00 + d01 * C01 + d02 * C02;
+    if (!(d00 > 0.0) || !(C22 > 0.0) || !(det > 0.0)) ok = false;     // leading minors of a positive definite block
+    const double id = fast_rcp(det);
+    const double i00 = C00 * id, i01 = C01 * id, i02 = C02 * id, i11 = C11 * id, i12 = C12 * id, i22 = C22 * id;
+    const bool piv = rel >= 0 && rel < 3;
+    if (piv) {                                                        // keep this row of the block inverse for the end
+        minv[0] = rel == 0 ? i00 : (rel == 1 ? i01 : i02);
+        minv[1] = rel == 0 ? i01 : (rel == 1 ? i11 : i12);
+        minv[2] = rel == 0 ? i02 : (rel == 1 ? i12 : i22);
+    }
+    const double a0 = piv ? 0.0 : w[0], a1 = piv ? 0.0 : w[1], a2 = piv ? 0.0 : w[2];   // pivot rows only shift
+    const double n0 = -(a0 * i00 + a1 * i01 + a2 * i02), n1 = -(a0 * i01 + a1 * i11 + a2 * i12), n2 = -(a0 * i02 + a1 * i12 + a2 * i22);
+    b = fma(n2, bq[2], fma(n1, bq[1], fma(n0, bq[0], b)));
+    if (W > 3) w[0] = fma(n2, c2[3], fma(n1, c1[3], fma(n0, c0[3], w[W > 3 ? 3 : 0])));
+#pragma unroll
+    for (int p = 4; p + 1 < W; p += 2) {
+        const double2 x0 = *reinterpret_cast<const double2*>(c0 + p);
+        const double2 x1 = *reinterpret_cast<const double2*>(c1 + p);
+        const double2 x2 = *reinterpret_cast<const double2*>(c2 + p);
+        w[p - 3] = fma(n2, x2.x, fma(n1, x1.x, fma(n0, x0.x, w[p])));
+        w[p - 2] = fma(n2, x2.y, fma(n1, x1.y, fma(n0, x0.y, w[p + 1])));
+    }
+}
+
+template <int K0, class WK, class G>
+__device__ __forceinline__ void gj3_stages(double (&w)[WK::NC], double& b, double (&minv)[3], bool& ok, double* buf, const G& g) {
+    constexpr int NC = WK::NC;
+    static_assert(NC % 6 == 0, "two 3-column steps per stage");
+    if constexpr (K0 < NC) {
+        gj3_step<NC - K0, 0, WK, G>(w, b, minv, ok, buf, g, K0);
+        gj3_step<NC - K0, 1, WK, G>(w, b, minv, ok, buf, g, K0 + 3);
+        gj3_stages<K0 + 6, WK, G>(w, b, minv, ok, buf, g);
+    }
+}
+
+template <class WK>
+struct Gj3Fits {   // two buffers of (3 NC + 4) doubles must fit into ee + adj + g = 30 (N + 1) + 6 N doubles
+    static constexpr bool value = 2 * (3 * WK::NC + 4) <= 30 * (WK::N + 1) + 6 * WK::N && WK::NC % 6 == 0;
+};
+
+template <class WK, class G>
+__device__ __noinline__ bool gj3_solve_regs(WK& S, const G& g) {
+    constexpr int NC = WK::NC;
+    static_assert(G::kThreads >= NC, "one row per thread");
+    static_assert(offsetof(WK, adj) == offsetof(WK, ee) + sizeof(S.ee) && offsetof(WK, g) == offsetof(WK, adj) + sizeof(S.adj),
+                  "ee, adj, g must be contiguous");
+    const int n = S.nc, t = g.tid();
+    const double* A = S.Ap();
+    double w[NC];
+    const bool row = t < n;
+    double b;
+    if (n == NC) {
+        const int tt = t < NC ? t : NC - 1;
+        const double* rowp = A + MPC_PK(tt, 0);
+        const double* colp = A + tt;
+#pragma unroll
+        for (int j = 0; j < NC; ++j) {
+            double v;
+            if (j <= tt) v = rowp[j]; else v = colp[j * (j + 1) / 2];
+            w[j] = v;
+        }
+        b = A[MPC_PK(NC, tt)];
+    } else {
+        const double* rowp = A + MPC_PK(row ? t : 0, 0);
+        const double* colp = A + (row ? t : 0);
+#pragma unroll
+        for (int j = 0; j < NC; ++j) {
+            const double* q = (j <= t) ? rowp + j : colp + j * (j + 1) / 2;
+            w[j] = (row && j < n) ? *q : ((j == t) ? 1.0 : 0.0);
+        }
+        b = row ? A[MPC_PK(n, t)] : 0.0;
+    }
+    double minv[3] = {0.0, 0.0, 0.0};
+    bool ok = true;
+    g.sync();                       // the aliased arrays are dead from here (every thread has left the rhs staging)
+    gj3_stages<0, WK, G>(w, b, minv, ok, S.ee, g);
+    // x of a pivot triple = (block inverse) * (final right-hand sides of the triple), exchanged through the (now idle)
+    // broadcast area -- not through S.y/S.z, which carry the ADMM iterates when this runs as a polish step
+    g.sync();
+    if (t < NC) S.ee[t] = b;
+    g.sync();
+    if (row) {
+        const int kb = (t / 3) * 3;
+        S.w[t] = minv[0] * S.ee[kb] + minv[1] * S.ee[kb + 1] + minv[2] * S.ee[kb + 2];
+    }
+    g.sync();
+    return ok;
+}
+
 // forward solve L y = b (b in S.w) for one-warp groups; y goes to row nc of the packed factor, which is
 // where backward_regs expects it.  Column access A[PK(i,k)] over i is bank-conflict free.
 // The L entries each lane needs do not depend on the recurrence, so they are loaded up front and the
@@ -872,7 +990,9 @@ MPC_HD bool face_solve(const Tron1Const& P, WK& S, const G& g) {
     bool ok;
 #if defined(__CUDA_ARCH__)
     if constexpr (G::kThreads >= WK::NC && WK::NC <= 60) {
-        ok = gj_solve_regs<WK>(S, g);
+        // measured: +12 % for the double-support class of horizon 10 (168 registers), -9 % for horizon 20 (already at 254)
+        if constexpr (G::kThreads > 32 && WK::NC == 6 * WK::N && Gj3Fits<WK>::value) ok = gj3_solve_regs<WK>(S, g);
+        else ok = gj_solve_regs<WK>(S, g);
         MPC_TICK(S, g, 7);
     } else
 #endif
