@@ -281,6 +281,16 @@ def run_gpu(args):
         if j >= 200:
             lat.append(time.perf_counter() - t0)
     lat = np.array(lat if lat else [float("nan")]) * 1e6
+    # BASELINE configs[0]-style single robot STANDING on both feet (gait clock < 0): the double-support class
+    lat_s = []
+    one_s = torch.full((1,), -1, dtype=torch.int32).pin_memory()
+    stand_call = bind_solve_host(eng, one["x0"], one["x_ref"], one["feet"], it=one_s, forces=F1, status=s1, iters=i1)
+    for j in range(args.latency_calls // 4 + 200):
+        t0 = time.perf_counter()
+        stand_call()
+        if j >= 200:
+            lat_s.append(time.perf_counter() - t0)
+    lat_s = np.array(lat_s if lat_s else [float("nan")]) * 1e6
 
     # ---- roofline of the dominant (only) kernel of the step --------------------------------------------
     peaks = load_peaks()
@@ -336,7 +346,8 @@ def run_gpu(args):
                                    "generated on the device"},
         "gpu_launches": int(launches),
         "latency": {"p50_us": float(np.percentile(lat, 50)), "p99_us": float(np.percentile(lat, 99)), "calls": len(lat),
-                    "what": "B=1 host call -> forces on host (pinned buffers)"},
+                    "what": "B=1 host call -> forces on host (pinned buffers)",
+                    "standing_p50_us": float(np.percentile(lat_s, 50)), "standing_p99_us": float(np.percentile(lat_s, 99))},
         "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": achieved_tf / fp64_peak if fp64_peak else None, "traffic": traffic,
                      "peak_source": "FP64 DFMA peak measured in this run by mpc_b200_measure_fp64_peak "

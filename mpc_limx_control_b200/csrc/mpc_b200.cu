@@ -238,15 +238,19 @@ tron1_solve_kernel(const __grid_constant__ Tron1Const P, int B, const double* __
         asm volatile("griddepcontrol.wait;" ::: "memory");
         // ovf_count[0] = list length, ovf_count[1] = CTAs that have read it; the last reader clears both
         // so the next call starts from zero without a memset (calls of one engine never overlap)
+        // ovf_list == nullptr: the host has established that EVERY instance belongs to this class (e.g. a standing
+        // robot): the list is the identity and no direct pass ran
         __shared__ int s_count;
-        if (threadIdx.x == 0) {
-            s_count = ovf_count[0];
-            if (atomicAdd(&ovf_count[1], 1) == (int)gridDim.x - 1) { ovf_count[0] = 0; ovf_count[1] = 0; }
+        if (ovf_list) {
+            if (threadIdx.x == 0) {
+                s_count = ovf_count[0];
+                if (atomicAdd(&ovf_count[1], 1) == (int)gridDim.x - 1) { ovf_count[0] = 0; ovf_count[1] = 0; }
+            }
+            __syncthreads();
         }
-        __syncthreads();
-        const int count = s_count;
+        const int count = ovf_list ? s_count : B;
         for (int slot = blockIdx.x * IPC + g.gid; slot < count; slot += gridDim.x * IPC) {
-            const int b = ovf_list[slot];
+            const int b = ovf_list ? ovf_list[slot] : slot;
             double* sx = st.xr + g.gid * XR;
             double* s0 = st.x0 + g.gid * 13;
             double* sf = st.feet + g.gid * fstride;
@@ -442,6 +446,7 @@ struct mpc_b200_engine {
     int host_mode = MPC_B200_HOST_AUTO;                      // how the host-buffer entry points move data
     int last_host_path = 0;                                  // 1 = zero-copy, 0 = staged (for tests / bench)
     bool skip_large = false;                                 // host entry points: the caller's schedule needs no large-class pass
+    bool only_large = false;                                 // host entry points: every instance needs the large class
     int num_sms = 148;
     int64_t launches = 0;
     std::string err;
@@ -480,6 +485,16 @@ static int launch_solve(mpc_b200_engine* e, int B, const double* x0, const doubl
         CU(e, cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
         CU(e, cudaFuncSetAttribute(kl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l));
         configured[e->device & 63] = true;
+    }
+    if (e->only_large) {   // the host entry point has looked at the schedule: every instance is double support
+        int grid = (B + IPC_L - 1) / IPC_L;
+        if (grid > e->num_sms * (MINB_L > 2 ? MINB_L : 2)) grid = e->num_sms * (MINB_L > 2 ? MINB_L : 2);
+        if (!AINL_L && grid * IPC_L > e->extA_slabs) grid = e->extA_slabs / IPC_L;
+        kl<<<grid, 32 * WPI_L * IPC_L, smem_l, s>>>(e->C, B, x0, xref, feet, contact, iter, forces, status, iters, nullptr, ovf_count,
+                                                  AINL_L ? nullptr : e->d_extA, cmd_oy, cmd_vx, first_only);
+        CU(e, cudaGetLastError());
+        e->launches += 1;
+        return MPC_B200_OK;
     }
     ks<<<(B + IPC_S - 1) / IPC_S, 32 * WPI_S * IPC_S, smem_s, s>>>(e->C, B, x0, xref, feet, contact, iter, forces, status,
                                                                  iters, ovf_list, ovf_count, nullptr, cmd_oy, cmd_vx, first_only);
@@ -711,21 +726,24 @@ static void* device_view(const void* p) {
 
 // Host entry points see the schedule in host memory: when it is cheap to prove that no instance needs the large
 // capacity class (double support), the list-driven second kernel is not launched at all (2 us per call).
-// A gait clock >= 0 alternates single support (gait_contact); a negative one means standing on both feet.
-static bool schedule_needs_large_class(const mpc_b200_engine* e, int B, const uint8_t* contact, const int32_t* iter) {
+// A gait clock >= 0 alternates single support (gait_contact); a negative one means standing on both feet.  When
+// EVERY instance is double support (a standing robot) only the large-class kernel runs, over the identity list.
+// returns 0 = no instance needs it, 2 = every instance needs it, 1 = mixed or not worth scanning
+static int schedule_large_class(const mpc_b200_engine* e, int B, const uint8_t* contact, const int32_t* iter) {
     const int N = e->N;
+    int n_large = 0;
     if (iter) {
-        if (B > 8192) return true;                       // not worth scanning: keep the general two-kernel launch
-        for (int b = 0; b < B; ++b) if (iter[b] < 0) return true;
-        return false;
+        if (B > 8192) return 1;                          // not worth scanning: keep the general two-kernel launch
+        for (int b = 0; b < B; ++b) n_large += iter[b] < 0;
+    } else {
+        if ((size_t)B * 2 * N > 32768) return 1;
+        for (int b = 0; b < B; ++b) {
+            int c = 0;
+            for (int s = 0; s < 2 * N; ++s) c += contact[(size_t)b * 2 * N + s] ? 1 : 0;
+            n_large += c > N;
+        }
     }
-    if ((size_t)B * 2 * N > 32768) return true;
-    for (int b = 0; b < B; ++b) {
-        int c = 0;
-        for (int s = 0; s < 2 * N; ++s) c += contact[(size_t)b * 2 * N + s] ? 1 : 0;
-        if (c > N) return true;
-    }
-    return false;
+    return n_large == 0 ? 0 : (n_large == B ? 2 : 1);
 }
 
 // shared implementation of the two host-buffer entry points.
@@ -739,11 +757,13 @@ static int solve_host_impl(mpc_b200_engine* e, int B, const double* x0, const do
     const size_t fstride = (e->C.per_step_feet && e->C.ltv) ? 6 * (size_t)N : 6;
     const size_t XR = 13 * (size_t)(N + 1);
     e->last_host_path = 0;
-    struct SkipGuard {   // every dispatch of this call may skip the large-class kernel; always restored on return
+    struct SkipGuard {   // every dispatch of this call may skip one of the two kernels; always restored on return
         mpc_b200_engine* e;
-        ~SkipGuard() { e->skip_large = false; }
+        ~SkipGuard() { e->skip_large = false; e->only_large = false; }
     } guard{e};
-    e->skip_large = !schedule_needs_large_class(e, B, contact, iter);
+    const int cls = schedule_large_class(e, B, contact, iter);
+    e->skip_large = cls == 0;
+    e->only_large = cls == 2;
     if (e->host_mode != MPC_B200_HOST_STAGED) {
         // ---- zero-copy path: when every caller buffer is pinned (device-addressable), the solve kernel
         // reads its inputs straight from host memory (each CTA's slice arrives by TMA bulk copies over

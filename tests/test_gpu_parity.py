@@ -463,6 +463,34 @@ def test_host_zero_copy_and_staged_paths_agree(torch_cuda):
         eng.close()
 
 
+def test_host_paths_all_double_support_batches(torch_cuda):
+    """when the schedule in host memory shows that EVERY instance is double support (standing robots), the host entry
+    points launch the large-class kernel alone over the identity list: same bits as the device entry point, for the
+    gait-clock and the explicit-contact forms, pinned (zero-copy) and pageable (staged), horizons 10 and 20"""
+    torch = torch_cuda
+    for N in (10, 20):
+        for B in (1, 6, 300):
+            d = synth.tron1_batch(91, B, N, 0.005, standing=True)
+            eng = make_engine(N, max(B, 8), Ts=0.005)
+            t = to_dev(torch, d)
+            F, st, it = eng.solve(t["x0"], t["x_ref"], t["feet"], it=t["iter"])
+            torch.cuda.synchronize()
+            F = F.cpu().numpy(); st = st.cpu().numpy()
+            assert (st == 0).all() and (d["iter"] < 0).all()
+            l0 = eng.launch_count()
+            Fh, sh, _ = eng.solve_host(d["x0"], d["x_ref"], d["feet"], it=d["iter"])                  # pageable
+            assert np.array_equal(Fh, F) and np.array_equal(sh, st)
+            contact = np.ones((B, N, 2), np.uint8)
+            pin = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in dict(d, contact=contact).items() if k in ("x0", "x_ref", "feet", "contact")}
+            Fp = torch.zeros((B, N, 6), dtype=torch.float64).pin_memory(); sp = torch.zeros(B, dtype=torch.int32).pin_memory()
+            ip = torch.zeros(B, dtype=torch.int32).pin_memory()
+            l1 = eng.launch_count()
+            eng.solve_host(pin["x0"], pin["x_ref"], pin["feet"], contact=pin["contact"], forces=Fp, status=sp, iters=ip)   # pinned
+            assert eng.last_host_path() == 1 and eng.launch_count() - l1 == 1                          # one kernel, not two
+            assert np.array_equal(Fp.numpy(), F) and np.array_equal(sp.numpy(), st)
+            eng.close()
+
+
 def test_pin_host_buffer_switches_numpy_arrays_to_zero_copy(torch_cuda):
     """plain numpy arrays take the staged path; after mpc_b200_pin_host_buffer the same arrays run zero-copy, same bits"""
     from mpc_limx_control_b200.engine import pin_host_buffer, unpin_host_buffer
