@@ -32,4 +32,4 @@ for B in Bs:
         e1.record(); torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1) * 1e3 / n)
     out.append(f"B {B}: {best:.2f} us {B/best:.1f} M/s (bad {int((st != 0).sum())})")
-print(os.path.basename(_capi.LIB_PATH), os.environ.get("MPC_B200_IPC", ""), " | ".join(out))
+print(os.path.basename(_capi.LIB_PATH), " | ".join(out))
