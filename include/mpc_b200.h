@@ -95,7 +95,10 @@ int mpc_b200_contact_schedule_device(mpc_b200_engine *e, int B, const int32_t *d
 
 /* The hot path on device-resident data: linearise -> discretise -> condense -> QP solve.
  * Exactly one of d_contact / d_iter may be NULL (d_iter: schedule evaluated in-kernel).
- * d_status / d_iters may be NULL. */
+ * d_status / d_iters may be NULL.
+ * Stream contract: an engine is single-caller.  All calls on ONE engine must be stream-ordered and must not
+ * overlap (same stream, or streams ordered by events): the capacity-overflow list, its counters and (horizon 50)
+ * the global factor slabs are per-engine scratch.  Use one engine per concurrent stream. */
 int mpc_b200_tron1_solve_device(mpc_b200_engine *e, int B, const double *d_x0, const double *d_x_ref,
                                 const double *d_feet, const uint8_t *d_contact, const int32_t *d_iter,
                                 double *d_forces, int32_t *d_status, int32_t *d_iters, void *stream);

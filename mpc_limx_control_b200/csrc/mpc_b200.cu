@@ -243,8 +243,14 @@ tron1_solve_kernel(const __grid_constant__ Tron1Const P, int B, const double* __
         __shared__ int s_count;
         if (ovf_list) {
             if (threadIdx.x == 0) {
-                s_count = ovf_count[0];
-                if (atomicAdd(&ovf_count[1], 1) == (int)gridDim.x - 1) { ovf_count[0] = 0; ovf_count[1] = 0; }
+                // the read of the length must be performed before this CTA's ticket becomes visible: the CTA that
+                // draws the last ticket clears the length, and a relaxed load could otherwise be ordered after it
+                s_count = *reinterpret_cast<volatile int32_t*>(ovf_count);
+                __threadfence();
+                if (atomicAdd(&ovf_count[1], 1) == (int)gridDim.x - 1) {
+                    __threadfence();
+                    ovf_count[0] = 0; ovf_count[1] = 0;
+                }
             }
             __syncthreads();
         }
@@ -442,6 +448,8 @@ struct mpc_b200_engine {
     unsigned char *h_small = nullptr, *d_small = nullptr;    // pinned / device staging of the packed path
     double* d_extA = nullptr;                                // global-memory factor slabs (N = 50 double support)
     int extA_slabs = 0;
+    cudaEvent_t extA_free = nullptr;                         // recorded behind every kernel that uses the slabs: the next user
+                                                             // (possibly on another pipe stream) waits on it
     size_t small_bytes = 0;
     int host_mode = MPC_B200_HOST_AUTO;                      // how the host-buffer entry points move data
     int last_host_path = 0;                                  // 1 = zero-copy, 0 = staged (for tests / bench)
@@ -486,6 +494,9 @@ static int launch_solve(mpc_b200_engine* e, int B, const double* x0, const doubl
         CU(e, cudaFuncSetAttribute(kl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l));
         configured[e->device & 63] = true;
     }
+    // the large class of horizon 50 keeps its factors in ONE set of global slabs indexed by CTA: two such kernels must
+    // never overlap, whatever streams they are on (the chunk-pipelined host path uses several)
+    if (!AINL_L) CU(e, cudaStreamWaitEvent(s, e->extA_free, 0));
     if (e->only_large) {   // the host entry point has looked at the schedule: every instance is double support
         int grid = (B + IPC_L - 1) / IPC_L;
         if (grid > e->num_sms * (MINB_L > 2 ? MINB_L : 2)) grid = e->num_sms * (MINB_L > 2 ? MINB_L : 2);
@@ -493,6 +504,7 @@ static int launch_solve(mpc_b200_engine* e, int B, const double* x0, const doubl
         kl<<<grid, 32 * WPI_L * IPC_L, smem_l, s>>>(e->C, B, x0, xref, feet, contact, iter, forces, status, iters, nullptr, ovf_count,
                                                   AINL_L ? nullptr : e->d_extA, cmd_oy, cmd_vx, first_only);
         CU(e, cudaGetLastError());
+        if (!AINL_L) CU(e, cudaEventRecord(e->extA_free, s));
         e->launches += 1;
         return MPC_B200_OK;
     }
@@ -518,6 +530,7 @@ static int launch_solve(mpc_b200_engine* e, int B, const double* x0, const doubl
                                  cmd_oy, cmd_vx, first_only));
     }
     CU(e, cudaGetLastError());
+    if (!AINL_L) CU(e, cudaEventRecord(e->extA_free, s));
     e->launches += 2;
     return MPC_B200_OK;
 }
@@ -620,7 +633,8 @@ int mpc_b200_create(const mpc_b200_tron1_params* p, int horizon, int max_batch, 
     if (ok && horizon == 50) {   // double-support factor (301*302/2 doubles = 364 KB) does not fit shared memory
         e->extA_slabs = e->num_sms * 2;
         if (e->extA_slabs > max_batch) e->extA_slabs = max_batch;
-        ok = cudaMalloc(&e->d_extA, sizeof(double) * Tron1Work<50, 300, false>::PKN * (size_t)e->extA_slabs) == cudaSuccess;
+        ok = cudaMalloc(&e->d_extA, sizeof(double) * Tron1Work<50, 300, false>::PKN * (size_t)e->extA_slabs) == cudaSuccess &&
+             cudaEventCreateWithFlags(&e->extA_free, cudaEventDisableTiming) == cudaSuccess;
     }
     if (!ok) {
         cudaGetLastError();
@@ -643,6 +657,7 @@ int mpc_b200_destroy(mpc_b200_engine* e) {
     if (e->h_small) cudaFreeHost(e->h_small);
     cudaFree(e->d_small);
     cudaFree(e->d_extA);
+    if (e->extA_free) cudaEventDestroy(e->extA_free);
     delete e;
     return MPC_B200_OK;
 }
@@ -834,6 +849,11 @@ static int solve_host_impl(mpc_b200_engine* e, int B, const double* x0, const do
     if (nchunk < 1) nchunk = 1;
     int chunk = (B + nchunk - 1) / nchunk;
     chunk = (chunk + 3) & ~3;   // chunk starts stay multiples of 4: CTA slices remain 16-byte aligned
+    // an error half way must not leave copies of earlier chunks in flight into the caller's buffers
+    struct Drain {
+        mpc_b200_engine* e; bool armed;
+        ~Drain() { if (armed) for (int i = 0; i < mpc_b200_engine::kPipe; ++i) cudaStreamSynchronize(e->pipe[i]); }
+    } drain{e, true};
     for (int c = 0, first = 0; first < B; ++c, first += chunk) {
         const int nb = (B - first < chunk) ? (B - first) : chunk;
         cudaStream_t s = e->pipe[c % mpc_b200_engine::kPipe];
@@ -861,6 +881,7 @@ static int solve_host_impl(mpc_b200_engine* e, int B, const double* x0, const do
         if (iters) CU(e, cudaMemcpyAsync(iters + f, e->d_iters + f, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, s));
     }
     for (int i = 0; i < mpc_b200_engine::kPipe; ++i) CU(e, cudaStreamSynchronize(e->pipe[i]));
+    drain.armed = false;
     return MPC_B200_OK;
 }
 

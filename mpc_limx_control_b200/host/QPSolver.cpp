@@ -22,9 +22,16 @@ QPSolver::QPSolver(double Ts_, int N_, const MatrixXd& Ac_, const MatrixXd& Bc_,
     if (Ac.cols() != NX || Bc.rows() != NX || Q.rows() != NX || Q.cols() != NX || P.rows() != NX || P.cols() != NX ||
         R.rows() != NU || R.cols() != NU || x_min.size() != NX || x_max.size() != NX || N < 1)
         throw DeviceError(MPC_B200_EINVAL, "QPSolver: inconsistent dimensions");
+    if (NX + NU > 64) throw DeviceError(MPC_B200_EINVAL, "QPSolver: NX + NU > 64 is not supported by the discretisation kernel");
     xi = VectorXd::Zero(NX);
     check(mpc_b200_lti_create(device, &ctx), "QPSolver");
-    discretizeSystem();
+    try {
+        discretizeSystem();
+    } catch (...) {   // the destructor does not run for a throwing constructor: release the context here
+        mpc_b200_lti_destroy(ctx);
+        ctx = nullptr;
+        throw;
+    }
 }
 
 QPSolver::~QPSolver() {

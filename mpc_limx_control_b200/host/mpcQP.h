@@ -81,11 +81,15 @@ public:
     void setContactSchedule(const std::vector<uint8_t>& c) {
         if ((int)c.size() != 2 * N) throw DeviceError(MPC_B200_EINVAL, "setContactSchedule: need N x 2");
         contact = c;
+        use_iter = false;   // an explicit schedule replaces a gait clock set earlier
     }
     // schedule from the gait clock (MPC::calculateGait at iter + k*mpcStep); iter < 0 = standing
     void setGaitIteration(int iter) { gait_iter = iter; use_iter = true; }
 
     bool solve() {
+        // this facade holds ONE pair of foot positions (the reference computes one FK result per solve,
+        // include/mpcQP.h:125-137); per-step feet are a batch-entry feature (solveBatch, caller-owned [B][N][2][3])
+        if (prm.per_step_feet && prm.ltv) throw DeviceError(MPC_B200_EINVAL, "mpcQP::solve: per_step_feet engines take their feet through solveBatch");
         int32_t st = 2, it = 0;
         int rc = mpc_b200_tron1_solve_host(eng, 1, x0.data(), x_ref.data(), feet.data(), use_iter ? nullptr : contact.data(),
                                            use_iter ? &gait_iter : nullptr, U_opt.data(), &st, &it);

@@ -589,3 +589,28 @@ def test_random_contact_patterns(torch_cuda, N):
     nc = 3 * contact.reshape(B, -1).sum(1)
     assert ((nc > 0) & (nc < 3 * N)).any() and ((nc > 3 * N) & (nc < 6 * N)).any()   # both partial classes present
     eng.close()
+
+
+def test_staged_host_path_horizon50_large_class_matches_device(torch_cuda):
+    """Horizon 50 double support keeps its 364 KB factors in ONE set of global slabs.  The chunk-pipelined staged host
+    path runs several chunks on different streams: their large-class kernels must not share slabs concurrently
+    (they are serialised by an event).  Standing and mixed batches, >= 2 chunks, bit-identical to the device call."""
+    torch = torch_cuda
+    N, B, Ts = 50, 2048, 0.005
+    eng = make_engine(N, B, Ts=Ts)
+    for standing_frac in (1.0, 0.3):
+        d = synth.tron1_batch(91, B, N, Ts)
+        it = d["iter"].copy()
+        it[: int(standing_frac * B)] = -1          # iter < 0: standing on both feet (n = 300)
+        d["iter"] = it
+        t = to_dev(torch, d)
+        F, st, its = eng.solve(t["x0"], t["x_ref"], t["feet"], it=t["iter"])
+        torch.cuda.synchronize()
+        eng.set_host_mode(eng.HOST_STAGED)
+        Fh, sh, ih = eng.solve_host(d["x0"], d["x_ref"], d["feet"], it=d["iter"])
+        eng.set_host_mode(eng.HOST_AUTO)
+        assert eng.last_host_path() == 0
+        assert np.array_equal(np.asarray(sh), st.cpu().numpy())
+        assert (np.asarray(sh) == 0).all()
+        assert np.array_equal(np.asarray(Fh), F.cpu().numpy())
+    eng.close()
