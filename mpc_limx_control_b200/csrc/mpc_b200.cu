@@ -25,6 +25,17 @@
 
 using namespace mpcb200;
 
+// horizon 50 uses the tiled storage + tensor-core Cholesky (tron1_core.cuh: chol_tiled); the shorter horizons keep the
+// packed triangle and the register-resident eliminations
+#ifndef MPC_N50_WPI_S
+#define MPC_N50_WPI_S 8      // warps per instance of the single-stance class of horizon 50
+#endif
+#ifndef MPC_TILED_N50
+#define MPC_TILED_N50 1
+#endif
+template <int N, int NC, bool AINL = true>
+using SolveWork = Tron1Work<N, NC, AINL, (N == 50 && MPC_TILED_N50 != 0)>;
+
 // ------------------------------------------------------------------------------------------------
 // thread group = WPI warps cooperating on one instance
 template <int WPI>
@@ -115,7 +126,7 @@ tron1_solve_kernel(const __grid_constant__ Tron1Const P, int B, const double* __
     // first_step_only: write u_0 (6 doubles per instance, include/mpcQP.h:118) instead of the whole horizon
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using Stage = CtaStage<N, IPC>;
-    using Work = Tron1Work<N, NC, AINL>;
+    using Work = SolveWork<N, NC, AINL>;
     Stage& st = *reinterpret_cast<Stage*>(smem_raw);
     constexpr size_t stage_bytes = (sizeof(Stage) + 15) & ~size_t(15);
     Work* works = reinterpret_cast<Work*>(smem_raw + stage_bytes);
@@ -134,7 +145,7 @@ tron1_solve_kernel(const __grid_constant__ Tron1Const P, int B, const double* __
     Work& S = works[g.gid];
     S.x0 = st.x0 + g.gid * 13;
     S.feet = st.feet + g.gid * fstride;
-    S.Aext = Work::AINL ? nullptr : ext_A + ((size_t)blockIdx.x * IPC + g.gid) * Work::PKN;   // one slab per resident group
+    S.Aext = Work::AINL ? nullptr : ext_A + ((size_t)blockIdx.x * IPC + g.gid) * Work::ASZ;   // one slab per resident group
     const double* xr_s = st.xr + g.gid * XR;
 
     auto load_contact = [&](int b) {   // fills S.contact, returns the compact size 3 * stance foot-steps
@@ -384,7 +395,7 @@ tron1_condense_kernel(const __grid_constant__ Tron1Const P, int B, const double*
         double* Hb = H + (size_t)b * n * n;
         for (int idx = g.t; idx < n * n; idx += 32) {
             int i = idx % n, j = idx / n;
-            Hb[idx] = i >= j ? S.Ap()[MPC_PK(i, j)] : S.Ap()[MPC_PK(j, i)];
+            Hb[idx] = i >= j ? S.Ap()[Work::pk(i, j)] : S.Ap()[Work::pk(j, i)];
         }
     }
     if (f) for (int i = g.t; i < n; i += 32) f[(size_t)b * n + i] = S.f[i];
@@ -486,8 +497,8 @@ static int launch_solve(mpc_b200_engine* e, int B, const double* x0, const doubl
                         const double* cmd_oy, const double* cmd_vx, int first_only) {
     auto ks = tron1_solve_kernel<N, 3 * N, WPI_S, IPC_S, MINB_S, false, true>;
     auto kl = tron1_solve_kernel<N, 6 * N, WPI_L, IPC_L, MINB_L, true, AINL_L>;
-    const size_t smem_s = ((sizeof(CtaStage<N, IPC_S>) + 15) & ~size_t(15)) + sizeof(Tron1Work<N, 3 * N, true>) * IPC_S;
-    const size_t smem_l = ((sizeof(CtaStage<N, IPC_L>) + 15) & ~size_t(15)) + sizeof(Tron1Work<N, 6 * N, AINL_L>) * IPC_L;
+    const size_t smem_s = ((sizeof(CtaStage<N, IPC_S>) + 15) & ~size_t(15)) + sizeof(SolveWork<N, 3 * N, true>) * IPC_S;
+    const size_t smem_l = ((sizeof(CtaStage<N, IPC_L>) + 15) & ~size_t(15)) + sizeof(SolveWork<N, 6 * N, AINL_L>) * IPC_L;
     static bool configured[64] = {};
     if (!configured[e->device & 63]) {
         CU(e, cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
@@ -546,7 +557,7 @@ static int dispatch_solve(mpc_b200_engine* e, int B, const double* x0, const dou
     switch (e->N) {
         case 10: return launch_solve<10, 1, 4, 4, 2, 2, true, 3>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only);
         case 20: return launch_solve<20, 2, 2, 2, 2, 2>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only);
-        case 50: return launch_solve<50, 8, 1, 1, 8, 1, false>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only);
+        case 50: return launch_solve<50, MPC_N50_WPI_S, 1, 1, 8, 1, false, 2>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only);
         default: return set_err(e, MPC_B200_EINVAL, "unsupported horizon");
     }
 }
@@ -633,7 +644,7 @@ int mpc_b200_create(const mpc_b200_tron1_params* p, int horizon, int max_batch, 
     if (ok && horizon == 50) {   // double-support factor (301*302/2 doubles = 364 KB) does not fit shared memory
         e->extA_slabs = e->num_sms * 2;
         if (e->extA_slabs > max_batch) e->extA_slabs = max_batch;
-        ok = cudaMalloc(&e->d_extA, sizeof(double) * Tron1Work<50, 300, false>::PKN * (size_t)e->extA_slabs) == cudaSuccess &&
+        ok = cudaMalloc(&e->d_extA, sizeof(double) * SolveWork<50, 300, false>::ASZ * (size_t)e->extA_slabs) == cudaSuccess &&
              cudaEventCreateWithFlags(&e->extA_free, cudaEventDisableTiming) == cudaSuccess;
     }
     if (!ok) {

@@ -90,16 +90,27 @@ MPC_HD void gait_contact(const Tron1Const& P, int iter, int& left_stance, int& r
 // AINL_ = the packed factor lives inside the struct (shared memory); false = the wrapper points S.A at
 // external storage (global memory) -- needed when (NC+1)(NC+2)/2 doubles exceed shared memory (N = 50
 // double support: 364 KB).
-template <int N_, int NC_, bool AINL_ = true>
+// TILED_ = the matrix is stored as 8x8 tiles of the lower triangle (tile (I,J) at (I(I+1)/2+J)*64, inside a tile two
+// 8x4 halves [half][row][4], so that the fragments of an FP64 tensor-core MMA (DMMA.8x8x4) are 32 consecutive doubles)
+// and factorised by the tiled right-looking Cholesky with DMMA trailing updates (chol_tiled, horizon 50).  The
+// right-hand side is then row NC (fixed), rows nc..NC-1 are identity padding, and after the factorisation the diagonal
+// tiles hold inv(L_KK) instead of L_KK.
+template <int N_, int NC_, bool AINL_ = true, bool TILED_ = false>
 struct Tron1Work {
     static constexpr int N = N_;
     static constexpr int NC = NC_;
     static constexpr bool AINL = AINL_;
+    static constexpr bool TILED = TILED_;
     static constexpr int NS = 2 * N;     // foot-steps
     static constexpr int NV = 6 * N;     // decision variables (full layout)
     static constexpr int PKN = (NC + 1) * (NC + 2) / 2;  // packed lower triangle incl. rhs row
-    double* Aext;           // external packed factor storage (only used when !AINL)
-    double Astore[AINL ? PKN : 2];   // packed reduced Hessian / Cholesky factor; row nc holds the rhs
+    static constexpr int NT = (NC + 8) / 8;              // tile rows covering rows 0..NC (row NC = right-hand side)
+    static constexpr int TSZ = NT * (NT + 1) / 2 * 64;   // tiled lower triangle
+    static constexpr int ASZ = TILED ? TSZ : PKN;        // doubles of matrix storage per instance
+    double* Aext;           // external factor storage (only used when !AINL)
+    alignas(16) double Astore[AINL ? ASZ : 2];   // reduced Hessian / Cholesky factor; the rhs is row nc (packed) or row NC (tiled)
+    alignas(16) double pbuf[TILED ? NT * 64 + 64 : 2];   // tiled: current panel column + the diagonal tile being factored
+    double xt[TILED ? 8 * NT : 2], st[TILED ? 8 * NT : 2];   // tiled triangular solves: solution blocks, running sums
     double dinv[NC];        // 1 / L_kk
     static constexpr int CBS = (NC + 4) & ~1;   // stride of one broadcast buffer (even: 16-byte aligned halves)
     alignas(16) double colbuf[2 * CBS];   // double-buffered broadcast copy of the current pivot column
@@ -130,6 +141,16 @@ struct Tron1Work {
     MPC_HD double* tau() { return adj; }
     // address of the packed factor: a compile-time offset for the shared-memory case, a pointer otherwise
     MPC_HD double* Ap() { if constexpr (AINL) return Astore; else return Aext; }
+    // index of entry (i, j), i >= j, of the lower triangle
+    static MPC_HD int pk(int i, int j) {
+        if constexpr (TILED) {
+            const int I = i >> 3, J = j >> 3;
+            return ((I * (I + 1) / 2 + J) << 6) + ((j & 4) << 3) + ((i & 7) << 2) + (j & 3);
+        } else {
+            return i * (i + 1) / 2 + j;
+        }
+    }
+    MPC_HD int rhs_row() const { return TILED ? NC : nc; }
 };
 
 #define MPC_PK(i, j) ((i) * ((i) + 1) / 2 + (j))
@@ -448,7 +469,7 @@ MPC_HD void build_hessian(const Tron1Const& P, WK& S, double rho, bool use_face,
         for (int r = 0; r < 3; ++r)
             for (int c = 0; c < 3; ++c) {
                 if (sa == sb && c > r) continue;
-                Ap[MPC_PK(ra + r, cb + c)] = T[r * 3 + c];
+                Ap[WK::pk(ra + r, cb + c)] = T[r * 3 + c];
             }
     }
     g.sync();
@@ -915,6 +936,316 @@ MPC_HD void forward_solve(WK& S, const G& g) {
     g.sync();
 }
 
+// =====================================================================================================
+// Tiled storage (Work types with TILED = true, horizon 50): padding, tiled right-looking Cholesky whose trailing
+// updates run on the FP64 tensor cores (DMMA.8x8x4), blocked triangular solves.
+// What it replaces: the dense factorisation the reference pays inside qpOASES for every solve
+// (reference src/QPSolver.cpp:87-96 on the H of :58); here on the reduced Hessian of one active face.
+// =====================================================================================================
+
+// rows nc..8NT-1 become the identity (a compact size below the capacity, the right-hand-side row NC and the rows that
+// only pad the last tile); the diagonal entry of the right-hand-side row is large so that its pivot stays positive
+// whatever the right-hand side is (that pivot is never used).  Ends with a barrier: the caller fills row NC next.
+template <class WK, class G>
+MPC_HD void tiled_pad(WK& S, const G& g) {
+    double* A = S.Ap();
+    for (int r = S.nc; r < 8 * WK::NT; ++r)
+        for (int c = g.tid(); c <= r; c += g.size()) A[WK::pk(r, c)] = (c == r) ? (r == WK::NC ? 1.0e30 : 1.0) : 0.0;
+    g.sync();
+}
+
+// any group size (host build, single-warp groups): scalar right-looking blocked factorisation with the same result
+// layout as the tensor-core path: strictly-lower tiles hold L, diagonal tiles hold inv(L_KK) (upper part zero).
+template <class WK, class G>
+MPC_HD bool chol_tiled_generic(WK& S, const G& g) {
+    constexpr int NT = WK::NT;
+    double* A = S.Ap();
+    if (g.tid() == 0) S.flag = 0;
+    g.sync();
+    for (int K = 0; K < NT; ++K) {
+        if (g.tid() == 0) {
+            double a[8][8], x[8][8];
+            for (int i = 0; i < 8; ++i) for (int j = 0; j <= i; ++j) a[i][j] = A[WK::pk(8 * K + i, 8 * K + j)];
+            for (int k = 0; k < 8; ++k) {
+                double d = a[k][k];
+                if (!(d > 0.0)) { S.flag = 1; d = 1.0; }
+                const double rs = 1.0 / sqrt(d);
+                a[k][k] = rs;                                     // keep 1 / L_kk on the diagonal
+                for (int i = k + 1; i < 8; ++i) a[i][k] *= rs;
+                for (int j = k + 1; j < 8; ++j) for (int i = j; i < 8; ++i) a[i][j] -= a[i][k] * a[j][k];
+            }
+            for (int j = 0; j < 8; ++j) {                         // column j of X = L^-1 by forward substitution
+                double r[8];
+                for (int i = 0; i < 8; ++i) r[i] = (i == j) ? 1.0 : 0.0;
+                for (int k = 0; k < 8; ++k) {
+                    x[k][j] = r[k] * a[k][k];
+                    for (int i = k + 1; i < 8; ++i) r[i] -= a[i][k] * x[k][j];
+                }
+            }
+            for (int i = 0; i < 8; ++i) for (int j = 0; j < 8; ++j) S.pbuf[i * 8 + j] = (j <= i) ? x[i][j] : 0.0;
+            for (int i = 0; i < 8; ++i) for (int j = 0; j <= i; ++j) A[WK::pk(8 * K + i, 8 * K + j)] = x[i][j];
+        }
+        g.sync();
+        // panel: L_IK = A_IK inv(L_KK)', one row of one tile per work item (rows are independent)
+        for (int idx = g.tid(); idx < (NT - 1 - K) * 8; idx += g.size()) {
+            const int i = 8 * (K + 1) + idx;
+            double row[8], out[8];
+            for (int m = 0; m < 8; ++m) row[m] = A[WK::pk(i, 8 * K + m)];
+            for (int c = 0; c < 8; ++c) { double v = 0.0; for (int m = 0; m <= c; ++m) v += row[m] * S.pbuf[c * 8 + m]; out[c] = v; }
+            for (int c = 0; c < 8; ++c) A[WK::pk(i, 8 * K + c)] = out[c];
+        }
+        g.sync();
+        for (int i = 8 * (K + 1) + g.tid(); i < 8 * NT; i += g.size())
+            for (int j = 8 * (K + 1); j <= i; ++j) {
+                double v = 0.0;
+                for (int m = 0; m < 8; ++m) v += A[WK::pk(i, 8 * K + m)] * A[WK::pk(j, 8 * K + m)];
+                A[WK::pk(i, j)] -= v;
+            }
+        g.sync();
+    }
+    return S.flag == 0;
+}
+
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double fast_rsqrt(double d) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));     // MUFU.RSQ64H, relative error ~2^-23
+    const double h = 0.5 * d;
+    double e = fma(-h * y, y, 0.5);                              // two Newton steps: ~2^-45, then rounding-limited
+    y = fma(y, e, y);
+    e = fma(-h * y, y, 0.5);
+    return fma(y, e, y);
+}
+// 8x8 diagonal tile: Cholesky factor L and its inverse X = L^-1, one warp.  Lane j (mod 8) owns COLUMN j of the symmetric
+// tile (all 8 rows, so that a_jk is its own register k) and column j of X.  Every lane gets column k by shuffles ONE STEP
+// AHEAD (the old values, to which it applies the pending rank-1 update itself), so the pivot-to-pivot chain is
+// rsqrt -> multiply -> fma with no shuffle on it; the forward substitution for X rides along (r -= l_k x_k).
+// D: 64 doubles in tile layout, in = A_KK (lower triangle valid), out = X (upper part zero).
+// Measured alone: 1.2 k cycles (tools/microbench/chol_dmma_bench.cu); a shuffle-free variant in which every lane
+// eliminates the whole triangle redundantly took 5.4 k (bound by the FP64 issue rate of a single warp).
+__device__ __noinline__ bool factor_diag8(double* __restrict__ D, int lane) {
+    const int j = lane & 7;
+    double a[8], r[8], x[8], c[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int lo = i > j ? i : j, hi = i > j ? j : i;            // symmetric read of the lower triangle
+        a[i] = D[((hi & 4) << 3) + (lo << 2) + (hi & 3)];
+        r[i] = (i == j) ? 1.0 : 0.0;
+        x[i] = 0.0;
+    }
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c[i] = __shfl_sync(0xffffffffu, a[i], 0);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        double d = c[k];
+        if (!(d > 0.0)) { ok = false; d = 1.0; }
+        const double rs = fast_rsqrt(d);
+        double l[8], cn[8];
+        if (k + 1 < 8) {             // old values of column k+1, fetched before this column's update is applied to them
+#pragma unroll
+            for (int i = k + 1; i < 8; ++i) cn[i] = __shfl_sync(0xffffffffu, a[i], k + 1);
+        }
+#pragma unroll
+        for (int i = k + 1; i < 8; ++i) l[i] = c[i] * rs;
+        const double ljk = a[k] * rs;                                 // l_jk (a_jk = a_kj: own register)
+        x[k] = r[k] * rs;
+#pragma unroll
+        for (int i = k + 1; i < 8; ++i) {
+            a[i] -= l[i] * ljk;                                       // trailing update of my column (rows > k)
+            r[i] -= l[i] * x[k];                                      // forward substitution for my column of X
+            if (k + 1 < 8) c[i] = cn[i] - l[i] * l[k + 1];            // column k+1 as every lane needs it next
+        }
+    }
+    __syncwarp();
+    if (lane < 8) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) D[((j & 4) << 3) + (i << 2) + (j & 3)] = (i >= j) ? x[i] : 0.0;
+    }
+    __syncwarp();
+    return ok;
+}
+
+// Tiled right-looking Cholesky, NW = G::kThreads / 32 warps on one matrix (shared or global memory).  Step K:
+//   panel    L_IK = A_IK inv(L_KK)'            two DMMAs per tile, written to its final place and to S.pbuf
+//   trailing A_IJ -= L_IK L_JK' (K < J <= I)   two DMMAs per tile; A/B fragments are 32 consecutive doubles of S.pbuf
+//                                              (conflict-free 64-bit loads), the accumulator is one 128-bit load/store
+//   look-ahead: warp 0 does not take part in the update; it updates tile (K+1,K+1) and factors it (factor_diag8) while
+//   the other warps work through the update, so the factor's latency chain is hidden whenever the update is long enough.
+// Measured (tools/microbench/chol_dmma_bench.cu, n = 150, one CTA of 8 warps per SM): 49 k cycles against 244 k for the
+// packed left-looking shared-memory Cholesky on the FP64 CUDA cores (cholesky_with_rhs) it replaces.
+template <class WK, class G>
+__device__ __forceinline__ bool chol_tiled_dmma(WK& S, const G& g) {
+    constexpr int NT = WK::NT, NW = G::kThreads / 32;
+    static_assert(NW >= 2, "needs a look-ahead warp and at least one updating warp");
+    double* __restrict__ T = S.Ap();
+    double* __restrict__ pbuf = S.pbuf;
+    double* dbuf = S.pbuf + NT * 64;
+    const int tid = g.tid(), lane = tid & 31, warp = tid >> 5, gid = lane >> 2, tig = lane & 3;
+    const int fo = (gid << 2) + tig;                                     // fragment offset inside a half tile
+    const int co = ((tig >> 1) << 5) + (gid << 2) + ((tig & 1) << 1);    // accumulator (C layout) offset inside a tile
+    bool ok = true;
+    if (warp == 0) {
+        *reinterpret_cast<double2*>(dbuf + 2 * lane) = *reinterpret_cast<const double2*>(T + 2 * lane);
+        __syncwarp();
+        ok &= factor_diag8(dbuf, lane);
+        *reinterpret_cast<double2*>(T + 2 * lane) = *reinterpret_cast<const double2*>(dbuf + 2 * lane);
+    }
+    g.sync();
+    for (int K = 0; K < NT - 1; ++K) {
+        {
+            const double b_lo = dbuf[fo], b_hi = dbuf[32 + fo];
+            for (int I = K + 1 + warp; I < NT; I += NW) {
+                double* P = T + ((I * (I + 1) / 2 + K) << 6);
+                const double a_lo = P[fo], a_hi = P[32 + fo];
+                double c0 = 0.0, c1 = 0.0;
+                dmma884(c0, c1, a_lo, b_lo);
+                dmma884(c0, c1, a_hi, b_hi);
+                __syncwarp();
+                *reinterpret_cast<double2*>(P + co) = make_double2(c0, c1);
+                *reinterpret_cast<double2*>(pbuf + (I << 6) + co) = make_double2(c0, c1);
+            }
+        }
+        g.sync();
+        const int m = NT - 1 - K, M = m * (m + 1) / 2;
+        if (warp == 0) {
+            // next diagonal tile first, then its factor (overlaps the other warps' update)
+            double* Dn = T + (((K + 1) * (K + 2) / 2 + K + 1) << 6);
+            const double al = pbuf[((K + 1) << 6) + fo], ah = pbuf[((K + 1) << 6) + 32 + fo];
+            double2 c = *reinterpret_cast<double2*>(Dn + co);
+            dmma884(c.x, c.y, -al, al);
+            dmma884(c.x, c.y, -ah, ah);
+            __syncwarp();
+            *reinterpret_cast<double2*>(dbuf + co) = c;
+            __syncwarp();
+            ok &= factor_diag8(dbuf, lane);
+            *reinterpret_cast<double2*>(Dn + 2 * lane) = *reinterpret_cast<const double2*>(dbuf + 2 * lane);
+        } else {
+            // tiles 1..M-1 in row-major order (tile 0 is the next diagonal tile), cut into contiguous ranges: a range mostly
+            // stays inside one tile row, whose A fragments are reused; two tiles in flight per warp
+            const int t0 = 1 + ((M - 1) * (warp - 1)) / (NW - 1), t1 = 1 + ((M - 1) * warp) / (NW - 1);
+            if (t0 < t1) {
+                int r = (int)((sqrtf(8.0f * (float)t0 + 1.0f) - 1.0f) * 0.5f);
+                while (r * (r + 1) / 2 > t0) --r;
+                while ((r + 1) * (r + 2) / 2 <= t0) ++r;
+                int I = K + 1 + r, J = K + 1 + (t0 - r * (r + 1) / 2);
+                double a_lo = -pbuf[(I << 6) + fo], a_hi = -pbuf[(I << 6) + 32 + fo];
+                for (int t = t0; t < t1; t += 2) {
+                    double* C0 = T + ((I * (I + 1) / 2 + J) << 6) + co;
+                    const double a0l = a_lo, a0h = a_hi;
+                    const double b0l = pbuf[(J << 6) + fo], b0h = pbuf[(J << 6) + 32 + fo];
+                    double2 c0 = *reinterpret_cast<double2*>(C0);
+                    if (J == I) { ++I; J = K + 1; const int Ic = I < NT ? I : NT - 1; a_lo = -pbuf[(Ic << 6) + fo]; a_hi = -pbuf[(Ic << 6) + 32 + fo]; } else ++J;
+                    const bool two = t + 1 < t1;
+                    double* C1 = T + ((I * (I + 1) / 2 + J) << 6) + co;
+                    const double a1l = a_lo, a1h = a_hi;
+                    double b1l = 0.0, b1h = 0.0;
+                    double2 c1 = make_double2(0.0, 0.0);
+                    if (two) {
+                        b1l = pbuf[(J << 6) + fo]; b1h = pbuf[(J << 6) + 32 + fo];
+                        c1 = *reinterpret_cast<double2*>(C1);
+                        if (J == I) { ++I; J = K + 1; const int Ic = I < NT ? I : NT - 1; a_lo = -pbuf[(Ic << 6) + fo]; a_hi = -pbuf[(Ic << 6) + 32 + fo]; } else ++J;
+                    }
+                    dmma884(c0.x, c0.y, a0l, b0l);
+                    dmma884(c1.x, c1.y, a1l, b1l);
+                    dmma884(c0.x, c0.y, a0h, b0h);
+                    dmma884(c1.x, c1.y, a1h, b1h);
+                    *reinterpret_cast<double2*>(C0) = c0;
+                    if (two) *reinterpret_cast<double2*>(C1) = c1;
+                }
+            }
+        }
+        g.sync();
+    }
+    // only warp 0 has seen the pivots
+    if (tid == 0) S.flag = ok ? 0 : 1;
+    g.sync();
+    return S.flag == 0;
+}
+#endif
+
+template <class WK, class G>
+MPC_HD bool chol_tiled(WK& S, const G& g) {
+#if defined(__CUDA_ARCH__) && !defined(MPC_TILED_NO_DMMA)
+    if constexpr (G::kThreads >= 64 && G::kThreads % 32 == 0) return chol_tiled_dmma<WK>(S, g);
+    else
+#endif
+        return chol_tiled_generic<WK>(S, g);
+}
+
+// L y = b with b in S.w[0..nc) (zero beyond), blocked over the tile rows: y_K = inv(L_KK) s_K, then every later row
+// subtracts L_rK y_K.  y goes to S.st (zero in the rows >= NC), where tiled_backward(.., false) picks it up.
+template <class WK, class G>
+MPC_HD void tiled_forward(WK& S, const G& g) {
+    constexpr int NT = WK::NT, NC = WK::NC;
+    const double* A = S.Ap();
+    for (int r = g.tid(); r < 8 * NT; r += g.size()) S.st[r] = (r < S.nc) ? S.w[r] : 0.0;
+    g.sync();
+    for (int K = 0; K < NT; ++K) {
+        for (int a = g.tid(); a < 8; a += g.size()) {
+            double v = 0.0;
+            for (int b = 0; b <= a; ++b) v += A[WK::pk(8 * K + a, 8 * K + b)] * S.st[8 * K + b];
+            S.xt[8 * K + a] = v;
+        }
+        g.sync();
+        for (int r = 8 * K + g.tid(); r < 8 * NT; r += g.size()) {
+            if (r < 8 * K + 8) { S.st[r] = S.xt[r]; continue; }       // block K itself: s becomes y
+            double acc = S.st[r];
+            for (int b = 0; b < 8; ++b) acc -= A[WK::pk(r, 8 * K + b)] * S.xt[8 * K + b];
+            S.st[r] = acc;
+        }
+        g.sync();
+    }
+    for (int r = NC + g.tid(); r < 8 * NT; r += g.size()) S.st[r] = 0.0;
+    g.sync();
+}
+
+// L' x = y, blocked: x_K = inv(L_KK)' s_K, then every earlier column c subtracts sum_a L[8K+a][c] x[8K+a].
+// from_factor = true : y is row NC of the factor (the right-hand side that was carried through chol_tiled).  The last
+//   tile's part of that row was overwritten by the tile's inverse X; its solution is read off X directly:
+//   X[q][a] = -(1/delta) (L_qq^-T y_last)_a and X[q][q] = 1/delta (q = NC mod 8), so x_last = -X[q][.] / X[q][q].
+// from_factor = false: y is in S.st (tiled_forward).
+// Result in S.w[0..NC).
+template <class WK, class G>
+MPC_HD void tiled_backward(WK& S, const G& g, bool from_factor) {
+    constexpr int NT = WK::NT, NC = WK::NC, KL = NT - 1;
+    const double* A = S.Ap();
+    if (from_factor) {
+        const double xqq = A[WK::pk(NC, NC)];
+        for (int c = g.tid(); c < 8 * NT; c += g.size()) {
+            S.st[c] = (c < 8 * KL) ? A[WK::pk(NC, c)] : 0.0;
+            S.xt[c] = (c >= 8 * KL && c < NC) ? -A[WK::pk(NC, c)] / xqq : 0.0;
+        }
+        g.sync();
+    }
+    for (int K = KL; K >= 0; --K) {
+        if (!(from_factor && K == KL)) {
+            for (int a = g.tid(); a < 8; a += g.size()) {
+                double v = 0.0;
+                for (int b = a; b < 8; ++b) v += A[WK::pk(8 * K + b, 8 * K + a)] * S.st[8 * K + b];
+                S.xt[8 * K + a] = (8 * K + a < NC) ? v : 0.0;
+            }
+            g.sync();
+        }
+        // column c reads L[8K+a][c], a = 0..7, starting at a different a per group of four columns (bank spreading)
+        for (int c = g.tid(); c < 8 * K; c += g.size()) {
+            double acc = S.st[c];
+            const int rot = c >> 2;
+            for (int a = 0; a < 8; ++a) {
+                const int aa = (a + rot) & 7;
+                acc -= A[WK::pk(8 * K + aa, c)] * S.xt[8 * K + aa];
+            }
+            S.st[c] = acc;
+        }
+        g.sync();
+    }
+    for (int i = g.tid(); i < NC; i += g.size()) S.w[i] = S.xt[i];
+    g.sync();
+}
+
 // exact Euclidean projection onto {|x|<=mu z, |y|<=mu z, 0<=z<=fmax}; returns face codes
 MPC_HD void project_pyramid(double mu, double fmax, const double v[3], double out[3], int& ax, int& ay, int& zt) {
     double x = v[0], y = v[1], w = v[2];
@@ -975,19 +1306,27 @@ MPC_HD bool face_solve(const Tron1Const& P, WK& S, const G& g) {
     build_hessian<WK>(P, S, 0.0, true, g);
     MPC_TICK(S, g, 5);
     const int n = S.nc;
+    if constexpr (WK::TILED) tiled_pad<WK>(S, g);
+    const int R = S.rhs_row();
     for (int s = g.tid(); s < 2 * N; s += g.size()) {
         if (!S.contact[s]) continue;
         FaceZ Z = face_basis(P.mu, S.ax[s], S.ay[s], S.zt[s]);
         const double* g0 = any_fixed ? S.g + 3 * s : S.f + 3 * s;
-        double* rhs = S.Ap() + MPC_PK(n, 3 * S.cidx[s]);
-        rhs[0] = -Z.fx * g0[0];
-        rhs[1] = -Z.fy * g0[1];
-        rhs[2] = -Z.fz * (Z.mx * g0[0] + Z.my * g0[1] + g0[2]);
+        double* A = S.Ap();
+        const int c0 = 3 * S.cidx[s];
+        A[WK::pk(R, c0)] = -Z.fx * g0[0];
+        A[WK::pk(R, c0 + 1)] = -Z.fy * g0[1];
+        A[WK::pk(R, c0 + 2)] = -Z.fz * (Z.mx * g0[0] + Z.my * g0[1] + g0[2]);
     }
-    if (g.tid() == 0) S.Ap()[MPC_PK(n, n)] = 1.0;
+    if constexpr (!WK::TILED) { if (g.tid() == 0) S.Ap()[MPC_PK(n, n)] = 1.0; }
     g.sync();
     MPC_TICK(S, g, 6);
     bool ok;
+    if constexpr (WK::TILED) {
+        ok = chol_tiled<WK>(S, g);
+        MPC_TICK(S, g, 7);
+        tiled_backward<WK>(S, g, true);
+    } else
 #if defined(__CUDA_ARCH__)
     if constexpr (G::kThreads >= WK::NC && WK::NC <= 60) {
         // measured: +12 % for the double-support class of horizon 10 (168 registers), -9 % for horizon 20 (already at 254)
@@ -1261,7 +1600,7 @@ MPC_HD int solve_instance(const Tron1Const& P, WK& S, const double* xref, const 
     const int n = S.nc;
     double hmax = 0.0;
     build_hessian<WK>(P, S, 0.0, false, g);
-    for (int i = 0; i < n; ++i) hmax = S.Ap()[MPC_PK(i, i)] > hmax ? S.Ap()[MPC_PK(i, i)] : hmax;
+    for (int i = 0; i < n; ++i) hmax = S.Ap()[WK::pk(i, i)] > hmax ? S.Ap()[WK::pk(i, i)] : hmax;
     g.sync();
     const double rho = sqrt(2.0 * P.r * hmax * 4.0);
     // start from the projection of the last face solution
@@ -1279,14 +1618,21 @@ MPC_HD int solve_instance(const Tron1Const& P, WK& S, const double* xref, const 
         ++iters;
         if (!have_factor) {
             build_hessian<WK>(P, S, rho, false, g);
+            bool okf;
+            if constexpr (WK::TILED) {
+                tiled_pad<WK>(S, g);
+                for (int i = g.tid(); i < WK::NC; i += g.size()) S.Ap()[WK::pk(WK::NC, i)] = 0.0;
+                g.sync();
+                okf = chol_tiled<WK>(S, g);
+            } else {
             for (int i = g.tid(); i <= n; i += g.size()) S.Ap()[MPC_PK(n, i)] = (i == n) ? 1.0 : 0.0;
             g.sync();
-            bool okf;
 #if defined(__CUDA_ARCH__)
             if constexpr (G::kThreads >= WK::NC + 1 && WK::NC <= 60) okf = cholesky_regs<WK>(S, g);
             else
 #endif
                 okf = cholesky_with_rhs<WK>(S, g);
+            }
             if (!okf) return ST_FAILED;
             have_factor = true;
         }
@@ -1296,6 +1642,10 @@ MPC_HD int solve_instance(const Tron1Const& P, WK& S, const double* xref, const 
             for (int c = 0; c < 3; ++c) S.w[b + c] = rho * (S.z[b + c] - S.y[b + c]) - S.f[3 * s + c];
         }
         g.sync();
+        if constexpr (WK::TILED) {
+            tiled_forward<WK>(S, g);
+            tiled_backward<WK>(S, g, false);
+        } else
 #if defined(__CUDA_ARCH__)
         if constexpr (G::kThreads == 32 && WK::NC <= 31) {
             forward_regs<WK>(S, g);

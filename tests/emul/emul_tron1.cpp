@@ -23,7 +23,10 @@ struct GrpSerial {
 template <int N, int NC>
 static int run_solve_nc(const Tron1Const& P, const double* x0, const double* xref, const double* feet,
                         const uint8_t* contact, double* forces, int* iters) {
-    using Work = Tron1Work<N, NC>;
+    // same storage rule as the kernel wrapper (mpc_b200.cu: SolveWork): horizon 50 uses the tiled layout, so this build
+    // checks the tile indexing, the blocked triangular solves and the padding (the tensor-core factorisation itself is
+    // device code; chol_tiled_generic stands in with the same result layout)
+    using Work = Tron1Work<N, NC, true, (N == 50)>;
     auto* S = new Work();
     S->Aext = nullptr;
     S->x0 = x0;

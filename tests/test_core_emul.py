@@ -52,6 +52,27 @@ def test_random_vs_oracle(N, Ts, ltv, standing, scale, mu):
         assert O.tron1_natural_residual(po, N, c["H"], c["f"], contact, F) < 1e-6   # KKT residual bound
 
 
+def test_admm_fallback_path_tiled_horizon50():
+    """Horizon 50 stores the reduced Hessian as 8x8 tiles: max_newton=1 sends instances through the ADMM, i.e. through the
+    blocked forward AND backward solves on that layout (the face solve alone only needs the backward one)."""
+    N, Ts = 50, 0.02
+    d = synth.tron1_batch(12, 2, N, Ts, standing=False)
+    po = O.tron1_defaults(Ts=Ts, mu=0.3); pe = E.default_params(Ts=Ts, mu=0.3, max_newton=1)
+    used_admm = 0
+    for b in range(2):
+        x0 = d["x0"][b].copy(); x0[[0, 1, 6, 7, 8, 9, 10, 11]] *= 6
+        contact = O.contact_schedule(int(d["iter"][b]), N)
+        c = O.tron1_condense(po, N, x0, d["x_ref"][b], d["feet"][b], want_pred=False)
+        A, lbA, ubA, lb, ub = O.tron1_constraints(po, N, contact)
+        u, info = O.qp_solve(c["H"], c["f"], A, lbA, ubA, lb, ub)
+        F, st, it = E.solve(pe, N, x0, d["x_ref"][b], d["feet"][b], contact)
+        used_admm += it > 1
+        assert st == 0 and info["status"] == 0
+        assert np.abs(F.reshape(-1) - u).max() / max(1.0, np.abs(u).max()) < 1e-4
+        assert O.tron1_natural_residual(po, N, c["H"], c["f"], contact, F) < 1e-6
+    assert used_admm >= 1
+
+
 def test_admm_fallback_path():
     """max_newton=1 forces every instance whose first face guess is wrong through ADMM + polish."""
     N, Ts, B = 10, 0.02, 12
