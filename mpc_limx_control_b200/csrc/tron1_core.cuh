@@ -109,7 +109,7 @@ struct Tron1Work {
     static constexpr int ASZ = TILED ? TSZ : PKN;        // doubles of matrix storage per instance
     double* Aext;           // external factor storage (only used when !AINL)
     alignas(16) double Astore[AINL ? ASZ : 2];   // reduced Hessian / Cholesky factor; the rhs is row nc (packed) or row NC (tiled)
-    alignas(16) double pbuf[TILED ? NT * 64 + 64 : 2];   // tiled: current panel column + the diagonal tile being factored
+    alignas(16) double pbuf[TILED ? NT * 64 + 128 : 2];  // tiled: current panel column + two inverse diagonal tiles (double buffer)
     double xt[TILED ? 8 * NT : 2], st[TILED ? 8 * NT : 2];   // tiled triangular solves: solution blocks, running sums
     double dinv[NC];        // 1 / L_kk
     static constexpr int CBS = (NC + 4) & ~1;   // stride of one broadcast buffer (even: 16-byte aligned halves)
@@ -1073,8 +1073,10 @@ __device__ __noinline__ bool factor_diag8(double* __restrict__ D, int lane) {
 //   panel    L_IK = A_IK inv(L_KK)'            two DMMAs per tile, written to its final place and to S.pbuf
 //   trailing A_IJ -= L_IK L_JK' (K < J <= I)   two DMMAs per tile; A/B fragments are 32 consecutive doubles of S.pbuf
 //                                              (conflict-free 64-bit loads), the accumulator is one 128-bit load/store
-//   look-ahead: warp 0 does not take part in the update; it updates tile (K+1,K+1) and factors it (factor_diag8) while
-//   the other warps work through the update, so the factor's latency chain is hidden whenever the update is long enough.
+//   look-ahead: warp 0 is the critical-path warp.  It solves panel tile (K+1,K), signals the panel barrier WITHOUT
+//   waiting on it (bar.arrive), updates tile (K+1,K+1) and factors it (factor_diag8) while the other warps finish the
+//   panel and work through the update; one full barrier closes the step.  The factor's latency chain is hidden whenever
+//   the update is long enough.  The inverse diagonal tile is double-buffered (warp 0 runs ahead of the panel readers).
 // Measured (tools/microbench/chol_dmma_bench.cu, n = 150, one CTA of 8 warps per SM): 49 k cycles against 244 k for the
 // packed left-looking shared-memory Cholesky on the FP64 CUDA cores (cholesky_with_rhs) it replaces.
 template <class WK, class G>
@@ -1083,12 +1085,13 @@ __device__ __forceinline__ bool chol_tiled_dmma(WK& S, const G& g) {
     static_assert(NW >= 2, "needs a look-ahead warp and at least one updating warp");
     double* __restrict__ T = S.Ap();
     double* __restrict__ pbuf = S.pbuf;
-    double* dbuf = S.pbuf + NT * 64;
     const int tid = g.tid(), lane = tid & 31, warp = tid >> 5, gid = lane >> 2, tig = lane & 3;
     const int fo = (gid << 2) + tig;                                     // fragment offset inside a half tile
     const int co = ((tig >> 1) << 5) + (gid << 2) + ((tig & 1) << 1);    // accumulator (C layout) offset inside a tile
+    const int bar_panel = 8 + g.gid;                                     // named barrier of the panel phase (ids 1..7: g.sync)
     bool ok = true;
     if (warp == 0) {
+        double* dbuf = S.pbuf + NT * 64;
         *reinterpret_cast<double2*>(dbuf + 2 * lane) = *reinterpret_cast<const double2*>(T + 2 * lane);
         __syncwarp();
         ok &= factor_diag8(dbuf, lane);
@@ -1096,9 +1099,33 @@ __device__ __forceinline__ bool chol_tiled_dmma(WK& S, const G& g) {
     }
     g.sync();
     for (int K = 0; K < NT - 1; ++K) {
-        {
-            const double b_lo = dbuf[fo], b_hi = dbuf[32 + fo];
-            for (int I = K + 1 + warp; I < NT; I += NW) {
+        const double* dbuf = S.pbuf + NT * 64 + ((K & 1) << 6);
+        const double b_lo = dbuf[fo], b_hi = dbuf[32 + fo];
+        if (warp == 0) {
+            // critical path: panel tile (K+1,K) -> tile (K+1,K+1) -> its factor
+            double* P = T + (((K + 1) * (K + 2) / 2 + K) << 6);
+            const double a_lo = P[fo], a_hi = P[32 + fo];
+            double c0 = 0.0, c1 = 0.0;
+            dmma884(c0, c1, a_lo, b_lo);
+            dmma884(c0, c1, a_hi, b_hi);
+            __syncwarp();
+            *reinterpret_cast<double2*>(P + co) = make_double2(c0, c1);
+            *reinterpret_cast<double2*>(pbuf + ((K + 1) << 6) + co) = make_double2(c0, c1);
+            __syncwarp();
+            asm volatile("bar.arrive %0, %1;" ::"r"(bar_panel), "n"(G::kThreads) : "memory");
+            double* Dn = T + (((K + 1) * (K + 2) / 2 + K + 1) << 6);
+            double* dnext = S.pbuf + NT * 64 + (((K + 1) & 1) << 6);
+            const double al = pbuf[((K + 1) << 6) + fo], ah = pbuf[((K + 1) << 6) + 32 + fo];
+            double2 c = *reinterpret_cast<double2*>(Dn + co);
+            dmma884(c.x, c.y, -al, al);
+            dmma884(c.x, c.y, -ah, ah);
+            __syncwarp();
+            *reinterpret_cast<double2*>(dnext + co) = c;
+            __syncwarp();
+            ok &= factor_diag8(dnext, lane);
+            *reinterpret_cast<double2*>(Dn + 2 * lane) = *reinterpret_cast<const double2*>(dnext + 2 * lane);
+        } else {
+            for (int I = K + 1 + warp; I < NT; I += NW - 1) {             // panel tiles K+2.. over the other warps
                 double* P = T + ((I * (I + 1) / 2 + K) << 6);
                 const double a_lo = P[fo], a_hi = P[32 + fo];
                 double c0 = 0.0, c1 = 0.0;
@@ -1108,24 +1135,10 @@ __device__ __forceinline__ bool chol_tiled_dmma(WK& S, const G& g) {
                 *reinterpret_cast<double2*>(P + co) = make_double2(c0, c1);
                 *reinterpret_cast<double2*>(pbuf + (I << 6) + co) = make_double2(c0, c1);
             }
-        }
-        g.sync();
-        const int m = NT - 1 - K, M = m * (m + 1) / 2;
-        if (warp == 0) {
-            // next diagonal tile first, then its factor (overlaps the other warps' update)
-            double* Dn = T + (((K + 1) * (K + 2) / 2 + K + 1) << 6);
-            const double al = pbuf[((K + 1) << 6) + fo], ah = pbuf[((K + 1) << 6) + 32 + fo];
-            double2 c = *reinterpret_cast<double2*>(Dn + co);
-            dmma884(c.x, c.y, -al, al);
-            dmma884(c.x, c.y, -ah, ah);
-            __syncwarp();
-            *reinterpret_cast<double2*>(dbuf + co) = c;
-            __syncwarp();
-            ok &= factor_diag8(dbuf, lane);
-            *reinterpret_cast<double2*>(Dn + 2 * lane) = *reinterpret_cast<const double2*>(dbuf + 2 * lane);
-        } else {
+            asm volatile("bar.sync %0, %1;" ::"r"(bar_panel), "n"(G::kThreads) : "memory");
             // tiles 1..M-1 in row-major order (tile 0 is the next diagonal tile), cut into contiguous ranges: a range mostly
             // stays inside one tile row, whose A fragments are reused; two tiles in flight per warp
+            const int m = NT - 1 - K, M = m * (m + 1) / 2;
             const int t0 = 1 + ((M - 1) * (warp - 1)) / (NW - 1), t1 = 1 + ((M - 1) * warp) / (NW - 1);
             if (t0 < t1) {
                 int r = (int)((sqrtf(8.0f * (float)t0 + 1.0f) - 1.0f) * 0.5f);
@@ -1178,6 +1191,8 @@ MPC_HD bool chol_tiled(WK& S, const G& g) {
 
 // L y = b with b in S.w[0..nc) (zero beyond), blocked over the tile rows: y_K = inv(L_KK) s_K, then every later row
 // subtracts L_rK y_K.  y goes to S.st (zero in the rows >= NC), where tiled_backward(.., false) picks it up.
+// The loads of a step do not depend on the running sums, so they are issued before the dependent arithmetic
+// (fixed trip counts: the upper parts of the inverse tiles are stored as zeros).
 template <class WK, class G>
 MPC_HD void tiled_forward(WK& S, const G& g) {
     constexpr int NT = WK::NT, NC = WK::NC;
@@ -1185,17 +1200,27 @@ MPC_HD void tiled_forward(WK& S, const G& g) {
     for (int r = g.tid(); r < 8 * NT; r += g.size()) S.st[r] = (r < S.nc) ? S.w[r] : 0.0;
     g.sync();
     for (int K = 0; K < NT; ++K) {
+        const double* XK = A + ((K * (K + 1) / 2 + K) << 6);
         for (int a = g.tid(); a < 8; a += g.size()) {
-            double v = 0.0;
-            for (int b = 0; b <= a; ++b) v += A[WK::pk(8 * K + a, 8 * K + b)] * S.st[8 * K + b];
-            S.xt[8 * K + a] = v;
+            double xr[8], sv[8];
+#pragma unroll
+            for (int b = 0; b < 8; ++b) { xr[b] = XK[((b & 4) << 3) + (a << 2) + (b & 3)]; sv[b] = S.st[8 * K + b]; }
+            double v0 = 0.0, v1 = 0.0;
+#pragma unroll
+            for (int b = 0; b < 8; b += 2) { v0 = fma(xr[b], sv[b], v0); v1 = fma(xr[b + 1], sv[b + 1], v1); }
+            S.xt[8 * K + a] = v0 + v1;
         }
         g.sync();
         for (int r = 8 * K + g.tid(); r < 8 * NT; r += g.size()) {
             if (r < 8 * K + 8) { S.st[r] = S.xt[r]; continue; }       // block K itself: s becomes y
-            double acc = S.st[r];
-            for (int b = 0; b < 8; ++b) acc -= A[WK::pk(r, 8 * K + b)] * S.xt[8 * K + b];
-            S.st[r] = acc;
+            const double* Lr = A + (((r >> 3) * ((r >> 3) + 1) / 2 + K) << 6) + ((r & 7) << 2);
+            double lv[8], yv[8];
+#pragma unroll
+            for (int b = 0; b < 8; ++b) { lv[b] = Lr[((b & 4) << 3) + (b & 3)]; yv[b] = S.xt[8 * K + b]; }
+            double a0 = S.st[r], a1 = 0.0;
+#pragma unroll
+            for (int b = 0; b < 8; b += 2) { a0 = fma(-lv[b], yv[b], a0); a1 = fma(-lv[b + 1], yv[b + 1], a1); }
+            S.st[r] = a0 + a1;
         }
         g.sync();
     }
@@ -1208,37 +1233,64 @@ MPC_HD void tiled_forward(WK& S, const G& g) {
 //   tile's part of that row was overwritten by the tile's inverse X; its solution is read off X directly:
 //   X[q][a] = -(1/delta) (L_qq^-T y_last)_a and X[q][q] = 1/delta (q = NC mod 8), so x_last = -X[q][.] / X[q][q].
 // from_factor = false: y is in S.st (tiled_forward).
+// The inverse diagonal tiles are first copied to S.pbuf (idle after the factorisation) so that the short dependent part
+// of every step runs out of shared memory even when the factor lives in global memory; a column's eight factor entries
+// of a step are loaded BEFORE the barrier that publishes x_K, so their latency overlaps it.
 // Result in S.w[0..NC).
 template <class WK, class G>
 MPC_HD void tiled_backward(WK& S, const G& g, bool from_factor) {
     constexpr int NT = WK::NT, NC = WK::NC, KL = NT - 1;
     const double* A = S.Ap();
+    for (int idx = g.tid(); idx < NT * 64; idx += g.size()) {
+        const int K = idx >> 6;
+        S.pbuf[idx] = A[((K * (K + 1) / 2 + K) << 6) + (idx & 63)];
+    }
     if (from_factor) {
         const double xqq = A[WK::pk(NC, NC)];
         for (int c = g.tid(); c < 8 * NT; c += g.size()) {
             S.st[c] = (c < 8 * KL) ? A[WK::pk(NC, c)] : 0.0;
             S.xt[c] = (c >= 8 * KL && c < NC) ? -A[WK::pk(NC, c)] / xqq : 0.0;
         }
-        g.sync();
     }
+    g.sync();
     for (int K = KL; K >= 0; --K) {
+        // this step's factor entries of my column(s): independent of x, in flight across the barrier below
+        const int c = g.tid();
+        const bool mine = c < 8 * K;
+        double lv[8];
+        const int rot = c >> 2;     // every group of four columns starts at a different row: spreads the shared-memory banks
+        if (mine) {
+            const double* Lc = A + ((K * (K + 1) / 2 + (c >> 3)) << 6) + ((c & 4) << 3) + (c & 3);
+#pragma unroll
+            for (int a = 0; a < 8; ++a) lv[a] = Lc[((a + rot) & 7) << 2];
+        }
         if (!(from_factor && K == KL)) {
+            const double* XK = S.pbuf + (K << 6);
             for (int a = g.tid(); a < 8; a += g.size()) {
-                double v = 0.0;
-                for (int b = a; b < 8; ++b) v += A[WK::pk(8 * K + b, 8 * K + a)] * S.st[8 * K + b];
-                S.xt[8 * K + a] = (8 * K + a < NC) ? v : 0.0;
+                double xc[8], sv[8];
+#pragma unroll
+                for (int b = 0; b < 8; ++b) { xc[b] = XK[((a & 4) << 3) + (b << 2) + (a & 3)]; sv[b] = S.st[8 * K + b]; }
+                double v0 = 0.0, v1 = 0.0;
+#pragma unroll
+                for (int b = 0; b < 8; b += 2) { v0 = fma(xc[b], sv[b], v0); v1 = fma(xc[b + 1], sv[b + 1], v1); }
+                S.xt[8 * K + a] = (8 * K + a < NC) ? v0 + v1 : 0.0;
             }
             g.sync();
         }
-        // column c reads L[8K+a][c], a = 0..7, starting at a different a per group of four columns (bank spreading)
-        for (int c = g.tid(); c < 8 * K; c += g.size()) {
-            double acc = S.st[c];
-            const int rot = c >> 2;
-            for (int a = 0; a < 8; ++a) {
-                const int aa = (a + rot) & 7;
-                acc -= A[WK::pk(8 * K + aa, c)] * S.xt[8 * K + aa];
-            }
-            S.st[c] = acc;
+        if (mine) {
+            double xv[8];
+#pragma unroll
+            for (int a = 0; a < 8; ++a) xv[a] = S.xt[8 * K + ((a + rot) & 7)];
+            double a0 = S.st[c], a1 = 0.0;
+#pragma unroll
+            for (int a = 0; a < 8; a += 2) { a0 = fma(-lv[a], xv[a], a0); a1 = fma(-lv[a + 1], xv[a + 1], a1); }
+            S.st[c] = a0 + a1;
+        }
+        // groups smaller than the matrix (host build, single-warp groups): the remaining columns, plain loop
+        for (int c2 = g.tid() + g.size(); c2 < 8 * K; c2 += g.size()) {
+            double acc = S.st[c2];
+            for (int a = 0; a < 8; ++a) acc -= A[WK::pk(8 * K + a, c2)] * S.xt[8 * K + a];
+            S.st[c2] = acc;
         }
         g.sync();
     }
