@@ -1,16 +1,22 @@
 #!/usr/bin/env python
-"""bench.py -- batched MPC solves/sec (TRON1, horizon 10) on N B200s + p50 single-solve latency.
+"""bench.py -- batched MPC solves/sec (TRON1) on N B200s + p50 single-solve latency.
 
-One "step" = one pass of the hot path (linearise -> discretise -> condense -> QP solve -> forces)
-over one batch of B synthetic instances per GPU (BASELINE.json configs[1]: B=4096, N=10, trot
-contact schedule from the gait clock, friction pyramid).  Instances are independent, so N GPUs
-each run their own B instances (weak scaling, no collective on the solve path; torch.distributed
-is used only for the barrier and the max-over-ranks time).
+One "step" = one pass of the hot path (linearise -> discretise -> condense -> QP solve -> forces) over one batch of
+synthetic instances.  Instances are independent, so GPUs shard by instance with no collective on the solve path
+(torch.distributed is used only for the barrier and the max-over-ranks time).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config 2|2s|2x|3|4|5] [--impl reference]
 
---impl reference times the reference's CPU path (the oracle port of QPSolver/mpcQP + a cold-start
-active-set QP; Eigen/qpOASES are not installable here) on all host cores, same workload."""
+--config selects a BASELINE.json workload (default 2 = the configuration the headline metric is quoted on):
+  2   B=4096 per GPU, horizon 10, trot schedule from the gait clock, friction pyramid   (weak scaling)
+  2s  same, every robot standing on both feet (double-support capacity class)
+  2x  same, stressed: state x5, mu=0.3, Ts=0.02 (friction pyramid active, multi-iteration instances)
+  3   B=65536 TOTAL, horizon 20, sharded 65536/G per GPU                                 (strong scaling)
+  4   B=8192 TOTAL, horizon 50 (tensor-core Cholesky path), sharded                      (strong scaling)
+  5   closed loop: 16384 robots TOTAL x 1000 control steps, warm-started, sharded        (strong scaling; a step =
+      one full rollout; --steps is clamped so the default run stays within minutes)
+--impl reference times the reference's CPU path (the oracle port of QPSolver/mpcQP + a cold-start active-set QP; Eigen /
+qpOASES are not installable here) on all host cores, on a bounded sample of the same workload."""
 import argparse
 import json
 import os
@@ -35,14 +41,66 @@ def emit(line):
     _JSON_OUT.flush()
 
 
-SEED, HORIZON, TS = 1001, 10, 0.005
-METRIC = "batched MPC solves/sec (TRON1, N=10)"
+CONFIGS = {
+    "2": dict(N=10, B=4096, seed=1001, Ts=0.005, standing=False, scale=1.0, mu=0.5, kind="solve", scaling="weak",
+              what="trot contact schedule from the gait clock, friction pyramid mu=0.5, f_max=2mg (BASELINE configs[1])"),
+    "2s": dict(N=10, B=4096, seed=1001, Ts=0.005, standing=True, scale=1.0, mu=0.5, kind="solve", scaling="weak",
+               what="every robot standing on both feet (double support), friction pyramid mu=0.5 (BASELINE configs[0] batched)"),
+    "2x": dict(N=10, B=4096, seed=1001, Ts=0.02, standing=False, scale=5.0, mu=0.3, kind="solve", scaling="weak",
+               what="stressed: state x5, mu=0.3, Ts=0.02, trot schedule (friction pyramid active)"),
+    "3": dict(N=20, B=65536, seed=1002, Ts=0.005, standing=False, scale=1.0, mu=0.5, kind="solve", scaling="strong",
+              what="randomised yaw / foot positions / gait phase, sharded by instance (BASELINE configs[2])"),
+    "4": dict(N=50, B=8192, seed=1003, Ts=0.005, standing=False, scale=1.0, mu=0.5, kind="solve", scaling="strong",
+              what="long horizon, reduced Hessian 150x150 per instance, tensor-core Cholesky (BASELINE configs[3])"),
+    "5": dict(N=10, B=16384, seed=1004, Ts=0.005, standing=False, scale=1.0, mu=0.5, kind="rollout", steps=1000, scaling="strong",
+              what="closed loop: linearise -> condense -> solve -> integrate, warm-started, state resident on the GPU (BASELINE configs[4])"),
+}
 
 
-def algorithmic_flops(N, iters):
-    """SURVEY.md 8d fixed accounting (n = 6N, p = 13(N+1))."""
+def metric_name(cfg):
+    return f"batched MPC solves/sec (TRON1, N={cfg['N']})"
+
+
+def workload_name(cfg, world):
+    """The SAME string in both arms (the driver compares config.workload of the two lines)."""
+    per = "per GPU" if cfg["scaling"] == "weak" else f"in total, sharded over {world} GPU(s)"
+    s = f"TRON1 convex MPC, horizon {cfg['N']}, Ts {cfg['Ts']}, B={cfg['B']} instances {per}"
+    if cfg["kind"] == "rollout":
+        s += f" x {cfg['steps']} closed-loop control steps"
+    return s + ", " + cfg["what"]
+
+
+def dense_equiv_flops(N, iters):
+    """SURVEY.md 8d DENSE accounting (n = 6N, p = 13(N+1)): what a dense evaluation of the reference's formulas costs."""
     n, p = 6 * N, 13 * (N + 1)
     return 6422 * N + (n * n * p + n * p) + (26 * p + 2 * p + 2 * p * n) + n ** 3 / 3 + iters * (4 * n * n + 10 * n + 32 * N)
+
+
+def structured_flops(N, nc, iters, group_threads):
+    """FP64 operations the kernel EXECUTES per solve (thread level, FMA = 2), hand-counted from csrc/tron1_core.cuh
+    (DESIGN.md section 4 'executed work').  m = nc/3 stance foot-steps.
+      setup (once)            : model + horizon sums + free response + adjoint        ~ 450 N
+      per active-face solve   : m(m+1)/2 Hessian blocks x 157  (build_hessian, one 3x3 block per work item)
+                                + elimination / factorisation (below)
+                                + gradient + optimality check                         ~ 300 N
+      elimination, nc <= 60   : register Gauss-Jordan, EVERY lane of the group carries a row window:
+                                lanes x sum over the 5 stages of (nc/5) columns x (2 W + 10), W = window length
+      factorisation, N = 50   : tiled Cholesky: 512 flops per DMMA.8x8x4 x (2 per trailing tile + 2 per panel tile
+                                + 2 per look-ahead tile) + 19 diagonal factors x ~600 x 32 lanes + blocked solves 2 nc^2
+    Checked against ncu's executed thread-level count for the headline kernel (profiles/r2_*: within 10 %)."""
+    m = nc / 3.0
+    setup = 450.0 * N
+    hess = 157.0 * m * (m + 1) / 2
+    it_rest = 300.0 * N
+    if N == 50:
+        NT = (int(nc) + 8) // 8
+        tiles = sum(k * (k + 1) // 2 for k in range(1, NT))          # trailing tiles incl. look-ahead
+        panel = NT * (NT - 1) // 2
+        elim = 512.0 * 2 * (tiles + panel) + NT * 600.0 * 32 + 2.0 * nc * nc
+    else:
+        lanes = group_threads
+        elim = lanes * sum((nc / 5.0) * (2 * (nc - s * nc / 5.0) + 10) for s in range(5))
+    return setup + iters * (hess + elim + it_rest)
 
 
 def algorithmic_bytes(N):
@@ -93,57 +151,98 @@ class ClockSampler:
         return out
 
 
-def cpu_reference(nthreads, target_seconds, B_cap):
-    """Times the oracle port (restated reference CPU path) on `nthreads` host threads."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import oracle_lib as O
+def synth_batch(cfg, B, first=0):
     from mpc_limx_control_b200 import synth
-    p = O.tron1_defaults(Ts=TS)
-    probe = max(nthreads * 4, 32)
-    d = synth.tron1_batch(SEED, probe, HORIZON, TS)
-    c = np.stack([O.contact_schedule(int(i), HORIZON) for i in d["iter"]])
-    O.tron1_solve_batch(p, HORIZON, d["x0"], d["x_ref"], d["feet"], c, nthreads)   # warm-up
-    t = time.perf_counter()
-    O.tron1_solve_batch(p, HORIZON, d["x0"], d["x_ref"], d["feet"], c, nthreads)
-    rate = probe / (time.perf_counter() - t)
-    n = int(min(B_cap, max(probe, rate * target_seconds)))
-    d = synth.tron1_batch(SEED, n, HORIZON, TS)
-    c = np.stack([O.contact_schedule(int(i), HORIZON) for i in d["iter"]])
-    return O, p, d, c, n
+    d = synth.tron1_batch(cfg["seed"], B, cfg["N"], cfg["Ts"], first=first, standing=cfg["standing"])
+    if cfg["scale"] != 1.0:
+        d["x0"][:, [0, 1, 6, 7, 8, 9, 10, 11]] *= cfg["scale"]
+    return d
 
 
-def run_reference(args):
+# ------------------------------------------------------------------------------------------------------------------
+# CPU path: the oracle port on the host cores (cpu_baseline of the GPU line, and the whole --impl reference arm)
+class CpuPath:
+    def __init__(self, cfg, nthreads):
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib as O
+        self.O, self.cfg, self.nthreads = O, cfg, nthreads
+        self.p = O.tron1_defaults(Ts=cfg["Ts"], mu=cfg["mu"])
+
+    def prepare(self, n):
+        cfg, O = self.cfg, self.O
+        self.d = synth_batch(cfg, n)
+        self.c = np.stack([O.contact_schedule(int(i), cfg["N"]) for i in self.d["iter"]])
+        self.n = n
+
+    def run(self, rollout_steps=None):
+        """one pass over the prepared sample; returns the number of solves done"""
+        cfg, O, d = self.cfg, self.O, self.d
+        if cfg["kind"] == "rollout":
+            from concurrent.futures import ThreadPoolExecutor
+            from mpc_limx_control_b200 import synth
+            steps = rollout_steps
+
+            def one(b):
+                O.tron1_rollout(self.p, cfg["N"], steps, d["x0"][b], float(d["omega_yaw"][b]), float(d["velocity_x"][b]),
+                                int(d["iter"][b]), synth.FOOT_OFFSET_L, synth.FOOT_OFFSET_R)
+            with ThreadPoolExecutor(self.nthreads) as ex:      # ctypes releases the GIL: one rollout per thread at a time
+                list(ex.map(one, range(self.n)))
+            return self.n * steps
+        O.tron1_solve_batch(self.p, cfg["N"], d["x0"], d["x_ref"], d["feet"], self.c, self.nthreads)
+        return self.n
+
+    def size_for(self, seconds, cap, rollout_steps=None):
+        """sample size that takes about `seconds` on this box"""
+        probe = max(self.nthreads * (1 if self.cfg["N"] >= 50 or self.cfg["kind"] == "rollout" else 4), 8)
+        self.prepare(probe)
+        self.run(rollout_steps)     # warm-up
+        t = time.perf_counter()
+        done = self.run(rollout_steps)
+        rate = done / (time.perf_counter() - t)
+        per_item = done / probe
+        n = int(min(cap, max(self.nthreads, rate * seconds / per_item)))
+        self.prepare(n)
+        return n
+
+
+def run_reference(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     cores = os.cpu_count() or 1
+    cpu = CpuPath(cfg, cores)
+    rsteps = 20 if cfg["kind"] == "rollout" else None
     # bounded sample per step so that the whole K+W run ends within a few minutes
-    O, p, d, c, n = cpu_reference(cores, min(2.0, 150.0 / (args.steps + args.warmup)), args.batch)
+    n = cpu.size_for(min(2.0, 150.0 / (args.steps + args.warmup)), cfg["B"], rsteps)
     for _ in range(args.warmup):
-        O.tron1_solve_batch(p, HORIZON, d["x0"], d["x_ref"], d["feet"], c, cores)
+        cpu.run(rsteps)
     t0 = time.perf_counter()
+    done = 0
     for _ in range(args.steps):
-        F, st, it = O.tron1_solve_batch(p, HORIZON, d["x0"], d["x_ref"], d["feet"], c, cores)
+        done += cpu.run(rsteps)
     dt = time.perf_counter() - t0
-    v = n * args.steps / dt
-    sample = f"{n} of the {args.batch} config-2 instances per step (seed {SEED}), {cores} threads, one solve per thread at a time"
+    v = done / dt
+    sample = (f"{n} of the {cfg['B']} instances per step (seed {cfg['seed']})"
+              + (f", first {rsteps} of the {cfg['steps']} control steps" if rsteps else "")
+              + f", {cores} threads, one solve per thread at a time")
     emit({
-        "impl": "reference", "metric": METRIC, "value": v, "unit": "solves/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": metric_name(cfg), "value": v, "unit": "solves/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": cfg["scaling"],
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"TRON1 convex MPC, horizon {HORIZON}, Ts {TS}, trot contact schedule + friction pyramid, "
-                               f"B={args.batch} per step (bounded sample: {n})", "seed": SEED},
+        "config": {"workload": workload_name(cfg, world), "seed": cfg["seed"], "config_id": args.config, "sample": sample},
         "cpu_baseline": {"value": v, "unit": "solves/s", "cores": cores, "kind": "port", "sample": sample,
                          "note": "restated reference CPU path (Eigen/qpOASES unavailable): dense condensing + cold-start active set"},
         "e2e": {"value": v, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     })
 
 
-def run_gpu(args):
+# ------------------------------------------------------------------------------------------------------------------
+def run_gpu(args, cfg):
     import torch
     import torch.distributed as dist
-    from mpc_limx_control_b200 import synth
-    from mpc_limx_control_b200.engine import Engine, measure_fp64_peak
+    from mpc_limx_control_b200 import shard
+    from mpc_limx_control_b200.engine import Engine, measure_fp64_peak, bind_solve_host, bind_control_host
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -155,30 +254,58 @@ def run_gpu(args):
     else:
         torch.cuda.set_device(0)
     dev = torch.device("cuda", local)
-    N, B, K, W = HORIZON, args.batch, args.steps, args.warmup
-
-    # rotating pool of distinct input batches, larger than the 126 MB L2, resident in HBM
-    per_batch_in = B * (104 + 104 * (N + 1) + 48 + 4)
-    pool_n = max(2, int(np.ceil(160e6 / per_batch_in)))
-    pool = []
-    for i in range(pool_n):
-        d = synth.tron1_batch(SEED, B, N, TS, first=(rank * pool_n + i) * B)
-        pool.append({k: torch.from_numpy(d[k]).to(dev) for k in ("x0", "x_ref", "feet", "iter")})
-    eng = Engine(horizon=N, max_batch=B, device=local, Ts=TS)
-    forces = torch.empty((B, N, 6), dtype=torch.float64, device=dev)
-    status = torch.empty(B, dtype=torch.int32, device=dev)
-    iters = torch.empty(B, dtype=torch.int32, device=dev)
-
-    # one pre-bound C-ABI call per pool entry: the timed loop issues mpc_b200_tron1_solve_device and nothing else
-    calls = [eng.bind_solve(p["x0"], p["x_ref"], p["feet"], it=p["iter"], forces=forces, status=status, iters=iters) for p in pool]
-
-    def step(i):
-        calls[i % pool_n]()
+    N, K, W = cfg["N"], args.steps, args.warmup
+    rollout = cfg["kind"] == "rollout"
+    # per-rank share: weak scaling keeps B per GPU, strong scaling block-partitions the total (shard.partition)
+    if cfg["scaling"] == "weak":
+        B, first_inst, B_total = cfg["B"], rank * cfg["B"], world * cfg["B"]
+    else:
+        first_inst, B = shard.partition(cfg["B"], world, rank)
+        B_total = cfg["B"]
+    if rollout:
+        K = max(1, min(K, 3)); W = max(1, min(W, 1))      # one step = 1000 control steps of every robot (~0.13 s)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    eng = Engine(horizon=N, max_batch=B, device=local, Ts=cfg["Ts"], mu=cfg["mu"])
+    per_batch_in = B * (104 + 104 * (N + 1) + 48 + 4)
+    extra = {}
+
+    if not rollout:
+        # rotating pool of distinct input batches, larger than the 126 MB L2, resident in HBM
+        pool_n = max(2, int(np.ceil(160e6 / per_batch_in)))
+        pool = []
+        for i in range(pool_n):
+            d = synth_batch(cfg, B, first=first_inst + i * B_total)
+            pool.append({k: torch.from_numpy(d[k]).to(dev) for k in ("x0", "x_ref", "feet", "iter")})
+        forces = torch.empty((B, N, 6), dtype=torch.float64, device=dev)
+        status = torch.empty(B, dtype=torch.int32, device=dev)
+        iters = torch.empty(B, dtype=torch.int32, device=dev)
+        # one pre-bound C-ABI call per pool entry: the timed loop issues mpc_b200_tron1_solve_device and nothing else
+        calls = [eng.bind_solve(p["x0"], p["x_ref"], p["feet"], it=p["iter"], forces=forces, status=status, iters=iters) for p in pool]
+        step = lambda i: calls[i % pool_n]()
+        l2_note = f"rotating pool of {pool_n} distinct input batches ({pool_n * per_batch_in / 1e6:.0f} MB) > 126 MB L2"
+    else:
+        d = synth_batch(cfg, B, first=first_inst)
+        x_init = torch.from_numpy(d["x0"]).to(dev)
+        oy = torch.from_numpy(d["omega_yaw"]).to(dev); vx = torch.from_numpy(d["velocity_x"]).to(dev)
+        it0 = torch.from_numpy(d["iter"]).to(dev)
+        x_state = x_init.clone()
+        res = {}
+
+        def step(i):
+            x_state.copy_(x_init)
+            _, res["bad"], res["its"] = eng.rollout(x_state, oy, vx, it0, cfg["steps"])
+        l2_note = "closed loop: the state never leaves the SM between control steps; inputs are 228 B per robot"
 
     for i in range(W):
         step(i)
@@ -194,123 +321,180 @@ def run_gpu(args):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = eng.launch_count() - l0
-    n_bad = int((status != 0).sum().item())
-    mean_iters = float(iters.float().mean().item())
-    tms = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms_max = float(tms.item())
+    ms_max = max_over_ranks(ms)
+    if rollout:
+        solves_per_step = B_total * cfg["steps"]
+        n_bad = int(res["bad"].sum().item())
+        mean_iters = float(res["its"].float().mean().item()) / cfg["steps"]
+    else:
+        solves_per_step = B_total
+        n_bad = int((status != 0).sum().item())
+        mean_iters = float(iters.float().mean().item())
+    value = solves_per_step * K / (ms_max * 1e-3)
 
     # ---- end to end through the host-buffer C-ABI call (pinned host memory, H2D + D2H inside) -------
-    d = synth.tron1_batch(SEED, B, N, TS, first=rank * B)
-    pin = {k: torch.from_numpy(d[k]).pin_memory() for k in ("x0", "x_ref", "feet", "iter")}
-    Fh = torch.empty((B, N, 6), dtype=torch.float64).pin_memory()
-    sh = torch.empty(B, dtype=torch.int32).pin_memory()
-    ih = torch.empty(B, dtype=torch.int32).pin_memory()
-    Ke = min(500, max(10, K // 4))
-    from mpc_limx_control_b200.engine import bind_solve_host, bind_control_host
-    host_call = bind_solve_host(eng, pin["x0"], pin["x_ref"], pin["feet"], it=pin["iter"], forces=Fh, status=sh, iters=ih)
-    # a rotating set of distinct pinned input/output batches: no step can be served from a copy of the previous step's
-    # bytes in any cache on either side of PCIe
-    host_calls = [host_call]
-    for j in range(1, 4):
-        dj = synth.tron1_batch(SEED, B, N, TS, first=(world * (j + 1) + rank) * B)
-        pj = {k: torch.from_numpy(dj[k]).pin_memory() for k in ("x0", "x_ref", "feet", "iter")}
-        host_calls.append(bind_solve_host(eng, pj["x0"], pj["x_ref"], pj["feet"], it=pj["iter"],
-                                          forces=torch.empty((B, N, 6), dtype=torch.float64).pin_memory(),
-                                          status=torch.empty(B, dtype=torch.int32).pin_memory(),
-                                          iters=torch.empty(B, dtype=torch.int32).pin_memory()))
-    for j in range(max(4, W // 4)):
-        host_calls[j % 4]()
-    barrier()
-    t0 = time.perf_counter()
-    for j in range(Ke):
-        host_calls[j % 4]()      # one mpc_b200_tron1_solve_host: inputs over PCIe, solve, results back, sync (pinned host buffers)
-    torch.cuda.synchronize()
-    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * Ke / float(te.item())
-    e2e_path = "zero-copy (kernel reads/writes the pinned host buffers over PCIe)" if eng.last_host_path() else "staged copies"
-    # the same call forced onto the staged-copy path (what a caller with pageable buffers gets), for comparison
-    eng.set_host_mode(Engine.HOST_STAGED)
-    for _ in range(3):
-        host_call()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(max(5, Ke // 4)):
-        host_call()
-    torch.cuda.synchronize()
-    ts_ = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ts_, op=dist.ReduceOp.MAX)
-    e2e_staged_value = world * B * max(5, Ke // 4) / float(ts_.item())
-    eng.set_host_mode(Engine.HOST_AUTO)
-    # controller-shaped host call (command in, first-step force out: the reference mpcQP's own I/O)
-    pin_c = {k: torch.from_numpy(d[k]).pin_memory() for k in ("omega_yaw", "velocity_x")}
-    u0h = torch.empty((B, 6), dtype=torch.float64).pin_memory()
-    ctrl_call = bind_control_host(eng, pin["x0"], pin_c["omega_yaw"], pin_c["velocity_x"], pin["feet"], it=pin["iter"], u0=u0h,
-                                  status=sh, iters=ih)
-    for _ in range(max(3, W // 4)):
-        ctrl_call()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(Ke):
-        ctrl_call()
-    torch.cuda.synchronize()
-    tc = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tc, op=dist.ReduceOp.MAX)
-    e2e_ctrl_value = world * B * Ke / float(tc.item())
+    e2e, e2e_ctrl = None, None
+    if not rollout:
+        Ke = min(500, max(5, K // 4)) if N == 10 else max(3, min(10, K // 2))
+        host_calls, keep = [], []
+        for j in range(4 if N == 10 else 2):
+            dj = synth_batch(cfg, B, first=first_inst + (j + 40) * B_total)
+            pj = {k: torch.from_numpy(dj[k]).pin_memory() for k in ("x0", "x_ref", "feet", "iter")}
+            out = (torch.empty((B, N, 6), dtype=torch.float64).pin_memory(), torch.empty(B, dtype=torch.int32).pin_memory(),
+                   torch.empty(B, dtype=torch.int32).pin_memory())
+            keep.append((dj, pj, out))
+            host_calls.append(bind_solve_host(eng, pj["x0"], pj["x_ref"], pj["feet"], it=pj["iter"], forces=out[0], status=out[1], iters=out[2]))
+        nh = len(host_calls)
+        for j in range(max(3, min(W, 8))):
+            host_calls[j % nh]()
+        barrier()
+        t0 = time.perf_counter()
+        for j in range(Ke):
+            host_calls[j % nh]()      # one mpc_b200_tron1_solve_host: inputs over PCIe, solve, results back, sync
+        torch.cuda.synchronize()
+        te = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": B_total * Ke / te, "unit": "solves/s", "h2d_bytes_per_step": B_total * (104 + 104 * (N + 1) + 48 + 4),
+               "d2h_bytes_per_step": B_total * (48 * N + 8), "steps": Ke,
+               "path": "zero-copy (kernel reads/writes the pinned host buffers over PCIe)" if eng.last_host_path() else "staged copies",
+               "host_batches": f"{nh} distinct pinned input/output batches in rotation"}
+        if N == 10:
+            # the same call forced onto the staged-copy path (what a caller with pageable buffers gets), for comparison
+            eng.set_host_mode(Engine.HOST_STAGED)
+            for _ in range(3):
+                host_calls[0]()
+            barrier()
+            ns = max(5, Ke // 4)
+            t0 = time.perf_counter()
+            for _ in range(ns):
+                host_calls[0]()
+            torch.cuda.synchronize()
+            e2e["staged_copies_value"] = B_total * ns / max_over_ranks(time.perf_counter() - t0)
+            eng.set_host_mode(Engine.HOST_AUTO)
+            # controller-shaped host call (command in, first-step force out: the reference mpcQP's own I/O)
+            dj, pj, out = keep[0]
+            pin_c = {k: torch.from_numpy(dj[k]).pin_memory() for k in ("omega_yaw", "velocity_x")}
+            u0h = torch.empty((B, 6), dtype=torch.float64).pin_memory()
+            ctrl_call = bind_control_host(eng, pj["x0"], pin_c["omega_yaw"], pin_c["velocity_x"], pj["feet"], it=pj["iter"], u0=u0h,
+                                          status=out[1], iters=out[2])
+            for _ in range(3):
+                ctrl_call()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(Ke):
+                ctrl_call()
+            torch.cuda.synchronize()
+            e2e_ctrl = {"value": B_total * Ke / max_over_ranks(time.perf_counter() - t0), "unit": "solves/s",
+                        "h2d_bytes_per_step": B_total * (104 + 16 + 48 + 4), "d2h_bytes_per_step": B_total * (48 + 8), "steps": Ke,
+                        "what": "mpc_b200_tron1_control_host: state + (yaw-rate, vx) command + feet + gait clock in, u = U_opt.col(0) "
+                                "out (the reference mpcQP constructor's own inputs/outputs); x_ref is generated on the device"}
+    else:
+        # closed loop end to end: initial states and commands from pinned host memory, final states and counters back
+        hp = {k: torch.from_numpy(d[k]).pin_memory() for k in ("x0", "omega_yaw", "velocity_x", "iter")}
+        xh = torch.empty((B, 13), dtype=torch.float64).pin_memory(); bh = torch.empty(B, dtype=torch.int32).pin_memory()
+        xd = torch.empty((B, 13), dtype=torch.float64, device=dev); oyd = torch.empty(B, dtype=torch.float64, device=dev)
+        vxd = torch.empty(B, dtype=torch.float64, device=dev); itd = torch.empty(B, dtype=torch.int32, device=dev)
+
+        def host_rollout():
+            xd.copy_(hp["x0"], non_blocking=True); oyd.copy_(hp["omega_yaw"], non_blocking=True)
+            vxd.copy_(hp["velocity_x"], non_blocking=True); itd.copy_(hp["iter"], non_blocking=True)
+            _, bad, _ = eng.rollout(xd, oyd, vxd, itd, cfg["steps"])
+            xh.copy_(xd, non_blocking=True); bh.copy_(bad, non_blocking=True)
+            torch.cuda.synchronize()
+        host_rollout()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            host_rollout()
+        te = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": B_total * cfg["steps"] * K / te, "unit": "solves/s", "h2d_bytes_per_step": B_total * (104 + 8 + 8 + 4),
+               "d2h_bytes_per_step": B_total * (104 + 4), "steps": K,
+               "path": "pinned host buffers -> cudaMemcpyAsync -> mpc_b200_tron1_rollout_device -> final state and counters back"}
     clocks = sampler.stop() if sampler else None
+
+    # ---- the other two regimes of the headline workload, first-class (config 2 only): short device-timed runs ----
+    if args.config == "2" and rank == 0:
+        for key, cid in (("standing", "2s"), ("stressed", "2x")):
+            c2 = CONFIGS[cid]
+            eng2 = Engine(horizon=N, max_batch=B, device=local, Ts=c2["Ts"], mu=c2["mu"])
+            pl = []
+            for i in range(8):
+                dd = synth_batch(c2, B, first=i * B)
+                pl.append({k: torch.from_numpy(dd[k]).to(dev) for k in ("x0", "x_ref", "feet", "iter")})
+            F2 = torch.empty((B, N, 6), dtype=torch.float64, device=dev)
+            s2 = torch.empty(B, dtype=torch.int32, device=dev); i2 = torch.empty(B, dtype=torch.int32, device=dev)
+            cl = [eng2.bind_solve(p["x0"], p["x_ref"], p["feet"], it=p["iter"], forces=F2, status=s2, iters=i2) for p in pl]
+            for i in range(8):
+                cl[i]()
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 200
+            a0.record()
+            for i in range(reps):
+                cl[i % 8]()
+            a1.record()
+            torch.cuda.synchronize()
+            extra[key] = {"value": B * reps / (a0.elapsed_time(a1) * 1e-3), "unit": "solves/s", "config_id": cid,
+                          "mean_iters": float(i2.float().mean().item()), "max_iters": int(i2.max().item()),
+                          "unsolved": int((s2 != 0).sum().item()), "workload": workload_name(c2, 1)}
+            eng2.close()
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- single-instance latency: host call -> forces on host, B = 1 --------------------------------
-    lat = []
-    one = {k: torch.from_numpy(d[k][:1].copy()).pin_memory() for k in ("x0", "x_ref", "feet", "iter")}
-    F1 = torch.empty((1, N, 6), dtype=torch.float64).pin_memory()
-    s1 = torch.empty(1, dtype=torch.int32).pin_memory(); i1 = torch.empty(1, dtype=torch.int32).pin_memory()
-    one_call = bind_solve_host(eng, one["x0"], one["x_ref"], one["feet"], it=one["iter"], forces=F1, status=s1, iters=i1)
-    for j in range(args.latency_calls + 200):
-        t0 = time.perf_counter()
-        one_call()       # host call -> forces on host
-        if j >= 200:
-            lat.append(time.perf_counter() - t0)
-    lat = np.array(lat if lat else [float("nan")]) * 1e6
-    # BASELINE configs[0]-style single robot STANDING on both feet (gait clock < 0): the double-support class
-    lat_s = []
-    one_s = torch.full((1,), -1, dtype=torch.int32).pin_memory()
-    stand_call = bind_solve_host(eng, one["x0"], one["x_ref"], one["feet"], it=one_s, forces=F1, status=s1, iters=i1)
-    for j in range(args.latency_calls // 4 + 200):
-        t0 = time.perf_counter()
-        stand_call()
-        if j >= 200:
-            lat_s.append(time.perf_counter() - t0)
-    lat_s = np.array(lat_s if lat_s else [float("nan")]) * 1e6
+    # ---- single-instance latency: host call -> forces on host, B = 1 (horizon 10 configs) ----------------
+    latency = None
+    if N == 10 and not rollout:
+        dj, pj, out = keep[0]
+        one = {k: torch.from_numpy(dj[k][:1].copy()).pin_memory() for k in ("x0", "x_ref", "feet", "iter")}
+        F1 = torch.empty((1, N, 6), dtype=torch.float64).pin_memory()
+        s1 = torch.empty(1, dtype=torch.int32).pin_memory(); i1 = torch.empty(1, dtype=torch.int32).pin_memory()
 
-    # ---- roofline of the dominant (only) kernel of the step --------------------------------------------
+        def lat_of(call, n):
+            v = []
+            for j in range(n + 200):
+                t0 = time.perf_counter()
+                call()       # host call -> forces on host
+                if j >= 200:
+                    v.append(time.perf_counter() - t0)
+            return np.array(v if v else [float("nan")]) * 1e6
+        walk = lat_of(bind_solve_host(eng, one["x0"], one["x_ref"], one["feet"], it=one["iter"], forces=F1, status=s1, iters=i1),
+                      args.latency_calls)
+        # BASELINE configs[0]: a single robot STANDING on both feet (gait clock < 0): the double-support class
+        one_s = torch.full((1,), -1, dtype=torch.int32).pin_memory()
+        stand = lat_of(bind_solve_host(eng, one["x0"], one["x_ref"], one["feet"], it=one_s, forces=F1, status=s1, iters=i1),
+                       args.latency_calls)
+        latency = {"p50_us": float(np.percentile(stand, 50)), "p99_us": float(np.percentile(stand, 99)), "calls": len(stand),
+                   "what": "BASELINE configs[0]: ONE standing robot (both feet in contact), B=1 host call -> forces on host, pinned buffers",
+                   "walking_p50_us": float(np.percentile(walk, 50)), "walking_p99_us": float(np.percentile(walk, 99))}
+
+    # ---- roofline of the dominant kernel of the step ---------------------------------------------------
     peaks = load_peaks()
     fp64_peak = measure_fp64_peak(local)
-    kernel_ms = ms / K                      # one kernel launch per step, timed with CUDA events on its stream
-    flops = algorithmic_flops(N, mean_iters) * B
-    achieved_tf = flops / (kernel_ms * 1e-3) / 1e12
+    kernel_ms = ms / K / (cfg["steps"] if rollout else 1)       # per batch-solve (rollout: per control step)
+    if cfg["standing"]:
+        nc, gthreads, kname = 6 * N, {10: 64, 20: 64, 50: 256}[N], {10: "tron1_solve_kernel<10,60,2,2,3,INDIRECT>", 20: "tron1_solve_kernel<20,120,2,2,1,INDIRECT>", 50: "tron1_solve_kernel<50,300,8,1,2,INDIRECT>"}[N]
+    else:
+        nc, gthreads = 3 * N, {10: 32, 20: 64, 50: 256}[N]
+        kname = {10: "tron1_solve_kernel<10,30,1,4,4,DIRECT,persistent>", 20: "tron1_solve_kernel<20,60,2,2,2,DIRECT,persistent>",
+                 50: "tron1_solve_kernel<50,150,8,1,1,DIRECT,persistent> (tiled DMMA Cholesky)"}[N]
+        if rollout:
+            kname = "tron1_rollout_kernel<10,30,1,4,4>"
+    f_exec = structured_flops(N, nc, max(mean_iters, 1.0), gthreads)
+    f_dense = dense_equiv_flops(N, mean_iters)
+    achieved_tf = f_exec * B / (kernel_ms * 1e-3) / 1e12
     hbm_peak = peaks["hbm_gbs"] if peaks else 6650.0
     achieved_gbs = algorithmic_bytes(N) * B / (kernel_ms * 1e-3) / 1e9
-    traffic, executed = None, None
+    traffic, ncu_exec = None, None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic = tj.get("dram_bytes_per_launch")
-        ex = tj.get("executed_fp64") or {}
-        if "flops_per_launch" in ex and B == tj.get("batch"):
-            # executed FP64 work from the committed ncu capture (thread-level DFMA x2 + DMUL + DADD), same batch
-            executed = {"flops_per_solve": ex["flops_per_launch"] / B,
-                        "achieved": ex["flops_per_launch"] / (kernel_ms * 1e-3) / 1e12, "unit": "TFLOP/s",
-                        "frac": ex["flops_per_launch"] / (kernel_ms * 1e-3) / 1e12 / fp64_peak if fp64_peak else None,
-                        "source": tj.get("source")}
+        ent = tj.get("configs", {}).get(args.config)
+        if ent and ent.get("batch") == B:
+            traffic = ent.get("dram_bytes_per_launch")
+            if ent.get("executed_fp64_flops_per_launch"):
+                ncu_exec = {"flops_per_solve": ent["executed_fp64_flops_per_launch"] / B, "source": ent.get("source"),
+                            "formula_over_ncu": f_exec / (ent["executed_fp64_flops_per_launch"] / B)}
     except Exception:
         pass
 
@@ -318,51 +502,50 @@ def run_gpu(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        O, p, dd, cc, n = cpu_reference(cores, 12.0, 1 << 20)
+        cp = CpuPath(cfg, cores)
+        rsteps = 20 if rollout else None
+        n = cp.size_for(12.0, 1 << 20, rsteps)
         t0 = time.perf_counter()
-        O.tron1_solve_batch(p, N, dd["x0"], dd["x_ref"], dd["feet"], cc, cores)
+        done = cp.run(rsteps)
         dt = time.perf_counter() - t0
-        cpu = {"value": n / dt, "unit": "solves/s", "cores": cores, "kind": "port",
-               "sample": f"{n} config-2 instances (seed {SEED}) in {dt:.1f} s, one solve per thread at a time",
+        cpu = {"value": done / dt, "unit": "solves/s", "cores": cores, "kind": "port",
+               "sample": f"{n} config-{args.config} instances (seed {cfg['seed']})" + (f" x {rsteps} control steps" if rsteps else "")
+                         + f" in {dt:.1f} s, one solve per thread at a time",
                "note": "restated reference CPU path (Eigen/qpOASES unavailable in the image)"}
 
     line = {
-        "metric": METRIC, "value": world * B * K / (ms_max * 1e-3), "unit": "solves/s", "n_gpus": world, "steps": K,
-        "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": metric_name(cfg), "value": value, "unit": "solves/s", "n_gpus": world, "steps": K,
+        "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"TRON1 convex MPC, horizon {N}, Ts {TS}, B={B} instances per GPU per step, trot contact "
-                               "schedule from the gait clock, friction pyramid mu=0.5, f_max=2mg (BASELINE configs[1])",
-                   "seed": SEED, "l2": f"rotating pool of {pool_n} distinct input batches ({pool_n * per_batch_in / 1e6:.0f} MB) > 126 MB L2",
-                   "parallelism": f"instance-sharded x{world}, no collective", "mean_iters": mean_iters, "unsolved": n_bad},
+        "config": {"workload": workload_name(cfg, world), "seed": cfg["seed"], "config_id": args.config, "l2": l2_note,
+                   "parallelism": f"instance-sharded x{world}, no collective", "instances_per_gpu": B,
+                   "mean_iters": mean_iters, "unsolved": n_bad},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": B * (104 + 104 * (N + 1) + 48 + 4),
-                "d2h_bytes_per_step": B * (48 * N + 8), "steps": Ke, "path": e2e_path,
-                "host_batches": "4 distinct pinned input/output batches in rotation",
-                "staged_copies_value": e2e_staged_value},
-        "e2e_controller": {"value": e2e_ctrl_value, "unit": "solves/s", "h2d_bytes_per_step": B * (104 + 16 + 48 + 4),
-                           "d2h_bytes_per_step": B * (48 + 8), "steps": Ke,
-                           "what": "mpc_b200_tron1_control_host: state + (yaw-rate, vx) command + feet + gait clock in, "
-                                   "u = U_opt.col(0) out (the reference mpcQP constructor's own inputs/outputs); x_ref is "
-                                   "generated on the device"},
+        "e2e": e2e,
         "gpu_launches": int(launches),
-        "latency": {"p50_us": float(np.percentile(lat, 50)), "p99_us": float(np.percentile(lat, 99)), "calls": len(lat),
-                    "what": "B=1 host call -> forces on host (pinned buffers)",
-                    "standing_p50_us": float(np.percentile(lat_s, 50)), "standing_p99_us": float(np.percentile(lat_s, 99))},
         "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": achieved_tf / fp64_peak if fp64_peak else None, "traffic": traffic,
                      "peak_source": "FP64 DFMA peak measured in this run by mpc_b200_measure_fp64_peak "
-                                    "(MEASURED_PEAKS.json has no FP64 entry)",
-                     "flops_per_solve": algorithmic_flops(N, mean_iters), "kernel": "tron1_solve_kernel<10,30,1,4,4,false>",
-                     "kernel_ms": kernel_ms,
-                     "note": "achieved uses SURVEY 8d's DENSE accounting (n^2 p condensing, n^3/3 Cholesky); the kernel's structured "
-                             "condensing executes ~10x fewer FLOPs, so frac can exceed 1 -- `executed` is the pipe-level view",
-                     "executed": executed},
+                                    "(MEASURED_PEAKS.json has no FP64 entry; DMMA.8x8x4 measures 37.1 TFLOP/s, "
+                                    "tools/microbench/chol_dmma_bench.cu)",
+                     "flops_per_solve": f_exec, "kernel": kname, "kernel_ms": kernel_ms,
+                     "what": "achieved = FP64 operations the kernel EXECUTES per solve (hand-counted structured formula, "
+                             "bench.py:structured_flops, DESIGN.md section 4) x instances / CUDA-event time of the launch",
+                     "ncu_check": ncu_exec,
+                     "dense_equiv": {"flops_per_solve": f_dense, "achieved": f_dense * B / (kernel_ms * 1e-3) / 1e12, "unit": "TFLOP/s",
+                                     "what": "SURVEY 8d DENSE accounting (n^2 p condensing, n^3/3 Cholesky): how fast the PROBLEM is "
+                                             "solved relative to a dense evaluation; can exceed the peak, not a hardware fraction"}},
         "roofline_hbm": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved_gbs / hbm_peak, "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                          "bytes_per_solve": algorithmic_bytes(N)},
         "cpu_baseline": cpu,
     }
+    if e2e_ctrl:
+        line["e2e_controller"] = e2e_ctrl
+    if latency:
+        line["latency"] = latency
+    line.update(extra)
     emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -373,17 +556,25 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=50)
-    ap.add_argument("--batch", type=int, default=4096)
+    ap.add_argument("--config", default="2", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=0, help="override the config's batch size")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--latency-calls", type=int, default=10000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    cfg = dict(CONFIGS[args.config])
+    if args.batch:
+        cfg["B"] = args.batch
+    if cfg["N"] != 10 or cfg["kind"] == "rollout":
+        # heavier steps: keep the default run within minutes (a horizon-50 batch is ~2.5 ms, a rollout ~0.13 s)
+        args.steps = min(args.steps, 200 if cfg["N"] == 20 else 50)
+        args.warmup = min(args.warmup, 10)
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, cfg)
     else:
-        run_gpu(args)
+        run_gpu(args, cfg)
 
 
 if __name__ == "__main__":

@@ -27,6 +27,15 @@ using namespace mpcb200;
 
 // horizon 50 uses the tiled storage + tensor-core Cholesky (tron1_core.cuh: chol_tiled); the shorter horizons keep the
 // packed triangle and the register-resident eliminations
+#ifndef MPC_DYNAMIC
+// direct class: 1 = persistent grid, groups pull instances from an atomic counter.  Built, parity
+// green and MEASURED (profiles/r2_dynamic_vs_static.log): 7-10 % SLOWER than the static one-CTA-per-four-instances
+// mapping at every batch size (B = 4096: 50.3 us against 45.5 us; B = 65536: 139.6 against 150.7 M solves/s).  The
+// hardware CTA scheduler already refills a slot as soon as a CTA retires, so what the batch time is made of is two
+// rounds of the ~20 us loaded single-instance latency, which instance-level pulling does not shorten, while the 8-byte
+// asynchronous copies cost more issue slots than the three TMA bulk copies per CTA of the static path.  Default: static.
+#define MPC_DYNAMIC 0
+#endif
 #ifndef MPC_N50_WPI_S
 #define MPC_N50_WPI_S 8      // warps per instance of the single-stance class of horizon 50
 #endif
@@ -117,7 +126,14 @@ struct CtaStage {
 // per-instance workspace small enough for 12-16 resident instances per SM; instances that need more
 // (double support) are appended to an overflow list and solved by the NC = 6N instantiation, which
 // runs INDIRECT (list-driven, grid-stride, plain loads) right after.  No host synchronisation.
-template <int N, int NC, int WPI, int IPC, int MINB, bool INDIRECT, bool AINL = true>
+// DYNAMIC (direct class only): the grid is PERSISTENT -- at most MINB CTAs per SM -- and every thread group pulls its next
+// instance from an atomic counter (ovf_count[2]; ovf_count[3] counts finished CTAs, the last one clears both), so a group
+// whose instance needs three active-face iterations no longer holds three finished neighbours' slots, and the batch
+// does not run in whole waves of CTAs.  A group's inputs arrive by 8-byte asynchronous copies (cp.async / LDGSTS; instance
+// slices are only 8-byte aligned, so the 16-byte bulk copies of the static path cannot address a single instance), and
+// the copy of the NEXT instance is issued as soon as the current one's staged inputs are dead (after setup_instance),
+// i.e. it overlaps the whole elimination.
+template <int N, int NC, int WPI, int IPC, int MINB, bool INDIRECT, bool AINL = true, bool DYNAMIC = false>
 __global__ void __launch_bounds__(32 * WPI * IPC, MINB)
 tron1_solve_kernel(const __grid_constant__ Tron1Const P, int B, const double* __restrict__ x0,
                    const double* __restrict__ xref, const double* __restrict__ feet,
@@ -203,7 +219,114 @@ tron1_solve_kernel(const __grid_constant__ Tron1Const P, int B, const double* __
 #endif
     };
 
-    if (!INDIRECT) {
+    if constexpr (!INDIRECT && DYNAMIC) {
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the overflow grid may queue up behind us
+        double* sx = st.xr + g.gid * XR;
+        double* s0 = st.x0 + g.gid * 13;
+        double* sf = st.feet + g.gid * fstride;
+        int32_t* next = ovf_count + 2;
+        int* s_next = reinterpret_cast<int*>(&st.bar) + (g.gid & 1);   // the static path's mbarrier slot: 2 ints (IPC <= 2 when WPI > 1)
+        auto claim = [&]() -> int {
+            int b;
+            if constexpr (WPI == 1) {
+                b = 0;
+                if (g.t == 0) b = atomicAdd(next, 1);
+                b = __shfl_sync(0xffffffffu, b, 0);
+            } else {
+                static_assert(WPI == 1 || IPC <= 2, "claim slot");
+                g.sync();                                  // the previous value has been read by every thread
+                if (g.t == 0) *s_next = atomicAdd(next, 1);
+                g.sync();
+                b = *s_next;
+            }
+            return b;
+        };
+        auto cp8 = [](double* dst, const double* src) {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+        };
+        auto fetch = [&](int b) {      // asynchronous: completes at the next wait_all
+            if (b >= B) return;
+            if (!cmd_oy) for (int i = g.t; i < XR; i += g.size()) cp8(sx + i, xref + (size_t)b * XR + i);
+            for (int i = g.t; i < 13; i += g.size()) cp8(s0 + i, x0 + (size_t)b * 13 + i);
+            for (int i = g.t; i < fstride; i += g.size()) cp8(sf + i, feet + (size_t)b * fstride + i);
+        };
+        // schedule word(s) of an instance, fetched when it is claimed and consumed when it is started
+        auto sched = [&](int b) -> int {
+            if (b >= B) return 0;
+            if (contact) { int v = 0; for (int s = g.t, k = 0; s < 2 * N; s += g.size(), ++k) v |= (contact[(size_t)b * 2 * N + s] ? 1 : 0) << k; return v; }
+            return iter[b];
+        };
+        auto put_contact = [&](int word) {   // fills S.contact from the schedule word, returns the compact size
+            if (contact) {
+                for (int s = g.t, k = 0; s < 2 * N; s += g.size(), ++k) S.contact[s] = (word >> k) & 1;
+            } else {
+                for (int k = g.t; k < N; k += g.size()) {
+                    int l, r;
+                    gait_contact(P, word < 0 ? word : word + k * P.gait_mpc_step, l, r);
+                    S.contact[2 * k] = (int8_t)l;
+                    S.contact[2 * k + 1] = (int8_t)r;
+                }
+            }
+            g.sync();
+            if constexpr (WPI == 1 && 2 * N <= 32) {
+                return 3 * __popc(__ballot_sync(0xffffffffu, g.t < 2 * N && S.contact[g.t]));
+            } else {
+                int c = 0;
+                for (int s = 0; s < 2 * N; ++s) c += S.contact[s];
+                return 3 * c;
+            }
+        };
+        int b = claim();
+        fetch(b);
+        int word = sched(b);
+        while (b < B) {
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            g.sync();
+            const int nc = put_contact(word);
+            int b_next = B, word_next = 0;
+            bool claimed = false;
+            auto prefetch_next = [&]() {
+                g.sync();                      // every thread of the group is done with the staged inputs
+                b_next = claim();
+                fetch(b_next);
+                word_next = sched(b_next);
+                claimed = true;
+            };
+            if (nc > NC) {     // does not fit this capacity class: hand over to the large instantiation
+                if (g.t == 0) {
+                    if (ovf_list) ovf_list[atomicAdd(ovf_count, 1)] = b;
+                    else if (status) status[b] = ST_FAILED;
+                }
+                prefetch_next();
+            } else {
+                int its = 0;
+                if (cmd_oy) {
+                    make_reference(S.x0, cmd_oy[b], cmd_vx[b], P.Ts, N, sx, g);
+                    g.sync();
+                }
+                const int code = solve_instance<Work>(P, S, sx, g, its, false, prefetch_next);
+                if (first_step_only) {
+                    if (g.t < 6) forces[(size_t)b * 6 + g.t] = S.u[g.t];
+                } else {
+                    double* out = forces + (size_t)b * 6 * N;
+                    for (int i = g.t; i < 6 * N; i += g.size()) out[i] = S.u[i];
+                }
+                if (g.t == 0) {
+                    if (status) status[b] = code;
+                    if (iters) iters[b] = its;
+                }
+                if (!claimed) prefetch_next();
+            }
+            b = b_next;
+            word = word_next;
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(&ovf_count[3], 1) == (int)gridDim.x - 1) { __threadfence(); ovf_count[2] = 0; ovf_count[3] = 0; }
+        }
+    } else if constexpr (!INDIRECT) {
         const int first = blockIdx.x * IPC;
         const int valid = min(IPC, B - first);
         // ---- stage this CTA's inputs: TMA bulk copies when the CTA's slice is 16-byte aligned ----------
@@ -454,7 +577,7 @@ struct mpc_b200_engine {
     double *d_x0 = nullptr, *d_xref = nullptr, *d_feet = nullptr, *d_forces = nullptr;
     uint8_t* d_contact = nullptr;
     int32_t *d_iter = nullptr, *d_status = nullptr, *d_iters = nullptr;
-    int32_t *d_ovf_list = nullptr, *d_ovf_count = nullptr;   // capacity-overflow routing: list, {length, readers} per slot
+    int32_t *d_ovf_list = nullptr, *d_ovf_count = nullptr;   // per slot: {overflow length, readers, next instance, finished CTAs}
     double *d_oy = nullptr, *d_vx = nullptr, *d_u0 = nullptr; // controller-shaped entry: commands in, first-step force out
     static constexpr int kPipe = 8;                          // streams used by the host-buffer entry
     static constexpr int kSmallB = 64;                       // packed single-copy path below this batch size
@@ -499,7 +622,7 @@ static int launch_solve(mpc_b200_engine* e, int B, const double* x0, const doubl
                         const uint8_t* contact, const int32_t* iter, double* forces, int32_t* status,
                         int32_t* iters, cudaStream_t s, int32_t* ovf_list, int32_t* ovf_count,
                         const double* cmd_oy, const double* cmd_vx, int first_only) {
-    auto ks = tron1_solve_kernel<N, 3 * N, WPI_S, IPC_S, MINB_S, false, true>;
+    auto ks = tron1_solve_kernel<N, 3 * N, WPI_S, IPC_S, MINB_S, false, true, MPC_DYNAMIC != 0>;
     auto kl = tron1_solve_kernel<N, 6 * N, WPI_L, IPC_L, MINB_L, true, AINL_L>;
     const size_t smem_s = ((sizeof(CtaStage<N, IPC_S>) + 15) & ~size_t(15)) + sizeof(SolveWork<N, 3 * N, true>) * IPC_S;
     const size_t smem_l = ((sizeof(CtaStage<N, IPC_L>) + 15) & ~size_t(15)) + sizeof(SolveWork<N, 6 * N, AINL_L>) * IPC_L;
@@ -523,7 +646,9 @@ static int launch_solve(mpc_b200_engine* e, int B, const double* x0, const doubl
         e->launches += 1;
         return MPC_B200_OK;
     }
-    ks<<<(B + IPC_S - 1) / IPC_S, 32 * WPI_S * IPC_S, smem_s, s>>>(e->C, B, x0, xref, feet, contact, iter, forces, status,
+    int grid_s = (B + IPC_S - 1) / IPC_S;
+    if (MPC_DYNAMIC != 0 && grid_s > e->num_sms * MINB_S) grid_s = e->num_sms * MINB_S;   // persistent: the groups pull instances
+    ks<<<grid_s, 32 * WPI_S * IPC_S, smem_s, s>>>(e->C, B, x0, xref, feet, contact, iter, forces, status,
                                                                  iters, ovf_list, ovf_count, nullptr, cmd_oy, cmd_vx, first_only);
     CU(e, cudaGetLastError());
     if (e->skip_large) {   // the host entry point has looked at the schedule: no instance can overflow, the list stays empty
@@ -557,7 +682,7 @@ static int dispatch_solve(mpc_b200_engine* e, int B, const double* x0, const dou
                           const double* cmd_oy = nullptr, const double* cmd_vx = nullptr, int first_only = 0) {
     if (B + list_offset > e->max_batch) return set_err(e, MPC_B200_ECAPACITY, "solve: B > max_batch");
     int32_t* ol = e->d_ovf_list + list_offset;
-    int32_t* oc = e->d_ovf_count + 2 * slot;
+    int32_t* oc = e->d_ovf_count + 4 * slot;
     switch (e->N) {
         case 10: return launch_solve<10, 1, 4, 4, 2, 2, true, 3>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only);
         case 20: return launch_solve<20, 2, 2, 2, 2, 2>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only);
@@ -633,8 +758,8 @@ int mpc_b200_create(const mpc_b200_tron1_params* p, int horizon, int max_batch, 
               cudaMalloc(&e->d_status, sizeof(int32_t) * max_batch) == cudaSuccess &&
               cudaMalloc(&e->d_iters, sizeof(int32_t) * max_batch) == cudaSuccess &&
               cudaMalloc(&e->d_ovf_list, sizeof(int32_t) * max_batch) == cudaSuccess &&
-              cudaMalloc(&e->d_ovf_count, 2 * (mpc_b200_engine::kPipe + 1) * sizeof(int32_t)) == cudaSuccess &&
-              cudaMemset(e->d_ovf_count, 0, 2 * (mpc_b200_engine::kPipe + 1) * sizeof(int32_t)) == cudaSuccess &&
+              cudaMalloc(&e->d_ovf_count, 4 * (mpc_b200_engine::kPipe + 1) * sizeof(int32_t)) == cudaSuccess &&
+              cudaMemset(e->d_ovf_count, 0, 4 * (mpc_b200_engine::kPipe + 1) * sizeof(int32_t)) == cudaSuccess &&
               cudaMalloc(&e->d_oy, sizeof(double) * max_batch) == cudaSuccess &&
               cudaMalloc(&e->d_vx, sizeof(double) * max_batch) == cudaSuccess &&
               cudaMalloc(&e->d_u0, sizeof(double) * 6 * max_batch) == cudaSuccess;

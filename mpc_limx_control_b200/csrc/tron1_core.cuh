@@ -1602,10 +1602,15 @@ MPC_HD void setup_instance(const Tron1Const& P, WK& S, const double* xref, const
 
 // ---- full QP solve of one instance.  On exit S.u holds the forces (full layout). -----------------
 // iters = face solves + ADMM iterations.
-template <class WK, class G>
-MPC_HD int solve_instance(const Tron1Const& P, WK& S, const double* xref, const G& g, int& iters, bool warm = false) {
+// `after_setup` runs once the staged inputs (xref, S.x0, S.feet) are dead: everything the iterations need has been
+// condensed into S by then, so a persistent kernel starts fetching its next instance into the same staging area there.
+struct NoHook { MPC_HD void operator()() const {} };
+template <class WK, class G, class Hook = NoHook>
+MPC_HD int solve_instance(const Tron1Const& P, WK& S, const double* xref, const G& g, int& iters, bool warm = false,
+                          Hook after_setup = Hook()) {
     [[maybe_unused]] constexpr int N = WK::N;
     setup_instance<WK>(P, S, xref, g, warm);
+    after_setup();
     iters = 0;
     // non-finite inputs (NaN/inf state, reference or feet) poison f: report failure instead of iterating
     // (a NaN would otherwise slip through the max-reductions of the optimality check)
