@@ -125,6 +125,17 @@ int mpc_b200_tron1_solve_host(mpc_b200_engine *e, int B, const double *x0, const
                               const double *feet, const uint8_t *contact, const int32_t *iter,
                               double *forces, int32_t *status, int32_t *iters);
 
+/* Single-process multi-GPU batch entry (the reference has no counterpart: it solves one robot per
+ * call, include/mpcQP.h:63,113).  engines[0..G) are engines of the SAME horizon and parameters on DIFFERENT devices, each
+ * with max_batch >= its share.  The batch is block-partitioned by instance -- GPU g owns [g*B/G + min(g, B%G), ...), the
+ * first B%G GPUs one instance more -- and every GPU runs mpc_b200_tron1_solve_host on its slice of the caller's arrays
+ * from its own host thread and stream; results land in the caller's arrays (one gather-free pinned result array when the
+ * buffers are pinned: every GPU writes its rows over PCIe itself).  No collective, no peer traffic.
+ * Returns the first non-zero status of any GPU (all GPUs are always waited for). */
+int mpc_b200_tron1_solve_host_multi(mpc_b200_engine *const *engines, int G, int B, const double *x0, const double *x_ref,
+                                    const double *feet, const uint8_t *contact, const int32_t *iter,
+                                    double *forces, int32_t *status, int32_t *iters);
+
 /* Controller-shaped host entry, the closest analogue of the reference's mpcQP constructor
  * (include/mpcQP.h:35-119): state, commanded yaw rate / forward velocity (the reference generator of
  * include/mpcQP.h:74-97 runs on the device), feet and gait in; u = U_opt.col(0) (include/mpcQP.h:118)

@@ -18,6 +18,8 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
+#include <vector>
 
 #include "../../include/mpc_b200.h"
 #include "tron1_core.cuh"
@@ -1032,6 +1034,41 @@ int mpc_b200_tron1_solve_host(mpc_b200_engine* e, int B, const double* x0, const
     if (B > e->max_batch) return set_err(e, MPC_B200_ECAPACITY, "solve_host: B > max_batch");
     CU(e, cudaSetDevice(e->device));
     return solve_host_impl(e, B, x0, x_ref, nullptr, nullptr, feet, contact, iter, forces, status, iters, false);
+}
+
+int mpc_b200_tron1_solve_host_multi(mpc_b200_engine* const* engines, int G, int B, const double* x0, const double* x_ref,
+                                    const double* feet, const uint8_t* contact, const int32_t* iter, double* forces,
+                                    int32_t* status, int32_t* iters) {
+    if (!engines || G < 1 || G > 64 || B < 1 || !x0 || !x_ref || !feet || !forces) return MPC_B200_EINVAL;
+    if ((contact == nullptr) == (iter == nullptr)) return MPC_B200_EINVAL;
+    for (int g = 0; g < G; ++g) {
+        if (!engines[g]) return MPC_B200_EINVAL;
+        if (engines[g]->N != engines[0]->N || engines[g]->C.per_step_feet != engines[0]->C.per_step_feet)
+            return set_err(engines[g], MPC_B200_EINVAL, "solve_host_multi: engines differ in horizon or feet layout");
+        for (int h = 0; h < g; ++h)
+            if (engines[h]->device == engines[g]->device) return set_err(engines[g], MPC_B200_EINVAL, "solve_host_multi: two engines on one device");
+    }
+    const int N = engines[0]->N;
+    const size_t fstride = (engines[0]->C.per_step_feet && engines[0]->C.ltv) ? 6 * (size_t)N : 6;
+    const size_t XR = 13 * (size_t)(N + 1);
+    const int base = B / G, extra = B % G;
+    std::vector<int> rc((size_t)G, MPC_B200_OK);
+    auto work = [&](int g) {
+        const int cnt = base + (g < extra ? 1 : 0);
+        const size_t f = (size_t)g * base + (size_t)(g < extra ? g : extra);
+        if (cnt == 0) return;
+        rc[g] = mpc_b200_tron1_solve_host(engines[g], cnt, x0 + 13 * f, x_ref + XR * f, feet + fstride * f,
+                                          contact ? contact + 2 * (size_t)N * f : nullptr, iter ? iter + f : nullptr,
+                                          forces + 6 * (size_t)N * f, status ? status + f : nullptr, iters ? iters + f : nullptr);
+    };
+    // one host thread per GPU (the calling thread takes GPU 0): each blocks in its own stream synchronise
+    std::vector<std::thread> th;
+    th.reserve((size_t)G);
+    for (int g = 1; g < G; ++g) th.emplace_back(work, g);
+    work(0);
+    for (auto& t : th) t.join();
+    for (int g = 0; g < G; ++g) if (rc[g]) return rc[g];
+    return MPC_B200_OK;
 }
 
 int mpc_b200_tron1_control_host(mpc_b200_engine* e, int B, const double* x0, const double* omega_yaw, const double* velocity_x,

@@ -258,6 +258,26 @@ def bind_control_host(eng, x0, omega_yaw, velocity_x, feet, contact=None, it=Non
     return call
 
 
+def solve_host_multi(engines, x0, x_ref, feet, contact=None, it=None, forces=None, status=None, iters=None):
+    """Single-process multi-GPU batch solve (mpc_b200_tron1_solve_host_multi): `engines` = one Engine per device, the batch
+    is block-partitioned by instance, every GPU reads/writes its rows of the caller's host arrays."""
+    e0 = engines[0]
+    x0 = _np(x0, np.float64); x_ref = _np(x_ref, np.float64); feet = _np(feet, np.float64)
+    contact = _np(contact, np.uint8); it = _np(it, np.int32)
+    B, N = x0.shape[0], e0.N
+    forces = np.empty((B, N, 6)) if forces is None else forces
+    status = np.empty(B, np.int32) if status is None else status
+    iters = np.empty(B, np.int32) if iters is None else iters
+    hs = (C.c_void_p * len(engines))(*[e.h for e in engines])
+    p = lambda a: None if a is None else C.c_void_p(as_np_out(a).ctypes.data)
+    rc = e0.lib.mpc_b200_tron1_solve_host_multi(hs, len(engines), B, p(x0), p(x_ref), p(feet), p(contact), p(it), p(forces),
+                                                p(status), p(iters))
+    for e in engines:
+        if rc:
+            _capi.check(rc, e.h)
+    return forces, status, iters
+
+
 def pin_host_buffer(a):
     """Page-lock a numpy array in place (mpc_b200_pin_host_buffer) so that host calls using it run zero-copy."""
     _capi.check(_capi.lib().mpc_b200_pin_host_buffer(C.c_void_p(a.ctypes.data), a.nbytes))

@@ -1,5 +1,7 @@
 """Summarise an ncu report + launch list into profiles/ (tracked evidence).
-usage: python tools/ncu_summary.py <tag> [gpurun_out/prof.ncu-rep] [gpurun_out/launches.csv]"""
+usage: python tools/ncu_summary.py <tag> [gpurun_out/prof.ncu-rep] [gpurun_out/launches.csv] [--config C --batch B]
+With --config the hot kernel's DRAM traffic and executed FP64 work are merged into profiles/traffic.json under
+configs[C] (bench.py --config C reads them back as roofline.traffic / roofline.ncu_check)."""
 import csv
 import json
 import os
@@ -8,9 +10,15 @@ import sys
 from collections import defaultdict
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-tag = sys.argv[1]
-rep = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "gpurun_out", "prof.ncu-rep")
-lst = sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, "gpurun_out", "launches.csv")
+argv = list(sys.argv)
+cfg_id, cfg_batch = None, None
+if "--config" in argv:
+    i = argv.index("--config"); cfg_id = argv[i + 1]; del argv[i:i + 2]
+if "--batch" in argv:
+    i = argv.index("--batch"); cfg_batch = int(argv[i + 1]); del argv[i:i + 2]
+tag = argv[1]
+rep = argv[2] if len(argv) > 2 else os.path.join(ROOT, "gpurun_out", "prof.ncu-rep")
+lst = argv[3] if len(argv) > 3 else os.path.join(ROOT, "gpurun_out", "launches.csv")
 out = os.path.join(ROOT, "profiles")
 
 KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
@@ -37,7 +45,8 @@ if os.path.exists(rep):
     for r in rows[2:]:
         k = {"kernel": r[kcol]}
         for i, h in enumerate(H):
-            if h in KEEP or "warp_issue_stalled" in h and h.endswith("_per_warp_active.pct"):
+            if h in KEEP or ("warp_issue_stalled" in h and h.endswith("_per_warp_active.pct")) or "dmma" in h.lower() or \
+                    ("pipe_tensor" in h and "pct_of_peak_sustained_active" in h) or "pipe_fp64" in h and "pct" in h:
                 k[h] = r[i] + (" " + rows[1][i] if rows[1][i] else "")
         kernels.append(k)
     summary["kernels"] = kernels
@@ -66,9 +75,18 @@ if os.path.exists(rep):
                                         "flops_per_launch": (2 * dfma + dmul + dadd) * cyc, "cycles_elapsed_max": cyc}
         except Exception as ex:
             summary["executed_fp64"] = {"error": str(ex)}
-        json.dump({"dram_bytes_per_launch": traffic, "source": f"profiles/{tag}_solve_kernel.json (ncu --set full)",
-                   "executed_fp64": summary.get("executed_fp64"), "batch": 4096},
-                  open(os.path.join(out, "traffic.json"), "w"), indent=1)
+        if cfg_id is not None:
+            tpath = os.path.join(out, "traffic.json")
+            try:
+                tj = json.load(open(tpath))
+            except Exception:
+                tj = {}
+            tj.setdefault("configs", {})[cfg_id] = {
+                "batch": cfg_batch, "kernel": k0["kernel"][:120], "dram_bytes_per_launch": traffic,
+                "executed_fp64_flops_per_launch": (summary.get("executed_fp64") or {}).get("flops_per_launch"),
+                "frac_of_dfma_peak_ncu": (summary.get("executed_fp64") or {}).get("frac_of_dfma_peak"),
+                "source": f"profiles/{tag}_solve_kernel.json (ncu --set full, hot kernel of bench.py --config {cfg_id})"}
+            json.dump(tj, open(tpath, "w"), indent=1)
 if os.path.exists(lst):
     rows = [r for r in csv.reader(open(lst)) if len(r) > 5]
     h = [i for i, r in enumerate(rows) if r[0] == "ID"][0]

@@ -1,11 +1,22 @@
+# Round-2 measurement pass on one B200 (run under gpurun): tests, bench lines, launch lists, ncu --set full captures.
+# Every ncu command is preceded by the same command without ncu (&&) as the profiling recipe asks.
 set -x
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3 > gpurun_out/pytest_r1f.log
-python bench.py --steps 2000 --warmup 50 > gpurun_out/bench_r1f.json 2> gpurun_out/bench_r1f.err
-python bench.py --steps 5 --warmup 3 --latency-calls 10 --no-cpu-baseline > gpurun_out/plain_r1f.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r1f.csv python bench.py --steps 5 --warmup 3 --latency-calls 10 --no-cpu-baseline > gpurun_out/ncu_r1f_1.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:tron1_solve_kernel -s 6 -c 2 -o gpurun_out/prof_r1f -f python bench.py --steps 5 --warmup 3 --latency-calls 10 --no-cpu-baseline > gpurun_out/ncu_r1f_2.log 2>&1
-cat gpurun_out/pytest_r1f.log
-cut -c1-300 gpurun_out/bench_r1f.json
-python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_r1f_ref.json 2> gpurun_out/bench_r1f_ref.err
-python tools/bench_configs.py > gpurun_out/configs_r1f.jsonl 2> gpurun_out/configs_r1f.err
-python tools/host_path_probe.py > gpurun_out/host_probe_r1f.log 2>&1
+T=${1:-r2}
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3 > gpurun_out/${T}_pytest.log
+python bench.py --steps 2000 --warmup 50 > gpurun_out/${T}_bench_1gpu.json 2> gpurun_out/${T}_bench_1gpu.err
+python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/${T}_bench_reference_arm.json 2> gpurun_out/${T}_bench_reference_arm.err
+for c in 2s 2x 3 4 5; do
+  python bench.py --config $c > gpurun_out/${T}_bench_config$c.json 2> gpurun_out/${T}_bench_config$c.err
+done
+SHORT="--steps 5 --warmup 3 --latency-calls 10 --no-cpu-baseline"
+python bench.py $SHORT > gpurun_out/${T}_plain.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${T}_launches.csv python bench.py $SHORT > gpurun_out/${T}_ncu_1.log 2>&1
+python bench.py $SHORT > gpurun_out/${T}_plain.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:tron1_solve_kernel -s 6 -c 2 -o gpurun_out/${T}_prof_c2 -f python bench.py $SHORT > gpurun_out/${T}_ncu_2.log 2>&1
+for c in 2s 3 4; do
+  python bench.py --config $c $SHORT > gpurun_out/${T}_plain.log 2>&1 && \
+  ncu --set full --clock-control none -k regex:tron1_solve_kernel -s 6 -c 2 -o gpurun_out/${T}_prof_c$c -f python bench.py --config $c $SHORT > gpurun_out/${T}_ncu_c$c.log 2>&1
+done
+python bench.py --config 5 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/${T}_plain.log 2>&1 && \
+ncu --set full --clock-control none -k regex:tron1_rollout_kernel -s 2 -c 1 -o gpurun_out/${T}_prof_c5 -f python bench.py --config 5 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/${T}_ncu_c5.log 2>&1
+ls -la gpurun_out/*.ncu-rep
