@@ -191,6 +191,8 @@ typedef struct mpc_b200_swing_params {
     double foot_offset_left[3], foot_offset_right[3];  /* include/MPCParam.h:64-73 */
     double ik_tol, ik_dt, ik_damp;                     /* 1e-3, 1e-1, 1e-6: include/pinocchio_kinematics.h:61,76-77 */
     int32_t ik_max_iter;                               /* 10 */
+    int32_t ik_mode;                                   /* 0 (default): position task; 1: the reference's 6-D log6 task as written,
+                                                          include/pinocchio_kinematics.h:92-132 */
 } mpc_b200_swing_params;
 
 int mpc_b200_leg_default_model(mpc_b200_leg_model *m);
@@ -212,6 +214,15 @@ int mpc_b200_swing_step_device(const mpc_b200_leg_model *m, const mpc_b200_swing
                                double *d_next_foot, int32_t *d_swing_leg, double *d_ik_err, int32_t *d_ik_iters,
                                void *stream);
 
+/* PinocchioKinematics::inverseKinematics (include/pinocchio_kinematics.h:61-149) for a batch: joint angles that bring
+ * contact_L_Link (leg[b] = 0) / contact_R_Link (1) to target [B][3] (world), starting from q_init [B][6]; q_out [B][6]
+ * (the other leg's entries are copied through).  p->ik_mode selects the task; tolerance / step / damping / iteration cap
+ * are the reference's constants in *p.  ik_err [B] = norm of the last error the loop computed (3-D or 6-D), ik_iters [B]
+ * (both may be NULL). */
+int mpc_b200_leg_ik_device(const mpc_b200_leg_model *m, const mpc_b200_swing_params *p, int B, const double *d_base_pos,
+                           const double *d_base_quat, const int32_t *d_leg, const double *d_target, const double *d_q_init,
+                           double *d_q_out, double *d_ik_err, int32_t *d_ik_iters, void *stream);
+
 /* tau = -J(q)' f for both legs from the first-step forces u0 (a swing foot has f = 0, hence tau = 0). */
 int mpc_b200_grf_to_torque_device(const mpc_b200_leg_model *m, int B, const double *d_base_quat, const double *d_q,
                                   const double *d_u0, double *d_tau, void *stream);
@@ -224,6 +235,9 @@ int mpc_b200_swing_step_host(int device, const mpc_b200_leg_model *m, const mpc_
                              const double *base_pos, const double *base_quat, const double *q, const double *des_vel,
                              const int32_t *iter, double *q_cmd, double *feet, double *next_foot, int32_t *swing_leg,
                              double *ik_err, int32_t *ik_iters);
+int mpc_b200_leg_ik_host(int device, const mpc_b200_leg_model *m, const mpc_b200_swing_params *p, int B,
+                         const double *base_pos, const double *base_quat, const int32_t *leg, const double *target,
+                         const double *q_init, double *q_out, double *ik_err, int32_t *ik_iters);
 int mpc_b200_grf_to_torque_host(int device, const mpc_b200_leg_model *m, int B, const double *base_quat, const double *q,
                                 const double *u0, double *tau);
 

@@ -21,6 +21,7 @@ SYMBOLS = [
     "mpc_b200_tron1_reference_device", "mpc_b200_tron1_rollout_device", "mpc_b200_tron1_control_host",
     "mpc_b200_leg_default_model", "mpc_b200_swing_default_params", "mpc_b200_leg_fk_device", "mpc_b200_swing_step_device",
     "mpc_b200_grf_to_torque_device", "mpc_b200_leg_fk_host", "mpc_b200_swing_step_host", "mpc_b200_grf_to_torque_host",
+    "mpc_b200_leg_ik_device", "mpc_b200_leg_ik_host",
     "mpc_b200_kf_default_params", "mpc_b200_kf_reset_device", "mpc_b200_kf_update_device", "mpc_b200_kf_update_host",
     "mpc_b200_lti_create", "mpc_b200_lti_destroy", "mpc_b200_lti_last_error", "mpc_b200_lti_launch_count",
     "mpc_b200_lti_discretize", "mpc_b200_lti_build_qp", "mpc_b200_qp_solve_dense", "mpc_b200_lti_update_state",
@@ -47,7 +48,8 @@ class LegModel(C.Structure):
 class SwingParams(C.Structure):
     _fields_ = [("dt", C.c_float), ("swing_time", C.c_float), ("stance_time", C.c_float), ("gait_height", C.c_float),
                 ("p_rel_max", C.c_double), ("foot_offset_left", C.c_double * 3), ("foot_offset_right", C.c_double * 3),
-                ("ik_tol", C.c_double), ("ik_dt", C.c_double), ("ik_damp", C.c_double), ("ik_max_iter", C.c_int32)]
+                ("ik_tol", C.c_double), ("ik_dt", C.c_double), ("ik_damp", C.c_double), ("ik_max_iter", C.c_int32),
+                ("ik_mode", C.c_int32)]
 
 
 class KfParams(C.Structure):
@@ -105,6 +107,8 @@ def lib():
         L.mpc_b200_leg_fk_device.argtypes = [C.POINTER(LegModel), ip] + [vp] * 6
         L.mpc_b200_swing_step_device.argtypes = [C.POINTER(LegModel), C.POINTER(SwingParams), ip] + [vp] * 12
         L.mpc_b200_grf_to_torque_device.argtypes = [C.POINTER(LegModel), ip] + [vp] * 5
+        L.mpc_b200_leg_ik_device.argtypes = [C.POINTER(LegModel), C.POINTER(SwingParams), ip] + [vp] * 9
+        L.mpc_b200_leg_ik_host.argtypes = [ip, C.POINTER(LegModel), C.POINTER(SwingParams), ip] + [vp] * 8
         L.mpc_b200_leg_fk_host.argtypes = [ip, C.POINTER(LegModel), ip] + [vp] * 5
         L.mpc_b200_swing_step_host.argtypes = [ip, C.POINTER(LegModel), C.POINTER(SwingParams), ip] + [vp] * 11
         L.mpc_b200_grf_to_torque_host.argtypes = [ip, C.POINTER(LegModel), ip] + [vp] * 4

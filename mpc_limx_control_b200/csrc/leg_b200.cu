@@ -41,6 +41,7 @@ SwingParams to_swing(const mpc_b200_swing_params& p) {
     S.p_rel_max = p.p_rel_max;
     for (int i = 0; i < 3; ++i) { S.foot_off_l[i] = p.foot_offset_left[i]; S.foot_off_r[i] = p.foot_offset_right[i]; }
     S.ik_tol = p.ik_tol; S.ik_dt = p.ik_dt; S.ik_damp = p.ik_damp; S.ik_max_iter = p.ik_max_iter;
+    S.ik_mode = p.ik_mode;
     return S;
 }
 
@@ -100,7 +101,7 @@ swing_step_kernel(const __grid_constant__ LegModel M, const __grid_constant__ Sw
         foot_placement(P, s_pos + 3 * t, s_dv + 3 * t, remain, ls, fin);
         swing_next_position(P, ft + 3 * leg, fin, remain, nxt);
         for (int k = 0; k < 3; ++k) qv[k] = s_q[6 * t + 3 * leg + k];
-        const int its = leg_ik(M, P, leg, s_pos + 3 * t, Rb, nxt, qv, err);
+        const int its = leg_ik_task(M, P, leg, s_pos + 3 * t, Rb, nxt, qv, err);
         for (int k = 0; k < 3; ++k) q_cmd[6 * b + 3 * leg + k] = qv[k];   // only the swing leg's targets are written (:164-174)
         for (int k = 0; k < 3; ++k) s_out[6 * kThreads + 3 * t + k] = nxt[k];
         if (swing_leg) swing_leg[b] = leg;
@@ -110,6 +111,38 @@ swing_step_kernel(const __grid_constant__ LegModel M, const __grid_constant__ Sw
     __syncthreads();
     if (feet) cta_store(feet + 6 * (size_t)first, s_out, 6 * nb);
     if (next_foot) cta_store(next_foot + 3 * (size_t)first, s_out + 6 * kThreads, 3 * nb);
+}
+
+// ---- PinocchioKinematics::inverseKinematics for a batch (reference include/pinocchio_kinematics.h:61-149) ----------------
+// one thread per robot: target position of contact_{L,R}_Link -> joint angles, from the initial guess q_init
+__global__ void __launch_bounds__(kThreads)
+leg_ik_kernel(const __grid_constant__ LegModel M, const __grid_constant__ SwingParams P, int B, const double* __restrict__ pos,
+              const double* __restrict__ quat, const int32_t* __restrict__ leg, const double* __restrict__ target,
+              const double* __restrict__ q_init, double* __restrict__ q_out, double* __restrict__ ik_err,
+              int32_t* __restrict__ ik_iters) {
+    __shared__ double s_in[kThreads * 16];    // pos 3 | quat 4 | q 6 | target 3
+    __shared__ double s_out[kThreads * 6];
+    const int first = blockIdx.x * kThreads, nb = min(kThreads, B - first), t = threadIdx.x;
+    double* s_pos = s_in; double* s_quat = s_in + 3 * kThreads; double* s_q = s_in + 7 * kThreads; double* s_tg = s_in + 13 * kThreads;
+    cta_load(s_pos, pos + 3 * (size_t)first, 3 * nb);
+    cta_load(s_quat, quat + 4 * (size_t)first, 4 * nb);
+    cta_load(s_q, q_init + 6 * (size_t)first, 6 * nb);
+    cta_load(s_tg, target + 3 * (size_t)first, 3 * nb);
+    __syncthreads();
+    if (t < nb) {
+        const size_t b = (size_t)first + t;
+        double Rb[9], qv[3], err;
+        quat_to_rot(s_quat + 4 * t, Rb);
+        const int l = leg[b] ? 1 : 0;
+        for (int k = 0; k < 3; ++k) qv[k] = s_q[6 * t + 3 * l + k];
+        const int its = leg_ik_task(M, P, l, s_pos + 3 * t, Rb, s_tg + 3 * t, qv, err);
+        for (int k = 0; k < 6; ++k) s_out[6 * t + k] = s_q[6 * t + k];      // the other leg's joints pass through
+        for (int k = 0; k < 3; ++k) s_out[6 * t + 3 * l + k] = qv[k];
+        if (ik_err) ik_err[b] = err;
+        if (ik_iters) ik_iters[b] = its;
+    }
+    __syncthreads();
+    cta_store(q_out + 6 * (size_t)first, s_out, 6 * nb);
 }
 
 // ---- stance-leg torques from the optimal ground-reaction forces: tau = -J' f --------------------
@@ -229,10 +262,20 @@ int mpc_b200_swing_step_device(const mpc_b200_leg_model* m, const mpc_b200_swing
                                double* d_q_cmd, double* d_feet, double* d_next_foot, int32_t* d_swing_leg, double* d_ik_err,
                                int32_t* d_ik_iters, void* stream) {
     if (!m || !p || B < 1 || !d_base_pos || !d_base_quat || !d_q || !d_des_vel || !d_iter || !d_q_cmd) return MPC_B200_EINVAL;
-    if (p->ik_max_iter < 0 || !(p->swing_time > 0.0f) || !(p->swing_time + p->stance_time > 0.0f)) return MPC_B200_EINVAL;
+    if (p->ik_max_iter < 0 || p->ik_mode < 0 || p->ik_mode > 1 || !(p->swing_time > 0.0f) || !(p->swing_time + p->stance_time > 0.0f)) return MPC_B200_EINVAL;
     swing_step_kernel<<<(B + kThreads - 1) / kThreads, kThreads, 0, (cudaStream_t)stream>>>(
         to_model(*m), to_swing(*p), B, d_base_pos, d_base_quat, d_q, d_des_vel, d_iter, d_q_cmd, d_feet, d_next_foot, d_swing_leg,
         d_ik_err, d_ik_iters);
+    return check_launch();
+}
+
+int mpc_b200_leg_ik_device(const mpc_b200_leg_model* m, const mpc_b200_swing_params* p, int B, const double* d_base_pos,
+                           const double* d_base_quat, const int32_t* d_leg, const double* d_target, const double* d_q_init,
+                           double* d_q_out, double* d_ik_err, int32_t* d_ik_iters, void* stream) {
+    if (!m || !p || B < 1 || !d_base_pos || !d_base_quat || !d_leg || !d_target || !d_q_init || !d_q_out) return MPC_B200_EINVAL;
+    if (p->ik_max_iter < 0 || p->ik_mode < 0 || p->ik_mode > 1) return MPC_B200_EINVAL;
+    leg_ik_kernel<<<(B + kThreads - 1) / kThreads, kThreads, 0, (cudaStream_t)stream>>>(
+        to_model(*m), to_swing(*p), B, d_base_pos, d_base_quat, d_leg, d_target, d_q_init, d_q_out, d_ik_err, d_ik_iters);
     return check_launch();
 }
 
@@ -281,6 +324,26 @@ int mpc_b200_swing_step_host(int device, const mpc_b200_leg_model* m, const mpc_
     if (rc) return rc;
     st.get(q_cmd, dc, 6 * nb); st.get(feet, df, 6 * nb); st.get(next_foot, dn, 3 * nb);
     st.get(swing_leg, dl, nb); st.get(ik_err, de, nb); st.get(ik_iters, dit, nb);
+    if (!st.ok || cudaStreamSynchronize(h->s) != cudaSuccess) { cudaGetLastError(); return MPC_B200_ECUDA; }
+    return MPC_B200_OK;
+}
+
+int mpc_b200_leg_ik_host(int device, const mpc_b200_leg_model* m, const mpc_b200_swing_params* p, int B, const double* base_pos,
+                         const double* base_quat, const int32_t* leg, const double* target, const double* q_init, double* q_out,
+                         double* ik_err, int32_t* ik_iters) {
+    if (!m || !p || B < 1 || !base_pos || !base_quat || !leg || !target || !q_init || !q_out) return MPC_B200_EINVAL;
+    HostScratch* h;
+    const size_t nb = (size_t)B;
+    int rc = scratch_for(device, 8 * nb * (3 + 4 + 3 + 6 + 6 + 1) + 4 * nb * 2 + 512, &h);
+    if (rc) return rc;
+    Stage st{h};
+    const double* dp = st.put(base_pos, 3 * nb); const double* dq4 = st.put(base_quat, 4 * nb);
+    const int32_t* dl = st.put(leg, nb); const double* dt = st.put(target, 3 * nb); const double* dq = st.put(q_init, 6 * nb);
+    double* dout = st.put((const double*)nullptr, 6 * nb); double* de = st.put((const double*)nullptr, nb);
+    int32_t* dit = st.put((const int32_t*)nullptr, nb);
+    rc = mpc_b200_leg_ik_device(m, p, B, dp, dq4, dl, dt, dq, dout, de, dit, h->s);
+    if (rc) return rc;
+    st.get(q_out, dout, 6 * nb); st.get(ik_err, de, nb); st.get(ik_iters, dit, nb);
     if (!st.ok || cudaStreamSynchronize(h->s) != cudaSuccess) { cudaGetLastError(); return MPC_B200_ECUDA; }
     return MPC_B200_OK;
 }

@@ -18,9 +18,15 @@
 // unpinned (no URDF, no Pinocchio); the oracle (oracle/leg_oracle.c) defines it.
 //
 // The reference's IK is 6-D (log6 to an identity target orientation) on the 6-joint fixed-base model; a
-// 3-DoF point-foot leg cannot track orientation, and the reference reads a stale frame placement inside its
-// loop (forwardKinematics without updateFramePlacements).  Here the IK is the position-only damped
-// least-squares iteration with the reference's constants.  Deviation recorded in DESIGN.md.
+// 3-DoF point-foot leg cannot track orientation.  Two tasks are provided (SwingParams::ik_mode):
+//   0  position-only damped least squares with the reference's constants (what the author evidently wants from a
+//      point foot; the default of the swing-leg step)
+//   1  REFERENCE-LITERAL: the 6-D task exactly as written at include/pinocchio_kinematics.h:61-149 -- err =
+//      log6(oMf^-1 oMdes) with oMdes = (I, target), J = -Jlog6(iMd^-1) J_frame(LOCAL_WORLD_ALIGNED),
+//      v = -J' (J J' + damp I)^-1 err, q += v DT -- with log6 / Jlog6 restated from Pinocchio's published formulas
+//      (Pinocchio itself is an absent, unpinned dependency).  The frame placement is recomputed every iteration
+//      (the reference reads data.oMf without updateFramePlacements inside its loop, :104-106; which placement that
+//      yields depends on the Pinocchio version and is not replicated).
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -45,6 +51,7 @@ struct SwingParams {          // include/MPCParam.h:44-51,64-73 (float members k
     // IK constants, include/pinocchio_kinematics.h:61,74-77
     double ik_tol, ik_dt, ik_damp;
     int ik_max_iter;
+    int ik_mode;              // 0 position task, 1 reference-literal 6-D task
 };
 
 // R = I + sin(q) [a]x + (1 - cos(q)) [a]x^2   (row-major 3x3)
@@ -199,6 +206,216 @@ LEG_HD int leg_ik(const LegModel& M, const SwingParams& P, int leg, const double
     }
     err_out = en;
     return it;
+}
+
+// ---- reference-literal 6-D task (include/pinocchio_kinematics.h:61-149) ---------------------------------------------
+// Frame placement of the contact point in the world: position pw, rotation Rf (row-major) and the 6 x 3 frame Jacobian
+// in LOCAL_WORLD_ALIGNED convention (rows 0-2 linear = z_k x (p - c_k), rows 3-5 angular = z_k), J[row * 3 + joint].
+LEG_HD void leg_frame_world(const LegModel& M, int leg, const double base_pos[3], const double Rb[9], const double q[3],
+                            double pw[3], double Rf[9], double J6[18]) {
+    const double (*o)[3] = M.offset[leg];
+    double R0[9], R1[9], R2[9], R01[9], R012[9];
+    axis_angle(M.axis[leg][0], q[0], R0);
+    axis_angle(M.axis[leg][1], q[1], R1);
+    axis_angle(M.axis[leg][2], q[2], R2);
+    mat3_mul(R0, R1, R01);
+    mat3_mul(R01, R2, R012);
+    const double tip[3] = {o[3][0] + o[4][0], o[3][1] + o[4][1], o[3][2] + o[4][2]};
+    double t2[3], t1[3], t0[3], pb[3];
+    mat3_vec(R012, tip, t2);
+    mat3_vec(R01, o[2], t1);
+    mat3_vec(R0, o[1], t0);
+    const double c0[3] = {o[0][0], o[0][1], o[0][2]};
+    const double c1[3] = {c0[0] + t0[0], c0[1] + t0[1], c0[2] + t0[2]};
+    const double c2[3] = {c1[0] + t1[0], c1[1] + t1[1], c1[2] + t1[2]};
+    for (int i = 0; i < 3; ++i) pb[i] = c2[i] + t2[i];
+    double r[3];
+    mat3_vec(Rb, pb, r);
+    for (int i = 0; i < 3; ++i) pw[i] = base_pos[i] + r[i];
+    mat3_mul(Rb, R012, Rf);            // link frames are axis-aligned at q = 0 (fixed joints carry no rotation)
+    double z[3][3], zb1[3], zb2[3];
+    mat3_vec(R0, M.axis[leg][1], zb1);
+    mat3_vec(R01, M.axis[leg][2], zb2);
+    mat3_vec(Rb, M.axis[leg][0], z[0]);
+    mat3_vec(Rb, zb1, z[1]);
+    mat3_vec(Rb, zb2, z[2]);
+    const double* cs[3] = {c0, c1, c2};
+    for (int k = 0; k < 3; ++k) {
+        double db[3], d[3], lin[3];
+        for (int i = 0; i < 3; ++i) db[i] = pb[i] - cs[k][i];
+        mat3_vec(Rb, db, d);
+        cross3(z[k], d, lin);
+        for (int i = 0; i < 3; ++i) { J6[i * 3 + k] = lin[i]; J6[(3 + i) * 3 + k] = z[k][i]; }
+    }
+}
+
+// below this angle the closed forms cancel catastrophically and the series are used (Pinocchio:
+// TaylorSeriesExpansion<double>::precision<3>() = eps^(1/4))
+#define LEG_TAYLOR_EPS 1.220703125e-4
+// w = log3(R): rotation vector of R (row-major), theta = |w|.  Pinocchio's log3: small-angle series below, the
+// symmetric-part formula near pi (where the antisymmetric part of R vanishes).
+LEG_HD void so3_log(const double R[9], double w[3], double& theta) {
+    const double tr = R[0] + R[4] + R[8];
+    double c = 0.5 * (tr - 1.0);
+    c = c > 1.0 ? 1.0 : (c < -1.0 ? -1.0 : c);
+    const double ax = R[7] - R[5], ay = R[2] - R[6], az = R[3] - R[1];   // 2 sin(theta) * axis
+    const double s2 = sqrt(ax * ax + ay * ay + az * az);                   // 2 sin(theta)
+    theta = atan2(0.5 * s2, c);
+    if (theta < LEG_TAYLOR_EPS) {
+        const double k = 0.5 * (1.0 + theta * theta / 6.0);
+        w[0] = k * ax; w[1] = k * ay; w[2] = k * az;
+    } else if (3.14159265358979323846 - theta > 1e-4) {
+        const double k = theta / s2;
+        w[0] = k * ax; w[1] = k * ay; w[2] = k * az;
+    } else {
+        // near pi: axis from the diagonal of (R + I)/2 = cos^2(theta/2) ... a a' (1 - c) + c I, signs from the antisymmetric part
+        const double d = 1.0 / (1.0 - c);
+        double x = sqrt(fmax((R[0] - c) * d, 0.0)), y = sqrt(fmax((R[4] - c) * d, 0.0)), zz = sqrt(fmax((R[8] - c) * d, 0.0));
+        if (ax < 0.0) x = -x;
+        if (ay < 0.0) y = -y;
+        if (az < 0.0) zz = -zz;
+        w[0] = theta * x; w[1] = theta * y; w[2] = theta * zz;
+    }
+}
+
+// log6 of the placement (R, p): [v; w] with w = log3(R) and v = alpha p - w x p / 2 + beta (w.p) w  (Pinocchio log6)
+LEG_HD void se3_log(const double R[9], const double p[3], double out[6]) {
+    double w[3], t;
+    so3_log(R, w, t);
+    double alpha, beta;
+    const double t2 = t * t;
+    if (t < LEG_TAYLOR_EPS) { alpha = 1.0 - t2 / 12.0 - t2 * t2 / 720.0; beta = 1.0 / 12.0 + t2 / 720.0; }
+    else {
+        double st, ct;
+        sincos(t, &st, &ct);
+        alpha = t * st / (2.0 * (1.0 - ct));
+        beta = 1.0 / t2 - st / (2.0 * t * (1.0 - ct));
+    }
+    double wxp[3];
+    cross3(w, p, wxp);
+    const double wp = w[0] * p[0] + w[1] * p[1] + w[2] * p[2];
+    for (int i = 0; i < 3; ++i) { out[i] = alpha * p[i] - 0.5 * wxp[i] + beta * wp * w[i]; out[3 + i] = w[i]; }
+}
+
+// Jlog3(theta, w): A = alpha w w' + diag + skew(w / 2)
+LEG_HD void so3_jlog(double t, const double w[3], double A[9]) {
+    double alpha, diag;
+    const double t2 = t * t;
+    if (t < LEG_TAYLOR_EPS) { alpha = 1.0 / 12.0 + t2 / 720.0; diag = 0.5 * (2.0 - t2 / 6.0); }
+    else {
+        double st, ct;
+        sincos(t, &st, &ct);
+        const double st_1mct = st / (1.0 - ct);
+        alpha = 1.0 / t2 - st_1mct / (2.0 * t);
+        diag = 0.5 * (t * st_1mct);
+    }
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) A[i * 3 + j] = alpha * w[i] * w[j];
+    A[0] += diag; A[4] += diag; A[8] += diag;
+    A[1] -= 0.5 * w[2]; A[2] += 0.5 * w[1];
+    A[3] += 0.5 * w[2]; A[5] -= 0.5 * w[0];
+    A[6] -= 0.5 * w[1]; A[7] += 0.5 * w[0];
+}
+
+// Jlog6 of the placement (R, p), 6 x 6 row-major, blocks [[A, B], [0, A]] (Pinocchio Jlog6)
+LEG_HD void se3_jlog(const double R[9], const double p[3], double Jl[36]) {
+    double w[3], t, A[9], C[9], B[9];
+    so3_log(R, w, t);
+    so3_jlog(t, w, A);
+    const double t2 = t * t;
+    double beta, bdot;
+    if (t < LEG_TAYLOR_EPS) { beta = 1.0 / 12.0 + t2 / 720.0; bdot = 1.0 / 360.0; }
+    else {
+        double st, ct;
+        sincos(t, &st, &ct);
+        const double tinv = 1.0 / t, t2inv = tinv * tinv, i22 = 1.0 / (2.0 * (1.0 - ct));
+        beta = t2inv - st * tinv * i22;
+        bdot = -2.0 * t2inv * t2inv + (1.0 + st * tinv) * t2inv * i22;
+    }
+    const double wp = w[0] * p[0] + w[1] * p[1] + w[2] * p[2];
+    double v3[3];
+    for (int i = 0; i < 3; ++i) v3[i] = (bdot * wp) * w[i] - (t2 * bdot + 2.0 * beta) * p[i];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) C[i * 3 + j] = v3[i] * w[j] + beta * w[i] * p[j];
+    C[0] += wp * beta; C[4] += wp * beta; C[8] += wp * beta;
+    C[1] -= 0.5 * p[2]; C[2] += 0.5 * p[1];
+    C[3] += 0.5 * p[2]; C[5] -= 0.5 * p[0];
+    C[6] -= 0.5 * p[1]; C[7] += 0.5 * p[0];
+    mat3_mul(C, A, B);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            Jl[i * 6 + j] = A[i * 3 + j];
+            Jl[i * 6 + 3 + j] = B[i * 3 + j];
+            Jl[(3 + i) * 6 + j] = 0.0;
+            Jl[(3 + i) * 6 + 3 + j] = A[i * 3 + j];
+        }
+}
+
+// x = S^-1 b for a symmetric positive definite 6 x 6 S (LDL' without pivoting; the reference calls Eigen's ldlt())
+LEG_HD void solve_spd6(double S[36], const double b[6], double x[6]) {
+    double d[6];
+    for (int j = 0; j < 6; ++j) {
+        double v = S[j * 6 + j];
+        for (int k = 0; k < j; ++k) v -= S[j * 6 + k] * S[j * 6 + k] * d[k];
+        d[j] = v;
+        for (int i = j + 1; i < 6; ++i) {
+            double l = S[i * 6 + j];
+            for (int k = 0; k < j; ++k) l -= S[i * 6 + k] * S[j * 6 + k] * d[k];
+            S[i * 6 + j] = l / v;
+        }
+    }
+    double y[6];
+    for (int i = 0; i < 6; ++i) { double v = b[i]; for (int k = 0; k < i; ++k) v -= S[i * 6 + k] * y[k]; y[i] = v; }
+    for (int i = 0; i < 6; ++i) y[i] /= d[i];
+    for (int i = 5; i >= 0; --i) { double v = y[i]; for (int k = i + 1; k < 6; ++k) v -= S[k * 6 + i] * x[k]; x[i] = v; }
+}
+
+// The reference's inverseKinematics as written (include/pinocchio_kinematics.h:92-132) for the chain of one leg (the
+// other leg's joints have zero Jacobian columns for this frame, so their velocity is exactly zero and they drop out).
+LEG_HD int leg_ik6(const LegModel& M, const SwingParams& P, int leg, const double base_pos[3], const double Rb[9],
+                   const double target[3], double q[3], double& err_out) {
+    int it = 0;
+    double en = 0.0;
+    for (; it < P.ik_max_iter; ++it) {
+        double p[3], Rf[9], J6[18], Ri[9], pi[3], err[6];
+        leg_frame_world(M, leg, base_pos, Rb, q, p, Rf, J6);
+        // iMd = oMf^-1 oMdes, oMdes = (I, target): rotation Rf', translation Rf' (target - p)      (:104)
+        const double d[3] = {target[0] - p[0], target[1] - p[1], target[2] - p[2]};
+        for (int i = 0; i < 3; ++i) {
+            for (int j = 0; j < 3; ++j) Ri[i * 3 + j] = Rf[j * 3 + i];
+            pi[i] = Rf[0 * 3 + i] * d[0] + Rf[1 * 3 + i] * d[1] + Rf[2 * 3 + i] * d[2];
+        }
+        se3_log(Ri, pi, err);                                                                          // (:105)
+        en = 0.0;
+        for (int i = 0; i < 6; ++i) en += err[i] * err[i];
+        en = sqrt(en);
+        if (en < P.ik_tol) break;                                                                      // (:108-111)
+        // J = -Jlog6(iMd^-1) J_frame   (:113-116); iMd^-1 = (Rf, -Rf pi) = (Rf, -(target - p))
+        double Jl[36], Jt[18], JJt[36], y[6];
+        const double pinv[3] = {-d[0], -d[1], -d[2]};
+        se3_jlog(Rf, pinv, Jl);
+        for (int i = 0; i < 6; ++i)
+            for (int k = 0; k < 3; ++k) {
+                double v = 0.0;
+                for (int m2 = 0; m2 < 6; ++m2) v += Jl[i * 6 + m2] * J6[m2 * 3 + k];
+                Jt[i * 3 + k] = -v;
+            }
+        for (int i = 0; i < 6; ++i)
+            for (int j = 0; j < 6; ++j) JJt[i * 6 + j] = Jt[i * 3] * Jt[j * 3] + Jt[i * 3 + 1] * Jt[j * 3 + 1] + Jt[i * 3 + 2] * Jt[j * 3 + 2];
+        for (int i = 0; i < 6; ++i) JJt[i * 6 + i] += P.ik_damp;                                         // (:118-120)
+        solve_spd6(JJt, err, y);
+        for (int k = 0; k < 3; ++k) {                                                                    // (:122-124)
+            double v = 0.0;
+            for (int i = 0; i < 6; ++i) v += Jt[i * 3 + k] * y[i];
+            q[k] += -v * P.ik_dt;
+        }
+    }
+    err_out = en;
+    return it;
+}
+
+LEG_HD int leg_ik_task(const LegModel& M, const SwingParams& P, int leg, const double base_pos[3], const double Rb[9],
+                       const double target[3], double q[3], double& err_out) {
+    return P.ik_mode == 1 ? leg_ik6(M, P, leg, base_pos, Rb, target, q, err_out)
+                          : leg_ik(M, P, leg, base_pos, Rb, target, q, err_out);
 }
 
 // Joint torques that realise the ground-reaction force f (world frame, acting ON the foot) of a stance leg:

@@ -33,6 +33,26 @@ int main(int argc, char** argv) {
         printf("gait250 fk_feet %.17g %.17g %.17g %.17g %.17g %.17g\n", fk[0], fk[1], fk[2], fk[3], fk[4], fk[5]);
         printf("gait250 swing_next %.17g %.17g %.17g cmd_q %.9g %.9g %.9g %.9g %.9g %.9g ik_err %.6g ik_iters %d\n", nf[0], nf[1], nf[2],
                cmd.q[0], cmd.q[1], cmd.q[2], cmd.q[3], cmd.q[4], cmd.q[5], mpc.ikError(), mpc.ikIterations());
+        {   // the reference's own call shape: PinocchioKinematics + mpcQP(state, pos, vel, rpy, omega, quat, kin, leg)
+            PinocchioKinematics kin;
+            Vector4d quat;   // [x, y, z, w] identity
+            Vector3d pos(0.0, 0.0, 0.655), vel(0.2, 0.0, 0.0), rpy(0.0, 0.0, 0.0), om(0.0, 0.0, 0.0);
+            mpcQP qp(st, pos, vel, rpy, om, quat, kin, /*left_leg_state=*/0);
+            auto u = qp.optimalForce();
+            Vector3d fl = kin.getLinkPosition("contact_L_Link"), fr = kin.getLinkPosition("contact_R_Link");
+            printf("mpcQP_ctor feet %.12g %.12g %.12g %.12g %.12g %.12g u %.12g %.12g %.12g %.12g %.12g %.12g certified %d\n",
+                   fl(0), fl(1), fl(2), fr(0), fr(1), fr(2), u[0], u[1], u[2], u[3], u[4], u[5], (int)(qp.lastStatus() == 0));
+            VectorXd q0(6);
+            for (int i = 0; i < 6; ++i) q0(i) = st.q[i];
+            Vector3d target(fl(0) + 0.02, fl(1) - 0.01, fl(2) + 0.03);
+            for (int mode = 0; mode < 2; ++mode) {
+                kin.ik_params.ik_mode = mode;
+                VectorXd qi = kin.inverseKinematics("contact_L_Link", target, q0);
+                printf("ik_mode%d q %.12g %.12g %.12g err %.9g iters %d\n", mode, qi(0), qi(1), qi(2), kin.lastIkError(), kin.lastIkIterations());
+            }
+            Vector3d none = kin.getLinkPosition("no_such_link");
+            printf("missing_frame %.1f %.1f %.1f\n", none(0), none(1), none(2));
+        }
         st.q = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         mpc.enable_leg_pipeline = false;   // the latency figure below is the force MPC alone (BASELINE config 1b)
         // the Kalman state estimator as the controller's state source: a robot standing still on both feet

@@ -14,12 +14,11 @@
 
 #include "../../include/mpc_b200.h"
 #include "QPSolver.h"
+#include "limxsdk_stub.h"
+#include "pinocchio_kinematics.h"
 
 namespace mpcb200 {
 namespace host {
-
-struct Vector3d { double v[3] = {0, 0, 0}; double& operator()(int i) { return v[i]; } double operator()(int i) const { return v[i]; } };
-struct Vector4d { double v[4] = {0, 0, 0, 1}; double& operator()(int i) { return v[i]; } double operator()(int i) const { return v[i]; } };
 
 class mpcQP {
 public:
@@ -35,8 +34,29 @@ public:
         contact.assign((size_t)2 * N, 1);
         U_opt.assign((size_t)6 * N, 0.0);
     }
-    // reference-shaped constructor (include/mpcQP.h:10): state + kinematics inputs; `leg` is
-    // left_leg_state (0 = left foot is the support foot, include/mpcQP.h:133-137); feet are the FK results
+    // THE REFERENCE'S CONSTRUCTOR (include/mpcQP.h:10,35-119), same argument list: joint state, base position / velocity /
+    // rpy / angular velocity / quaternion, the kinematics object and `leg` = left_leg_state (0 = the left foot is the
+    // support foot, :133-137).  As there: sets the base pose on the kinematics object, runs forward kinematics at state.q,
+    // reads contact_L_Link / contact_R_Link (:125-137), builds x0 and the reference trajectory (:66-97, omega_yaw 0.1,
+    // velocity_x 0.5), solves; u = U_opt.col(0) (:118) is then available from optimalForce().
+    // The quaternion is read as the estimator stores it, [x, y, z, w] (include/state_estimator_fake.h:22).
+    mpcQP(const limxsdk::RobotState& state, const Vector3d& currentPosition, const Vector3d& currentVelocity,
+          const Vector3d& currentOrientation, const Vector3d& currentAngularVelocity, const Vector4d& currentQuat,
+          PinocchioKinematics& kinematics, int leg, int horizon = 10, int device = 0)
+        : mpcQP(horizon, 1, device) {
+        kinematics.setBaseLinkPose(currentPosition, Quaterniond(currentQuat(3), currentQuat(0), currentQuat(1), currentQuat(2)));
+        VectorXd jointPositions((int)state.q.size());
+        for (int i = 0; i < (int)state.q.size(); ++i) jointPositions(i) = (double)state.q[i];
+        kinematics.forwardKinematics(jointPositions);
+        setState(currentPosition, currentVelocity, currentOrientation, currentAngularVelocity);
+        setFootPositions(kinematics.getLinkPosition("contact_L_Link"), kinematics.getLinkPosition("contact_R_Link"));
+        setReference(0.1, 0.5);
+        std::vector<uint8_t> c((size_t)2 * N);
+        for (int k = 0; k < N; ++k) { c[2 * k] = (leg == 0); c[2 * k + 1] = (leg != 0); }
+        setContactSchedule(c);
+        solve();
+    }
+    // the same with the feet given directly (no kinematics object)
     mpcQP(const Vector3d& currentPosition, const Vector3d& currentVelocity, const Vector3d& currentOrientation,
           const Vector3d& currentAngularVelocity, const Vector3d& leftFoot, const Vector3d& rightFoot, int leg,
           int horizon = 10, int device = 0)

@@ -58,6 +58,23 @@ class LegKinematics:
                                                             _ptr(err), _ptr(its), self._stream()))
         return dict(feet=feet, next_foot=nxt, swing_leg=leg, ik_err=err, ik_iters=its)
 
+    def ik(self, base_pos, base_quat, leg, target, q_init):
+        """PinocchioKinematics::inverseKinematics for a batch: leg [B] int32 (0 left, 1 right), target [B,3] world position
+        of the contact point, q_init [B,6] -> (q_out [B,6], ik_err [B], ik_iters [B]).  self.swing.ik_mode selects the
+        position task (0) or the reference's 6-D log6 task as written (1)."""
+        B = q_init.shape[0]
+        for t, n, nm in ((base_pos, 3, "base_pos"), (base_quat, 4, "base_quat"), (target, 3, "target"), (q_init, 6, "q_init")):
+            self._chk(t, torch.float64, n * B, nm)
+        self._chk(leg, torch.int32, B, "leg")
+        q_out = torch.empty((B, 6), dtype=torch.float64, device=self.tdev)
+        err = torch.empty(B, dtype=torch.float64, device=self.tdev)
+        its = torch.empty(B, dtype=torch.int32, device=self.tdev)
+        with torch.cuda.device(self.tdev):
+            _capi.check(self.lib.mpc_b200_leg_ik_device(C.byref(self.model), C.byref(self.swing), B, _ptr(base_pos), _ptr(base_quat),
+                                                        _ptr(leg), _ptr(target), _ptr(q_init), _ptr(q_out), _ptr(err), _ptr(its),
+                                                        self._stream()))
+        return q_out, err, its
+
     def grf_to_torque(self, base_quat, q, u0, tau=None):
         """tau [B,6] = -J(q)' f per leg from the first-step forces u0 [B,6]."""
         B = q.shape[0]

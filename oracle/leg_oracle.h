@@ -37,6 +37,7 @@ typedef struct orc_swing_params {
     double foot_offset_left[3], foot_offset_right[3];
     double ik_tol, ik_dt, ik_damp;
     int32_t ik_max_iter;
+    int32_t ik_mode;   /* 0 position task, 1 the reference's 6-D log6 task (include/pinocchio_kinematics.h:92-132) */
 } orc_swing_params;
 
 void orc_leg_defaults(orc_leg_model *m, orc_swing_params *p);
@@ -48,6 +49,16 @@ void orc_foot_placement(const orc_swing_params *p, const double pos[3], const do
 void orc_swing_next(const orc_swing_params *p, const double foot[3], const double fin[3], double remain, double nxt[3]);
 int orc_leg_ik(const orc_leg_model *m, const orc_swing_params *p, int leg, const double base_pos[3], const double quat[4],
                const double target[3], double q[3], double *err);
+/* The reference's 6-D task as written (include/pinocchio_kinematics.h:92-132): err = log6(oMf^-1 oMdes), oMdes = (I, target);
+ * J = -Jlog6(iMd^-1) J_frame; v = -J' (J J' + damp I)^-1 err; q += v DT.  log6 / Jlog6 are computed here by routes that share
+ * nothing with the product's closed forms: the rotation vector through a quaternion, the translation part by solving with
+ * the SO(3) left-Jacobian matrix, and Jlog6 as the INVERSE of the SE(3) right Jacobian summed as a power series of ad(xi). */
+int orc_leg_ik6(const orc_leg_model *m, const orc_swing_params *p, int leg, const double base_pos[3], const double quat[4],
+                const double target[3], double q[3], double *err);
+/* xi[6] = [v; w] = log6 of the placement with rotation R (row-major 3x3) and translation t */
+void orc_se3_log(const double R[9], const double t[3], double xi[6]);
+/* Jl (6x6 row-major) = Jlog6 of the same placement */
+void orc_se3_jlog(const double R[9], const double t[3], double Jl[36]);
 /* whole swing-leg step of MPC::run for one robot; q_cmd[6] in/out; returns the swing leg (0 left, 1 right) */
 int orc_swing_step(const orc_leg_model *m, const orc_swing_params *p, const double pos[3], const double quat[4],
                    const double q[6], const double des_v[3], int iter, double q_cmd[6], double feet[6], double next_foot[3],

@@ -19,6 +19,7 @@ static SwingParams to_swing(const mpc_b200_swing_params* p) {
     S.p_rel_max = p->p_rel_max;
     for (int i = 0; i < 3; ++i) { S.foot_off_l[i] = p->foot_offset_left[i]; S.foot_off_r[i] = p->foot_offset_right[i]; }
     S.ik_tol = p->ik_tol; S.ik_dt = p->ik_dt; S.ik_damp = p->ik_damp; S.ik_max_iter = p->ik_max_iter;
+    S.ik_mode = p->ik_mode;
     return S;
 }
 
@@ -44,7 +45,7 @@ int emul_swing_step(const mpc_b200_leg_model* m, const mpc_b200_swing_params* p,
     foot_placement(P, pos, des_vel, remain, ls, fin);
     swing_next_position(P, ft + 3 * leg, fin, remain, nxt);
     for (int k = 0; k < 3; ++k) qv[k] = q[3 * leg + k];
-    const int its = leg_ik(M, P, leg, pos, Rb, nxt, qv, err);
+    const int its = leg_ik_task(M, P, leg, pos, Rb, nxt, qv, err);
     for (int k = 0; k < 3; ++k) q_cmd[3 * leg + k] = qv[k];
     if (feet) memcpy(feet, ft, sizeof(ft));
     if (next_foot) memcpy(next_foot, nxt, sizeof(nxt));
@@ -52,6 +53,19 @@ int emul_swing_step(const mpc_b200_leg_model* m, const mpc_b200_swing_params* p,
     if (ik_iters) *ik_iters = its;
     return leg;
 }
+
+int emul_leg_ik(const mpc_b200_leg_model* m, const mpc_b200_swing_params* p, int leg, const double* pos, const double* quat,
+                const double* target, double* q3, double* err) {
+    LegModel M = to_model(m);
+    SwingParams P = to_swing(p);
+    double Rb[9], e = 0.0;
+    quat_to_rot(quat, Rb);
+    const int its = leg_ik_task(M, P, leg, pos, Rb, target, q3, e);
+    if (err) *err = e;
+    return its;
+}
+void emul_se3_log(const double* R, const double* t, double* xi) { se3_log(R, t, xi); }
+void emul_se3_jlog(const double* R, const double* t, double* Jl) { se3_jlog(R, t, Jl); }
 
 void emul_grf_to_torque(const mpc_b200_leg_model* m, const double* quat, const double* q, const double* u0, double* tau) {
     LegModel M = to_model(m);

@@ -171,6 +171,29 @@ def swing_step(m, sp, pos, quat, q6, des_v, it, q_cmd):
     return dict(leg=leg, q_cmd=q_cmd, feet=feet.reshape(2, 3), next_foot=nxt, ik_err=err.value, ik_iters=its.value)
 
 
+def leg_ik(m, sp, leg, pos, quat, target, q3):
+    a = lambda x: np.ascontiguousarray(x, np.float64)
+    pos, quat, target = a(pos), a(quat), a(target)
+    q = a(q3).copy(); err = C.c_double()
+    its = leg_lib().emul_leg_ik(C.byref(m), C.byref(sp), int(leg), pos.ctypes.data_as(_dp), quat.ctypes.data_as(_dp),
+                                target.ctypes.data_as(_dp), q.ctypes.data_as(_dp), C.byref(err))
+    return q, err.value, its
+
+
+def se3_log(R, t):
+    a = lambda x: np.ascontiguousarray(x, np.float64)
+    R, t = a(R), a(t); xi = np.zeros(6)
+    leg_lib().emul_se3_log(R.ctypes.data_as(_dp), t.ctypes.data_as(_dp), xi.ctypes.data_as(_dp))
+    return xi
+
+
+def se3_jlog(R, t):
+    a = lambda x: np.ascontiguousarray(x, np.float64)
+    R, t = a(R), a(t); J = np.zeros((6, 6))
+    leg_lib().emul_se3_jlog(R.ctypes.data_as(_dp), t.ctypes.data_as(_dp), J.ctypes.data_as(_dp))
+    return J
+
+
 def grf_to_torque(m, quat, q6, u0):
     a = lambda x: np.ascontiguousarray(x, np.float64)
     quat, q6, u0 = a(quat), a(q6), a(u0)

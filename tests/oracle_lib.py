@@ -211,7 +211,8 @@ class LegModel(C.Structure):
 class SwingParams(C.Structure):
     _fields_ = [("dt", C.c_float), ("swing_time", C.c_float), ("stance_time", C.c_float), ("gait_height", C.c_float),
                 ("p_rel_max", C.c_double), ("foot_offset_left", C.c_double * 3), ("foot_offset_right", C.c_double * 3),
-                ("ik_tol", C.c_double), ("ik_dt", C.c_double), ("ik_damp", C.c_double), ("ik_max_iter", C.c_int32)]
+                ("ik_tol", C.c_double), ("ik_dt", C.c_double), ("ik_damp", C.c_double), ("ik_max_iter", C.c_int32),
+                ("ik_mode", C.c_int32)]
 
 
 def leg_defaults():
@@ -237,6 +238,27 @@ def swing_step(m, sp, pos, quat, q6, des_v, it, q_cmd):
     leg = lib().orc_swing_step(C.byref(m), C.byref(sp), _p(pos), _p(quat), _p(q6), _p(des_v), int(it), _p(q_cmd), _p(feet), _p(nxt),
                                C.byref(err), C.byref(its))
     return dict(leg=leg, q_cmd=q_cmd, feet=feet.reshape(2, 3), next_foot=nxt, ik_err=err.value, ik_iters=its.value)
+
+
+def leg_ik(m, sp, leg, pos, quat, target, q3):
+    """position task (ik_mode 0) or the reference's 6-D task (ik_mode 1); returns (q3, err, iters)"""
+    pos, quat, target = _v(pos), _v(quat), _v(target)
+    q = _v(q3).copy(); err = C.c_double()
+    fn = lib().orc_leg_ik6 if sp.ik_mode == 1 else lib().orc_leg_ik
+    its = fn(C.byref(m), C.byref(sp), int(leg), _p(pos), _p(quat), _p(target), _p(q), C.byref(err))
+    return q, err.value, its
+
+
+def se3_log(R, t):
+    R, t = _v(R), _v(t); xi = np.zeros(6)
+    lib().orc_se3_log(_p(R), _p(t), _p(xi))
+    return xi
+
+
+def se3_jlog(R, t):
+    R, t = _v(R), _v(t); J = np.zeros((6, 6))
+    lib().orc_se3_jlog(_p(R), _p(t), _p(J))
+    return J
 
 
 def grf_to_torque(m, quat, q6, u0):

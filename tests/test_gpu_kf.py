@@ -46,8 +46,8 @@ def test_filter_runs_vs_oracle(torch_cuda):
             assert np.abs(Pg[b] - Po[b]).max() < 1e-9 * max(1.0, np.abs(Po[b]).max()), (step, b)
             assert np.abs(og[b] - od).max() < 1e-9 * max(1.0, np.abs(od).max())
         assert np.array_equal(Pg, Pg.transpose(0, 2, 1))
-        # re-synchronise the oracle state with the device state: one-step comparison
-        xo[:] = xg; Po[:] = Pg
+    # FREE-RUNNING: the oracle filter and the device filter each carried their own state through all 60 updates (nothing
+    # was re-synchronised), so the 1e-9 bound above is a bound on the accumulated drift, not on a single step
 
 
 def test_host_variant_and_errors(torch_cuda):

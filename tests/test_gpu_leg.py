@@ -163,3 +163,43 @@ def test_full_control_step_pipeline(torch_cuda):
         assert u0n[b, 3 * (1 - int(legn[b])) + 2] > 0.0                                      # the stance foot pushes up
         assert np.abs(taun[b] - O.grf_to_torque(mo, quat[b], q[b], u0n[b])).max() < 1e-10
     eng.close()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_inverse_kinematics_both_tasks(torch_cuda, mode):
+    """mpc_b200_leg_ik_device: the position task and the reference's 6-D log6 task as written
+    (include/pinocchio_kinematics.h:61-149), every robot of the batch against the oracle; host variant identical."""
+    torch = torch_cuda
+    from mpc_limx_control_b200 import _capi
+    from mpc_limx_control_b200.leg import LegKinematics, default_swing
+    mo, po = O.leg_defaults()
+    po.ik_mode = mode
+    sw = default_swing(); sw.ik_mode = mode
+    B = 300
+    pos, quat, q, _, _ = batch(77 + mode, B)
+    rng = np.random.default_rng(3)
+    leg = rng.integers(0, 2, B).astype(np.int32)
+    lk = LegKinematics(swing=sw)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    feet = lk.fk(t(pos), t(quat), t(q)).cpu().numpy()
+    target = feet[np.arange(B), leg] + rng.uniform(-0.04, 0.04, (B, 3))
+    q_out, err, its = lk.ik(t(pos), t(quat), t(leg), t(target), t(q))
+    q_out, err, its = q_out.cpu().numpy(), err.cpu().numpy(), its.cpu().numpy()
+    for b in range(B):
+        l = int(leg[b])
+        qo, eo, io = O.leg_ik(mo, po, l, pos[b], quat[b], target[b], q[b, 3 * l:3 * l + 3])
+        assert io == its[b]
+        assert np.abs(q_out[b, 3 * l:3 * l + 3] - qo).max() < 1e-8
+        assert np.array_equal(q_out[b, 3 * (1 - l):3 * (1 - l) + 3], q[b, 3 * (1 - l):3 * (1 - l) + 3])   # other leg untouched
+        assert abs(err[b] - eo) < 1e-8 * max(1.0, eo)
+    if mode == 0:
+        # ten steps of DT = 0.1 shrink a position error by about 0.9^10 = 0.35 (the reference's constants): it has moved
+        d0 = np.linalg.norm(target - feet[np.arange(B), leg], axis=1)
+        assert (err < d0).all()
+    # host variant: bit-identical
+    L = _capi.lib()
+    qh = np.zeros((B, 6)); eh = np.zeros(B); ih = np.zeros(B, np.int32)
+    p = lambda a: C.c_void_p(a.ctypes.data)
+    pos_c, quat_c, q_c, tg_c = (np.ascontiguousarray(a) for a in (pos, quat, q, target))
+    assert L.mpc_b200_leg_ik_host(0, C.byref(lk.model), C.byref(sw), B, p(pos_c), p(quat_c), p(leg), p(tg_c), p(q_c), p(qh), p(eh), p(ih)) == 0
+    assert np.array_equal(qh, q_out) and np.array_equal(ih, its)

@@ -127,11 +127,32 @@ def test_facade_tron1_single_binary(golden):
     assert np.abs(tau - O.grf_to_torque(mo, quat, q, fg)).max() < 1e-9 and np.all(tau[:3] == 0.0) and np.abs(tau[3:]).max() > 0.1
     # the Kalman estimator shim (host/stateEstimator.h) standing still: height = leg length + foot radius, zero velocity,
     # and the controller driven by it produces a certified, upward, near-symmetric standing force
-    est = lines[5].split()
-    assert lines[5].startswith("estimator pos")
+    by = lambda pre: next(l for l in lines if l.startswith(pre))
+    # the reference's own call shape: PinocchioKinematics shim + mpcQP(state, pos, vel, rpy, omega, quat, kin, leg)
+    # (include/mpcQP.h:10,35-119; include/pinocchio_kinematics.h:30-43,61-149,153-157)
+    mc = by("mpcQP_ctor").split()
+    pos2 = np.array([0.0, 0.0, 0.655])
+    feet_c = np.array([float(x) for x in mc[2:8]]); u_c = np.array([float(x) for x in mc[9:15]])
+    fk_ref = np.concatenate([O.leg_fk(mo, l, pos2, quat, q[3 * l:3 * l + 3], want_jac=False) for l in (0, 1)])
+    assert np.abs(feet_c - fk_ref).max() < 1e-11 and mc[-1] == "1"
+    x0 = np.array([0, 0, 0, 0, 0, 0.655, 0, 0, 0, 0.2, 0, 0, -9.8])
+    pt = O.tron1_defaults(Ts=0.005)
+    xr = O.tron1_reference(x0, 10, 0.005, 0.1, 0.5).T.copy()
+    contact = np.tile(np.array([1, 0], np.uint8), (10, 1))           # leg = 0: the left foot is the support foot
+    Fo, so, _ = O.tron1_solve_batch(pt, 10, x0[None], xr[None], fk_ref.reshape(1, 2, 3), contact[None], nthreads=1)
+    assert so[0] == 0 and np.abs(u_c - Fo[0, 0]).max() < 1e-4 * max(1.0, np.abs(Fo[0, 0]).max()) and np.all(u_c[3:] == 0.0)
+    target = fk_ref[:3] + np.array([0.02, -0.01, 0.03])
+    for mode in (0, 1):
+        ik = by(f"ik_mode{mode}").split()
+        po.ik_mode = mode
+        qo, eo, io = O.leg_ik(mo, po, 0, pos2, quat, target, q[:3])
+        assert np.abs(np.array([float(x) for x in ik[2:5]]) - qo).max() < 1e-8 and int(ik[-1]) == io and abs(float(ik[6]) - eo) < 1e-8
+    po.ik_mode = 0
+    assert by("missing_frame").split()[1:] == ["0.0", "0.0", "0.0"]
+    est = by("estimator pos").split()
     feet0 = O.leg_fk(mo, 0, [0, 0, 0], quat, q[:3], want_jac=False)
     assert abs(float(est[4]) - (-feet0[2] + 0.02)) < 2e-3 and max(abs(float(v)) for v in est[6:9]) < 1e-3
     assert abs(float(est[12])) < 2e-3          # left foot on the ground plane
-    ef = lines[6].split()
-    assert lines[6].startswith("estimator-driven forces") and ef[-1] == "1" and float(ef[4]) > 1.0 and float(ef[7]) > 1.0
-    assert lines[7].startswith("latency_us")
+    ef = by("estimator-driven forces").split()
+    assert ef[-1] == "1" and float(ef[4]) > 1.0 and float(ef[7]) > 1.0
+    assert by("latency_us")

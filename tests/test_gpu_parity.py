@@ -614,3 +614,34 @@ def test_staged_host_path_horizon50_large_class_matches_device(torch_cuda):
         assert (np.asarray(sh) == 0).all()
         assert np.array_equal(np.asarray(Fh), F.cpu().numpy())
     eng.close()
+
+
+@pytest.mark.parametrize("N,B,standing_every", [(20, 1536, 5), (50, 296, 4)])
+def test_every_instance_vs_oracle_horizons_20_50(torch_cuda, N, B, standing_every):
+    """EVERY instance of one horizon-20 and one horizon-50 batch (trot + some standing robots: both capacity classes,
+    horizon 50 = the tiled tensor-core Cholesky in shared memory AND in global slabs) against the oracle's active-set
+    solution and the oracle's dense H, f -- no stride."""
+    torch = torch_cuda
+    Ts = 0.005
+    d = synth.tron1_batch(4242 + N, B, N, Ts)
+    d["iter"][::standing_every] = -1
+    d["x0"][:, [0, 1, 6, 7, 8, 9, 10, 11]] *= 2.0          # some instances leave the interior face
+    eng = make_engine(N, B, Ts=Ts, mu=0.4)
+    t = to_dev(torch, d)
+    F, st, it = eng.solve(t["x0"], t["x_ref"], t["feet"], it=t["iter"])
+    torch.cuda.synchronize()
+    F, st, it = F.cpu().numpy(), st.cpu().numpy(), it.cpu().numpy()
+    assert (st == 0).all()
+    po = O.tron1_defaults(Ts=Ts, mu=0.4)
+    c_ref = np.stack([O.contact_schedule(int(i), N) for i in d["iter"]])
+    Fo, so, _ = O.tron1_solve_batch(po, N, d["x0"], d["x_ref"], d["feet"], c_ref, nthreads=os.cpu_count() or 8)
+    assert (so == 0).all()
+    scale = np.maximum(1.0, np.abs(Fo).reshape(B, -1).max(1))
+    err = np.abs(F - Fo).reshape(B, -1).max(1) / scale
+    assert err.max() < 1e-4, (int(err.argmax()), float(err.max()))
+    assert np.all(F.reshape(B, N, 2, 3)[c_ref == 0] == 0.0)
+    assert it.max() > 1                                        # the batch does contain multi-iteration instances
+    for b in range(0, B, max(1, B // 24)):                     # KKT certificate on a sample (dense H is O(n^2 p) on the CPU)
+        c = O.tron1_condense(po, N, d["x0"][b], d["x_ref"][b], d["feet"][b], want_pred=False)
+        assert O.tron1_natural_residual(po, N, c["H"], c["f"], c_ref[b], F[b]) < 1e-6
+    eng.close()

@@ -172,3 +172,86 @@ def test_foot_placement_clamp_and_offsets():
     assert np.allclose(fin[:2], [1.0 + 0.6 + 0.3 + po.foot_offset_left[0], 2.0 - 0.6 - 0.3 + po.foot_offset_left[1]], atol=1e-15)
     O.lib().orc_foot_placement(C.byref(po), O._p(pos), O._p(v), C.c_double(0.2), 0, O._p(fin))
     assert np.allclose(fin[:2], [1.9 + po.foot_offset_right[0], 1.1 + po.foot_offset_right[1]], atol=1e-15)
+
+
+# ---- the reference's 6-D IK task as written (include/pinocchio_kinematics.h:61-149) -----------------------------------
+def _exp6(xi):
+    """SE(3) exponential by scipy's dense matrix exponential of the 4x4 twist (independent of oracle and product)."""
+    from scipy.linalg import expm
+    v, w = xi[:3], xi[3:]
+    X = np.zeros((4, 4))
+    X[:3, :3] = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]]); X[:3, 3] = v
+    T = expm(X)
+    return T[:3, :3], T[:3, 3]
+
+
+def test_log6_against_scipy_matrix_logarithm():
+    """log6 of Pinocchio = the se(3) matrix logarithm: [v; w] with logm(T) = [[w]x, v; 0, 0]"""
+    from scipy.linalg import logm
+    rng = np.random.default_rng(5)
+    for scale in (1e-9, 1e-3, 0.3, 1.5, 3.0):
+        for _ in range(6):
+            xi = rng.standard_normal(6); xi[3:] *= scale / np.linalg.norm(xi[3:])
+            R, t = _exp6(xi)
+            T = np.eye(4); T[:3, :3] = R; T[:3, 3] = t
+            Lg = np.real(logm(T))
+            want = np.array([Lg[0, 3], Lg[1, 3], Lg[2, 3], Lg[2, 1], Lg[0, 2], Lg[1, 0]])
+            tol = 1e-9 if scale < 3.0 else 1e-7
+            assert np.abs(O.se3_log(R, t) - want).max() < tol
+            assert np.abs(E.se3_log(R, t) - want).max() < tol
+            assert np.abs(E.se3_log(R, t) - xi).max() < tol          # log6(exp6(xi)) = xi below pi
+
+
+def test_jlog6_is_the_derivative_of_log6():
+    """Jlog6(M) xi = d/de log6(M exp6(e xi)) (Pinocchio's convention): central differences through scipy's expm; the
+    oracle forms it as the inverse of the right-Jacobian power series, the product by Pinocchio's closed form."""
+    rng = np.random.default_rng(6)
+    for scale in (1e-6, 0.2, 1.0, 2.5):
+        xi0 = rng.standard_normal(6); xi0[3:] *= scale / np.linalg.norm(xi0[3:])
+        R, t = _exp6(xi0)
+        Jo, Je = O.se3_jlog(R, t), E.se3_jlog(R, t)
+        assert np.abs(Jo - Je).max() < 1e-9 * max(1.0, np.abs(Jo).max())
+        h = 1e-6
+        for k in range(6):
+            d = np.zeros(6); d[k] = h
+            Rp, tp = _exp6(d); Rm, tm = _exp6(-d)
+            fp = O.se3_log(R @ Rp, R @ tp + t); fm = O.se3_log(R @ Rm, R @ tm + t)
+            assert np.abs((fp - fm) / (2 * h) - Jo[:, k]).max() < 2e-6
+
+
+def test_reference_literal_ik_product_vs_oracle():
+    """ik_mode = 1: the 6-D log6 task.  Same iterates from the product source and the oracle; the task asks a point foot
+    for the identity orientation, so it does NOT converge to the position target in general (that is the reference's
+    behaviour as written) -- checked: the error norm it reports includes the orientation part."""
+    mo, po = O.leg_defaults(); mp, pp = product_defaults()
+    po.ik_mode = 1; pp.ik_mode = 1
+    rng = np.random.default_rng(8)
+    for trial in range(40):
+        pos, quat, q = rand_state(rng)
+        if trial % 4 == 0:
+            pos = np.zeros(3); quat = np.array([0, 0, 0, 1.0])     # the reference's fixed-base model: base at the origin
+        leg = trial % 2
+        p0 = O.leg_fk(mo, leg, pos, quat, q[3 * leg:3 * leg + 3], want_jac=False)
+        target = p0 + rng.uniform(-0.05, 0.05, 3)
+        for iters in (1, 3, 10):
+            po.ik_max_iter = iters; pp.ik_max_iter = iters
+            qo, eo, io = O.leg_ik(mo, po, leg, pos, quat, target, q[3 * leg:3 * leg + 3])
+            qe, ee, ie = E.leg_ik(mp, pp, leg, pos, quat, target, q[3 * leg:3 * leg + 3])
+            assert io == ie
+            assert np.abs(qo - qe).max() < 1e-8 and abs(eo - ee) < 1e-8 * max(1.0, eo)
+        # one step moves the joints along -J' (JJ' + damp)^-1 err, scaled by DT = 0.1: small but non-zero
+        po.ik_max_iter = 1
+        q1, e1, _ = O.leg_ik(mo, po, leg, pos, quat, target, q[3 * leg:3 * leg + 3])
+        assert 0.0 < np.abs(q1 - q[3 * leg:3 * leg + 3]).max() < 1.0
+        # the reported error is the 6-D norm: at least the orientation error of the foot frame w.r.t. the identity
+        Rf = (Rotation.from_quat(quat / np.linalg.norm(quat)) *
+              Rotation.from_rotvec(np.array(mo.axis).reshape(2, 3, 3)[leg][0] * q[3 * leg]) *
+              Rotation.from_rotvec(np.array(mo.axis).reshape(2, 3, 3)[leg][1] * q[3 * leg + 1]) *
+              Rotation.from_rotvec(np.array(mo.axis).reshape(2, 3, 3)[leg][2] * q[3 * leg + 2]))
+        assert e1 >= Rf.magnitude() - 1e-9
+    # the swing step honours the switch too
+    pos, quat, q = rand_state(rng)
+    po.ik_max_iter = 10; pp.ik_max_iter = 10
+    r_o = O.swing_step(mo, po, pos, quat, q, [0.4, 0.1, 0.0], 1234, q)
+    r_e = E.swing_step(mp, pp, pos, quat, q, [0.4, 0.1, 0.0], 1234, q)
+    assert r_o["ik_iters"] == r_e["ik_iters"] and np.abs(r_o["q_cmd"] - r_e["q_cmd"]).max() < 1e-8

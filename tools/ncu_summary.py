@@ -37,7 +37,9 @@ KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 
 summary = {"tag": tag}
 if os.path.exists(rep):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # either an .ncu-rep or the `ncu -i <rep> --page raw --csv` export of one (the reports themselves are too large to
+    # bring back from the GPU box: tools/run_profile.sh exports the raw page there and deletes them)
+    raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     H = rows[0]
     kcol = H.index("Kernel Name")

@@ -19,4 +19,15 @@ for c in 2s 3 4; do
 done
 python bench.py --config 5 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/${T}_plain.log 2>&1 && \
 ncu --set full --clock-control none -k regex:tron1_rollout_kernel -s 2 -c 1 -o gpurun_out/${T}_prof_c5 -f python bench.py --config 5 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/${T}_ncu_c5.log 2>&1
-ls -la gpurun_out/*.ncu-rep
+# the reports are tens of MB each and gpurun_out/ is capped at 64 MiB: keep the raw-metric page (and the source page of the
+# two kernels under work) as CSV, drop the reports
+for f in gpurun_out/${T}_prof_*.ncu-rep; do
+  b=${f%.ncu-rep}
+  ncu -i $f --page raw --csv > $b.raw.csv 2>/dev/null
+done
+for c in c2 c4; do
+  ncu -i gpurun_out/${T}_prof_$c.ncu-rep --page source --csv > gpurun_out/${T}_prof_$c.source.csv 2>/dev/null
+  gzip -f gpurun_out/${T}_prof_$c.source.csv
+done
+ls -la gpurun_out/
+rm -f gpurun_out/*.ncu-rep gpurun_out/libmpc_b200_timing.so
