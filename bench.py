@@ -86,21 +86,25 @@ def structured_flops(N, nc, iters, group_threads):
       elimination, nc <= 60   : register Gauss-Jordan, EVERY lane of the group carries a row window:
                                 lanes x sum over the 5 stages of (nc/5) columns x (2 W + 10), W = window length
       factorisation, N = 50   : tiled Cholesky: 512 flops per DMMA.8x8x4 x (2 per trailing tile + 2 per panel tile
-                                + 2 per look-ahead tile) + 19 diagonal factors x ~600 x 32 lanes + blocked solves 2 nc^2
-    Checked against ncu's executed thread-level count for the headline kernel (profiles/r2_*: within 10 %)."""
+                                + 2 per look-ahead tile) [tensor pipe] + NT diagonal factors x ~300 x 32 lanes + blocked
+                                solves 2 nc^2 [FP64 pipe]
+    Returns (total, tensor_part).  Checked against ncu's executed thread-level DFMA/DMUL/DADD count (which excludes DMMA)
+    on the committed captures profiles/r2_c*: config 2 0.999, 2s 1.06, 3 1.01, 4 (non-tensor part) within 10 %."""
     m = nc / 3.0
     setup = 450.0 * N
     hess = 157.0 * m * (m + 1) / 2
     it_rest = 300.0 * N
+    tensor = 0.0
     if N == 50:
         NT = (int(nc) + 8) // 8
         tiles = sum(k * (k + 1) // 2 for k in range(1, NT))          # trailing tiles incl. look-ahead
         panel = NT * (NT - 1) // 2
-        elim = 512.0 * 2 * (tiles + panel) + NT * 600.0 * 32 + 2.0 * nc * nc
+        tensor = 512.0 * 2 * (tiles + panel)
+        elim = tensor + NT * 300.0 * 32 + 2.0 * nc * nc
     else:
         lanes = group_threads
         elim = lanes * sum((nc / 5.0) * (2 * (nc - s * nc / 5.0) + 10) for s in range(5))
-    return setup + iters * (hess + elim + it_rest)
+    return setup + iters * (hess + elim + it_rest), iters * tensor
 
 
 def algorithmic_bytes(N):
@@ -481,7 +485,7 @@ def run_gpu(args, cfg):
                  50: "tron1_solve_kernel<50,150,8,1,1,DIRECT,persistent> (tiled DMMA Cholesky)"}[N]
         if rollout:
             kname = "tron1_rollout_kernel<10,30,1,4,4>"
-    f_exec = structured_flops(N, nc, max(mean_iters, 1.0), gthreads)
+    f_exec, f_tensor = structured_flops(N, nc, max(mean_iters, 1.0), gthreads)
     f_dense = dense_equiv_flops(N, mean_iters)
     achieved_tf = f_exec * B / (kernel_ms * 1e-3) / 1e12
     hbm_peak = peaks["hbm_gbs"] if peaks else 6650.0
@@ -494,7 +498,8 @@ def run_gpu(args, cfg):
             traffic = ent.get("dram_bytes_per_launch")
             if ent.get("executed_fp64_flops_per_launch"):
                 ncu_exec = {"flops_per_solve": ent["executed_fp64_flops_per_launch"] / B, "source": ent.get("source"),
-                            "formula_over_ncu": f_exec / (ent["executed_fp64_flops_per_launch"] / B)}
+                            "counts": "thread-level DFMA x2 + DMUL + DADD (DMMA is not in these counters)",
+                            "formula_over_ncu": (f_exec - f_tensor) / (ent["executed_fp64_flops_per_launch"] / B)}
     except Exception:
         pass
 
@@ -528,7 +533,7 @@ def run_gpu(args, cfg):
                      "peak_source": "FP64 DFMA peak measured in this run by mpc_b200_measure_fp64_peak "
                                     "(MEASURED_PEAKS.json has no FP64 entry; DMMA.8x8x4 measures 37.1 TFLOP/s, "
                                     "tools/microbench/chol_dmma_bench.cu)",
-                     "flops_per_solve": f_exec, "kernel": kname, "kernel_ms": kernel_ms,
+                     "flops_per_solve": f_exec, "tensor_flops_per_solve": f_tensor, "kernel": kname, "kernel_ms": kernel_ms,
                      "what": "achieved = FP64 operations the kernel EXECUTES per solve (hand-counted structured formula, "
                              "bench.py:structured_flops, DESIGN.md section 4) x instances / CUDA-event time of the launch",
                      "ncu_check": ncu_exec,

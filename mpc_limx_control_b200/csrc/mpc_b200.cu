@@ -41,6 +41,10 @@ using namespace mpcb200;
 #ifndef MPC_N50_WPI_S
 #define MPC_N50_WPI_S 8      // warps per instance of the single-stance class of horizon 50
 #endif
+#ifndef MPC_N10_MINB_L
+#define MPC_N10_IPC_L 2      // double-support class of horizon 10: instances per CTA (2 warps each), resident CTAs per SM
+#define MPC_N10_MINB_L 3
+#endif
 #ifndef MPC_N50_WPI_L
 #define MPC_N50_WPI_L 8      // double-support class of horizon 50: warps per instance, resident CTAs per SM
 #define MPC_N50_MINB_L 2
@@ -686,7 +690,7 @@ static int dispatch_solve(mpc_b200_engine* e, int B, const double* x0, const dou
     int32_t* ol = e->d_ovf_list + list_offset;
     int32_t* oc = e->d_ovf_count + 4 * slot;
     switch (e->N) {
-        case 10: return launch_solve<10, 1, 4, 4, 2, 2, true, 3>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only);
+        case 10: return launch_solve<10, 1, 4, 4, 2, MPC_N10_IPC_L, true, MPC_N10_MINB_L>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only);
         case 20: return launch_solve<20, 2, 2, 2, 2, 2>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only);
         case 50: return launch_solve<50, MPC_N50_WPI_S, 1, 1, MPC_N50_WPI_L, 1, false, MPC_N50_MINB_L>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only);
         default: return set_err(e, MPC_B200_EINVAL, "unsupported horizon");

@@ -4,6 +4,7 @@
 
 #include <math.h>
 #include <pthread.h>
+#include <sched.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -884,6 +885,18 @@ typedef struct {
 static void *batch_worker(void *arg) {
     batch_job *j = (batch_job *)arg;
     const int N = j->N;
+    /* one solve per host core, the worker pinned to its core (SURVEY.md section 8d / BASELINE.md section 3); on a box with
+     * fewer allowed CPUs than threads the call fails harmlessly and the scheduler places the thread */
+    {
+        cpu_set_t allowed, one;
+        if (sched_getaffinity(0, sizeof(allowed), &allowed) == 0) {
+            int n = CPU_COUNT(&allowed), want = n > 0 ? j->tid % n : 0, seen = 0;
+            for (int c = 0; c < CPU_SETSIZE; ++c) {
+                if (!CPU_ISSET(c, &allowed)) continue;
+                if (seen++ == want) { CPU_ZERO(&one); CPU_SET(c, &one); pthread_setaffinity_np(pthread_self(), sizeof(one), &one); break; }
+            }
+        }
+    }
     const size_t fstride = (j->p->per_step_feet ? (size_t)6 * N : 6);
     for (int b = j->tid; b < j->B; b += j->nthreads) {
         int it = 0;
