@@ -46,8 +46,11 @@ using namespace mpcb200;
 #define MPC_N10_MINB_L 3
 #endif
 #ifndef MPC_N50_WPI_L
-#define MPC_N50_WPI_L 8      // double-support class of horizon 50: warps per instance, resident CTAs per SM
-#define MPC_N50_MINB_L 2
+// double-support class of horizon 50: warps per instance, resident CTAs per SM.  16 warps x 1 CTA: the 379 KB factor slabs of
+// the resident CTAs (148 x 379 KB = 56 MB) stay inside the 126 MB L2; 8 warps x 2 CTAs (112 MB of slabs) measured between
+// 409 k and 757 k cycles per factorisation depending on how much of that the L2 kept (tools/microbench/chol_dmma_bench.cu).
+#define MPC_N50_WPI_L 16
+#define MPC_N50_MINB_L 1
 #endif
 #ifndef MPC_TILED_N50
 #define MPC_TILED_N50 1
@@ -644,6 +647,7 @@ static int launch_solve(mpc_b200_engine* e, int B, const double* x0, const doubl
     if (e->only_large) {   // the host entry point has looked at the schedule: every instance is double support
         int grid = (B + IPC_L - 1) / IPC_L;
         if (grid > e->num_sms * (MINB_L > 2 ? MINB_L : 2)) grid = e->num_sms * (MINB_L > 2 ? MINB_L : 2);
+        if (!AINL_L && grid > e->num_sms * MINB_L) grid = e->num_sms * MINB_L;     // slab class: only the resident CTAs (L2 working set)
         if (!AINL_L && grid * IPC_L > e->extA_slabs) grid = e->extA_slabs / IPC_L;
         kl<<<grid, 32 * WPI_L * IPC_L, smem_l, s>>>(e->C, B, x0, xref, feet, contact, iter, forces, status, iters, nullptr, ovf_count,
                                                   AINL_L ? nullptr : e->d_extA, cmd_oy, cmd_vx, first_only);
@@ -663,6 +667,7 @@ static int launch_solve(mpc_b200_engine* e, int B, const double* x0, const doubl
     }
     int grid_l = (B + IPC_L - 1) / IPC_L;
     if (grid_l > e->num_sms * (MINB_L > 2 ? MINB_L : 2)) grid_l = e->num_sms * (MINB_L > 2 ? MINB_L : 2);
+    if (!AINL_L && grid_l > e->num_sms * MINB_L) grid_l = e->num_sms * MINB_L;
     if (!AINL_L && grid_l * IPC_L > e->extA_slabs) grid_l = e->extA_slabs / IPC_L;
     {
         cudaLaunchConfig_t cfg = {};
