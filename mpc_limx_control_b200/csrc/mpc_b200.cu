@@ -945,6 +945,13 @@ static int solve_host_impl(mpc_b200_engine* e, int B, const double* x0, const do
         void* o1 = status ? device_view(status) : nullptr;
         void* o2 = iters ? device_view(iters) : nullptr;
         if (a0 && a1 && a2 && a3 && a4 && o0 && (!status || o1) && (!iters || o2)) {
+            // Results are written by the kernel too.  SM-issued stores to host memory are slow on these hosts (12 GB/s alone,
+            // 5 GB/s per GPU with eight GPUs busy, against 51 GB/s for SM-issued reads: tools/microbench/host_read_probe.cu,
+            // profiles/r2_host_bw_probe_8gpu.log), but inside ONE kernel they overlap the reads (PCIe is full duplex) and the
+            // solves.  Bringing the results home with the copy engine instead was measured three ways at B = 4096 and lost
+            // every time against the 26.3 M solves/s of this path: chunk kernels on concurrent streams 19.4 M, chunk kernels back
+            // to back with event-ordered copies 16.7 M (chunking breaks the overlap of later CTAs' reads with earlier CTAs'
+            // solves), one kernel + one copy behind it 21.5 M (the copy is serial time).
             cudaStream_t s = e->stream;
             int rc = dispatch_solve(e, B, (const double*)a0, cmd ? nullptr : (const double*)a1, (const double*)a3,
                                     contact ? (const uint8_t*)a4 : nullptr, contact ? nullptr : (const int32_t*)a4,

@@ -133,6 +133,7 @@ struct Tron1Work {
     int16_t cidx[NS];       // foot-step -> compact stance index
     int8_t cinv[NS];        // compact stance index -> foot-step (2 step + foot)
     int nc;         // compact variable count (3 * stance foot-steps)
+    int interior;   // group-uniform: the face just solved was the interior face of every stance foot-step (Z = I, nothing fixed)
     int flag;       // group-uniform scratch flag
 #if defined(MPC_PHASE_TIMING)
     long long prof[16];
@@ -1339,13 +1340,20 @@ MPC_HD bool face_solve(const Tron1Const& P, WK& S, const G& g) {
     [[maybe_unused]] constexpr int N = WK::N;
     // fixed part: z = fmax on zt==1 foot-steps
     bool any_fixed = false;
+    [[maybe_unused]] bool any_reduced = false;   // some stance foot-step sits on a face other than the interior one
 #if defined(__CUDA_ARCH__)
-    if constexpr (G::kThreads >= 2 * N) {     // one foot-step per thread, group-wide vote
+    if constexpr (G::kThreads >= 2 * N) {     // one foot-step per thread, group-wide votes
         const int s = g.tid();
-        any_fixed = g.any(s < 2 * N && S.contact[s] && S.zt[s] == 1);
+        const bool st = s < 2 * N && S.contact[s];
+        any_fixed = g.any(st && S.zt[s] == 1);
+        any_reduced = g.any(st && (S.ax[s] | S.ay[s] | S.zt[s]) != 0);
+        if (g.tid() == 0) S.interior = any_reduced ? 0 : 1;
     } else
 #endif
-    for (int s = 0; s < 2 * N; ++s) any_fixed |= (S.contact[s] && S.zt[s] == 1);
+    {
+        for (int s = 0; s < 2 * N; ++s) any_fixed |= (S.contact[s] && S.zt[s] == 1);
+        if (g.tid() == 0) S.interior = 0;
+    }
     for (int s = g.tid(); s < 2 * N; s += g.size()) {
         double fz = (S.contact[s] && S.zt[s] == 1) ? P.f_max : 0.0;
         S.u[3 * s] = (double)S.ax[s] * P.mu * fz;
@@ -1412,6 +1420,34 @@ MPC_HD bool face_solve(const Tron1Const& P, WK& S, const G& g) {
 template <class WK, class G>
 MPC_HD bool check_optimality(const Tron1Const& P, WK& S, const G& g, bool& changed, double& resid) {
     [[maybe_unused]] constexpr int N = WK::N;
+#if defined(__CUDA_ARCH__) && defined(MPC_REDUCED_CERTIFICATE)
+    // MEASURED AND NOT USED (profiles/r2_reduced_certificate.log: 47.2 us against 45.8 us per 4096-instance batch, 145 against 150 M
+    // solves/s at B = 65536, horizon 20 and double support 3-7 % slower as well): the strided column part of the packed
+    // symmetric mat-vec costs more shared-memory wavefronts than the matrix-free pass costs arithmetic.  Kept as a compile-time option.
+    // Interior face (Z = I, no fixed part: 99.7 % of the BASELINE config-2 instances): the gradient on the stance variables is
+    // the residual of the linear system that was just solved, g_c = A w + f_c, and A -- the compact Hessian build_hessian
+    // wrote -- is still intact in shared memory because the register elimination (gj_solve_regs / gj3_solve_regs) never
+    // writes it back.  One 30 x 30 (60 x 60) symmetric mat-vec out of shared memory replaces the matrix-free
+    // input-response + adjoint pass (2.3 k of 22 k cycles at horizon 10).  Swing foot-steps are not read by the check.
+    // Any other face needs the multipliers of the fixed variables, i.e. the full gradient.
+    if constexpr (G::kThreads >= WK::NC && WK::NC <= 60 && !WK::TILED) {
+        if (S.interior) {
+            const int n = S.nc, t = g.tid();
+            const double* A = S.Ap();
+            if (t < n) {
+                const double* rowp = A + MPC_PK(t, 0);
+                double a0 = 0.0, a1 = 0.0;
+                int j = 0;
+                for (; j + 1 <= t; j += 2) { a0 = fma(rowp[j], S.w[j], a0); a1 = fma(rowp[j + 1], S.w[j + 1], a1); }
+                if (j <= t) { a0 = fma(rowp[j], S.w[j], a0); ++j; }
+                for (; j < n; ++j) a1 = fma(A[MPC_PK(j, t)], S.w[j], a1);
+                const int s = S.cinv[t / 3], c = t - 3 * (t / 3);
+                S.g[3 * s + c] = a0 + a1 + S.f[3 * s + c];
+            }
+            g.sync();
+        } else gradient<WK>(P, S, g);
+    } else
+#endif
     gradient<WK>(P, S, g);
 #if defined(__CUDA_ARCH__)
     if constexpr (G::kThreads == 32 && 2 * N <= 32) {

@@ -645,3 +645,30 @@ def test_every_instance_vs_oracle_horizons_20_50(torch_cuda, N, B, standing_ever
         c = O.tron1_condense(po, N, d["x0"][b], d["x_ref"][b], d["feet"][b], want_pred=False)
         assert O.tron1_natural_residual(po, N, c["H"], c["f"], c_ref[b], F[b]) < 1e-6
     eng.close()
+
+
+@pytest.mark.parametrize("N,B,standing_every", [(10, 3001, 0), (10, 4096, 3), (20, 2048, 0), (50, 2100, 6)])
+def test_host_auto_path_large_batches(torch_cuda, N, B, standing_every):
+    """Pinned buffers at full batch sizes through the host entry (AUTO and forced zero-copy), mixed capacity classes,
+    horizon 50 with its shared factor slabs: bit-identical to the device call."""
+    torch = torch_cuda
+    from mpc_limx_control_b200.engine import Engine
+    Ts = 0.005
+    d = synth.tron1_batch(31 + N, B, N, Ts)
+    if standing_every:
+        d["iter"][::standing_every] = -1
+    eng = make_engine(N, B, Ts=Ts)
+    t = to_dev(torch, d)
+    F, st, it = eng.solve(t["x0"], t["x_ref"], t["feet"], it=t["iter"])
+    torch.cuda.synchronize()
+    F, st, it = F.cpu().numpy(), st.cpu().numpy(), it.cpu().numpy()
+    pin = {k: torch.from_numpy(np.ascontiguousarray(d[k])).pin_memory() for k in ("x0", "x_ref", "feet", "iter")}
+    for mode in (Engine.HOST_AUTO, Engine.HOST_ZEROCOPY):
+        Fh = torch.zeros((B, N, 6), dtype=torch.float64).pin_memory()
+        sh = torch.full((B,), -7, dtype=torch.int32).pin_memory(); ih = torch.zeros(B, dtype=torch.int32).pin_memory()
+        eng.set_host_mode(mode)
+        eng.solve_host(pin["x0"], pin["x_ref"], pin["feet"], it=pin["iter"], forces=Fh, status=sh, iters=ih)
+        assert eng.last_host_path() == 1
+        assert np.array_equal(Fh.numpy(), F) and np.array_equal(sh.numpy(), st) and np.array_equal(ih.numpy(), it)
+    eng.set_host_mode(Engine.HOST_AUTO)
+    eng.close()
