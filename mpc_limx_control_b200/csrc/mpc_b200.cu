@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <atomic>
 #include <string>
 #include <thread>
 #include <vector>
@@ -593,6 +594,8 @@ struct mpc_b200_engine {
     static constexpr int kZeroCopyB = 8;                     // below this the kernels read/write the pinned staging directly
     cudaStream_t pipe[kPipe] = {};
     unsigned char *h_small = nullptr, *d_small = nullptr;    // pinned / device staging of the packed path
+    double* d_condense_ws = nullptr;                         // horizon-50 parity dump: packed 300 x 300 workspace, grown on demand
+    size_t condense_ws_bytes = 0;
     double* d_extA = nullptr;                                // global-memory factor slabs (N = 50 double support)
     int extA_slabs = 0;
     cudaEvent_t extA_free = nullptr;                         // recorded behind every kernel that uses the slabs: the next user
@@ -600,8 +603,6 @@ struct mpc_b200_engine {
     size_t small_bytes = 0;
     int host_mode = MPC_B200_HOST_AUTO;                      // how the host-buffer entry points move data
     int last_host_path = 0;                                  // 1 = zero-copy, 0 = staged (for tests / bench)
-    bool skip_large = false;                                 // host entry points: the caller's schedule needs no large-class pass
-    bool only_large = false;                                 // host entry points: every instance needs the large class
     int num_sms = 148;
     int64_t launches = 0;
     std::string err;
@@ -630,21 +631,23 @@ template <int N, int WPI_S, int IPC_S, int MINB_S, int WPI_L, int IPC_L, bool AI
 static int launch_solve(mpc_b200_engine* e, int B, const double* x0, const double* xref, const double* feet,
                         const uint8_t* contact, const int32_t* iter, double* forces, int32_t* status,
                         int32_t* iters, cudaStream_t s, int32_t* ovf_list, int32_t* ovf_count,
-                        const double* cmd_oy, const double* cmd_vx, int first_only) {
+                        const double* cmd_oy, const double* cmd_vx, int first_only, int cls_hint) {
+    // cls_hint (host entry points have seen the schedule): 0 = no instance needs the large class, 2 = every instance does,
+    // 1 = mixed / unknown (device entry point)
     auto ks = tron1_solve_kernel<N, 3 * N, WPI_S, IPC_S, MINB_S, false, true, MPC_DYNAMIC != 0>;
     auto kl = tron1_solve_kernel<N, 6 * N, WPI_L, IPC_L, MINB_L, true, AINL_L>;
     const size_t smem_s = ((sizeof(CtaStage<N, IPC_S>) + 15) & ~size_t(15)) + sizeof(SolveWork<N, 3 * N, true>) * IPC_S;
     const size_t smem_l = ((sizeof(CtaStage<N, IPC_L>) + 15) & ~size_t(15)) + sizeof(SolveWork<N, 6 * N, AINL_L>) * IPC_L;
-    static bool configured[64] = {};
-    if (!configured[e->device & 63]) {
+    static std::atomic<bool> configured[64];      // per device; setting the attribute twice is harmless, so a lost race is too
+    if (!configured[e->device & 63].load(std::memory_order_acquire)) {
         CU(e, cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
         CU(e, cudaFuncSetAttribute(kl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l));
-        configured[e->device & 63] = true;
+        configured[e->device & 63].store(true, std::memory_order_release);
     }
     // the large class of horizon 50 keeps its factors in ONE set of global slabs indexed by CTA: two such kernels must
     // never overlap, whatever streams they are on (the chunk-pipelined host path uses several)
     if (!AINL_L) CU(e, cudaStreamWaitEvent(s, e->extA_free, 0));
-    if (e->only_large) {   // the host entry point has looked at the schedule: every instance is double support
+    if (cls_hint == 2) {   // the host entry point has looked at the schedule: every instance is double support
         int grid = (B + IPC_L - 1) / IPC_L;
         if (grid > e->num_sms * (MINB_L > 2 ? MINB_L : 2)) grid = e->num_sms * (MINB_L > 2 ? MINB_L : 2);
         if (!AINL_L && grid > e->num_sms * MINB_L) grid = e->num_sms * MINB_L;     // slab class: only the resident CTAs (L2 working set)
@@ -661,7 +664,7 @@ static int launch_solve(mpc_b200_engine* e, int B, const double* x0, const doubl
     ks<<<grid_s, 32 * WPI_S * IPC_S, smem_s, s>>>(e->C, B, x0, xref, feet, contact, iter, forces, status,
                                                                  iters, ovf_list, ovf_count, nullptr, cmd_oy, cmd_vx, first_only);
     CU(e, cudaGetLastError());
-    if (e->skip_large) {   // the host entry point has looked at the schedule: no instance can overflow, the list stays empty
+    if (cls_hint == 0) {   // the host entry point has looked at the schedule: no instance can overflow, the list stays empty
         e->launches += 1;
         return MPC_B200_OK;
     }
@@ -690,14 +693,14 @@ static int launch_solve(mpc_b200_engine* e, int B, const double* x0, const doubl
 static int dispatch_solve(mpc_b200_engine* e, int B, const double* x0, const double* xref, const double* feet,
                           const uint8_t* contact, const int32_t* iter, double* forces, int32_t* status,
                           int32_t* iters, cudaStream_t s, int slot = 0, int list_offset = 0,
-                          const double* cmd_oy = nullptr, const double* cmd_vx = nullptr, int first_only = 0) {
+                          const double* cmd_oy = nullptr, const double* cmd_vx = nullptr, int first_only = 0, int cls_hint = 1) {
     if (B + list_offset > e->max_batch) return set_err(e, MPC_B200_ECAPACITY, "solve: B > max_batch");
     int32_t* ol = e->d_ovf_list + list_offset;
     int32_t* oc = e->d_ovf_count + 4 * slot;
     switch (e->N) {
-        case 10: return launch_solve<10, 1, 4, 4, 2, MPC_N10_IPC_L, true, MPC_N10_MINB_L>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only);
-        case 20: return launch_solve<20, 2, 2, 2, 2, 2>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only);
-        case 50: return launch_solve<50, MPC_N50_WPI_S, 1, 1, MPC_N50_WPI_L, 1, false, MPC_N50_MINB_L>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only);
+        case 10: return launch_solve<10, 1, 4, 4, 2, MPC_N10_IPC_L, true, MPC_N10_MINB_L>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only, cls_hint);
+        case 20: return launch_solve<20, 2, 2, 2, 2, 2>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only, cls_hint);
+        case 50: return launch_solve<50, MPC_N50_WPI_S, 1, 1, MPC_N50_WPI_L, 1, false, MPC_N50_MINB_L>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only, cls_hint);
         default: return set_err(e, MPC_B200_EINVAL, "unsupported horizon");
     }
 }
@@ -808,6 +811,7 @@ int mpc_b200_destroy(mpc_b200_engine* e) {
     if (e->h_small) cudaFreeHost(e->h_small);
     cudaFree(e->d_small);
     cudaFree(e->d_extA);
+    cudaFree(e->d_condense_ws);
     if (e->extA_free) cudaEventDestroy(e->extA_free);
     delete e;
     return MPC_B200_OK;
@@ -923,13 +927,7 @@ static int solve_host_impl(mpc_b200_engine* e, int B, const double* x0, const do
     const size_t fstride = (e->C.per_step_feet && e->C.ltv) ? 6 * (size_t)N : 6;
     const size_t XR = 13 * (size_t)(N + 1);
     e->last_host_path = 0;
-    struct SkipGuard {   // every dispatch of this call may skip one of the two kernels; always restored on return
-        mpc_b200_engine* e;
-        ~SkipGuard() { e->skip_large = false; e->only_large = false; }
-    } guard{e};
-    const int cls = schedule_large_class(e, B, contact, iter);
-    e->skip_large = cls == 0;
-    e->only_large = cls == 2;
+    const int cls = schedule_large_class(e, B, contact, iter);   // 0 / 2: one of the two kernels of every dispatch is skipped
     if (e->host_mode != MPC_B200_HOST_STAGED) {
         // ---- zero-copy path: when every caller buffer is pinned (device-addressable), the solve kernel
         // reads its inputs straight from host memory (each CTA's slice arrives by TMA bulk copies over
@@ -956,7 +954,7 @@ static int solve_host_impl(mpc_b200_engine* e, int B, const double* x0, const do
             int rc = dispatch_solve(e, B, (const double*)a0, cmd ? nullptr : (const double*)a1, (const double*)a3,
                                     contact ? (const uint8_t*)a4 : nullptr, contact ? nullptr : (const int32_t*)a4,
                                     (double*)o0, (int32_t*)o1, (int32_t*)o2, s, 0, 0,
-                                    cmd ? (const double*)a1 : nullptr, cmd ? (const double*)a2 : nullptr, cmd ? 1 : 0);
+                                    cmd ? (const double*)a1 : nullptr, cmd ? (const double*)a2 : nullptr, cmd ? 1 : 0, cls);
             if (rc) return rc;
             CU(e, cudaStreamSynchronize(s));
             e->last_host_path = 1;
@@ -985,7 +983,7 @@ static int solve_host_impl(mpc_b200_engine* e, int B, const double* x0, const do
         int rc = dispatch_solve(e, B, (const double*)(d + L.x0), cmd ? nullptr : (const double*)(d + L.xref), (const double*)(d + L.feet),
                                 contact ? (const uint8_t*)(d + L.sched) : nullptr, contact ? nullptr : (const int32_t*)(d + L.sched),
                                 cmd ? (double*)(d + L.u0) : (double*)(d + L.forces), (int32_t*)(d + L.status), (int32_t*)(d + L.iters), s,
-                                0, 0, cmd ? (const double*)(d + L.oy) : nullptr, cmd ? (const double*)(d + L.vx) : nullptr, cmd ? 1 : 0);
+                                0, 0, cmd ? (const double*)(d + L.oy) : nullptr, cmd ? (const double*)(d + L.vx) : nullptr, cmd ? 1 : 0, cls);
         if (rc) return rc;
         if (!zc) CU(e, cudaMemcpyAsync(h + L.in_bytes, d + L.in_bytes, L.total - L.in_bytes, cudaMemcpyDeviceToHost, s));
         CU(e, cudaStreamSynchronize(s));
@@ -1028,7 +1026,7 @@ static int solve_host_impl(mpc_b200_engine* e, int B, const double* x0, const do
         int rc = dispatch_solve(e, nb, e->d_x0 + 13 * f, cmd ? nullptr : e->d_xref + XR * f, e->d_feet + fstride * f,
                                 contact ? e->d_contact + 2 * N * f : nullptr, contact ? nullptr : e->d_iter + f,
                                 cmd ? e->d_u0 + 6 * f : e->d_forces + 6 * N * f, e->d_status + f, e->d_iters + f, s,
-                                1 + c % mpc_b200_engine::kPipe, first, cmd ? e->d_oy + f : nullptr, cmd ? e->d_vx + f : nullptr, cmd ? 1 : 0);
+                                1 + c % mpc_b200_engine::kPipe, first, cmd ? e->d_oy + f : nullptr, cmd ? e->d_vx + f : nullptr, cmd ? 1 : 0, cls);
         if (rc) return rc;
         if (cmd) {
             CU(e, cudaMemcpyAsync(forces_out + 6 * f, e->d_u0 + 6 * f, sizeof(double) * 6 * nb, cudaMemcpyDeviceToHost, s));
@@ -1116,17 +1114,21 @@ int mpc_b200_tron1_condense_device(mpc_b200_engine* e, int B, const double* d_x0
     } else if (e->N == 50) {
         // the 300 x 300 packed factor lives in a temporary global workspace (parity dump only)
         using W50 = Tron1Work<50, 300, false>;
-        double* ws = nullptr;
-        if (cudaMalloc(&ws, sizeof(double) * W50::PKN * (size_t)B) != cudaSuccess) { cudaGetLastError(); return set_err(e, MPC_B200_ENOMEM, "condense: workspace"); }
+        const size_t need = sizeof(double) * W50::PKN * (size_t)B;
+        if (need > e->condense_ws_bytes) {      // kept by the engine: no allocation on repeated calls
+            CU(e, cudaStreamSynchronize(s));
+            cudaFree(e->d_condense_ws); e->d_condense_ws = nullptr; e->condense_ws_bytes = 0;
+            if (cudaMalloc(&e->d_condense_ws, need) != cudaSuccess) { cudaGetLastError(); return set_err(e, MPC_B200_ENOMEM, "condense: workspace"); }
+            e->condense_ws_bytes = need;
+        }
+        double* ws = e->d_condense_ws;
         auto k = tron1_condense_kernel<50, false>;
         size_t smem = sizeof(W50);
         cudaError_t ce = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (ce == cudaSuccess) {
             k<<<B, 32, smem, s>>>(e->C, B, d_x0, d_x_ref, d_feet, d_H, d_f, d_A_aug, d_B_aug, ws);
             ce = cudaGetLastError();
-            if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
         }
-        cudaFree(ws);
         if (ce != cudaSuccess) return set_err(e, MPC_B200_ECUDA, "condense<50>", ce);
     } else return set_err(e, MPC_B200_EINVAL, "unsupported horizon");
     CU(e, cudaGetLastError());
