@@ -1421,26 +1421,32 @@ template <class WK, class G>
 MPC_HD bool check_optimality(const Tron1Const& P, WK& S, const G& g, bool& changed, double& resid) {
     [[maybe_unused]] constexpr int N = WK::N;
 #if defined(__CUDA_ARCH__) && defined(MPC_REDUCED_CERTIFICATE)
-    // MEASURED AND NOT USED (profiles/r2_reduced_certificate.log: 47.2 us against 45.8 us per 4096-instance batch, 145 against 150 M
-    // solves/s at B = 65536, horizon 20 and double support 3-7 % slower as well): the strided column part of the packed
-    // symmetric mat-vec costs more shared-memory wavefronts than the matrix-free pass costs arithmetic.  Kept as a compile-time option.
-    // Interior face (Z = I, no fixed part: 99.7 % of the BASELINE config-2 instances): the gradient on the stance variables is
-    // the residual of the linear system that was just solved, g_c = A w + f_c, and A -- the compact Hessian build_hessian
-    // wrote -- is still intact in shared memory because the register elimination (gj_solve_regs / gj3_solve_regs) never
-    // writes it back.  One 30 x 30 (60 x 60) symmetric mat-vec out of shared memory replaces the matrix-free
-    // input-response + adjoint pass (2.3 k of 22 k cycles at horizon 10).  Swing foot-steps are not read by the check.
-    // Any other face needs the multipliers of the fixed variables, i.e. the full gradient.
+    // MEASURED TWICE AND NOT USED (profiles/r2_reduced_certificate.log): compile-time option only.
+    // Interior face (Z = I, no fixed part: 99.7 % of the BASELINE config-2 instances) at full compact size: the gradient on the
+    // stance variables is the residual of the linear system that was just solved, g_c = A w + f_c, and A -- the compact
+    // Hessian build_hessian wrote -- is still intact in shared memory because the register elimination (gj_solve_regs /
+    // gj3_solve_regs) never writes it back.  One symmetric mat-vec out of shared memory, fully unrolled with the same
+    // predicated row/column loads the elimination uses to fill its window (all loads independent), replaces the matrix-free
+    // input-response + adjoint pass.  Swing foot-steps are not read by the check.  Any other face needs the multipliers of
+    // the fixed variables, i.e. the full gradient.  Measured: 48.6 us against 45.6 us per 4096-instance batch for this
+    // unrolled version (47.2 us for a first version with lane-dependent loop bounds); horizon 20 7 % slower.
     if constexpr (G::kThreads >= WK::NC && WK::NC <= 60 && !WK::TILED) {
-        if (S.interior) {
-            const int n = S.nc, t = g.tid();
+        if (S.interior && S.nc == WK::NC) {
+            constexpr int NC = WK::NC;
+            const int t = g.tid(), tt = t < NC ? t : NC - 1;
             const double* A = S.Ap();
-            if (t < n) {
-                const double* rowp = A + MPC_PK(t, 0);
-                double a0 = 0.0, a1 = 0.0;
-                int j = 0;
-                for (; j + 1 <= t; j += 2) { a0 = fma(rowp[j], S.w[j], a0); a1 = fma(rowp[j + 1], S.w[j + 1], a1); }
-                if (j <= t) { a0 = fma(rowp[j], S.w[j], a0); ++j; }
-                for (; j < n; ++j) a1 = fma(A[MPC_PK(j, t)], S.w[j], a1);
+            const double* rowp = A + MPC_PK(tt, 0);
+            const double* colp = A + tt;
+            double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+            for (int j = 0; j < NC; j += 2) {
+                double v0, v1;
+                if (j <= tt) v0 = rowp[j]; else v0 = colp[j * (j + 1) / 2];
+                if (j + 1 <= tt) v1 = rowp[j + 1]; else v1 = colp[(j + 1) * (j + 2) / 2];
+                a0 = fma(v0, S.w[j], a0);
+                a1 = fma(v1, S.w[j + 1], a1);
+            }
+            if (t < NC) {
                 const int s = S.cinv[t / 3], c = t - 3 * (t / 3);
                 S.g[3 * s + c] = a0 + a1 + S.f[3 * s + c];
             }
