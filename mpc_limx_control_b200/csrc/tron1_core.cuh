@@ -1346,8 +1346,10 @@ MPC_HD bool face_solve(const Tron1Const& P, WK& S, const G& g) {
         const int s = g.tid();
         const bool st = s < 2 * N && S.contact[s];
         any_fixed = g.any(st && S.zt[s] == 1);
+#if defined(MPC_REDUCED_CERTIFICATE)
         any_reduced = g.any(st && (S.ax[s] | S.ay[s] | S.zt[s]) != 0);
         if (g.tid() == 0) S.interior = any_reduced ? 0 : 1;
+#endif
     } else
 #endif
     {
