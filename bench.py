@@ -296,7 +296,13 @@ def run_gpu(args, cfg):
         iters = torch.empty(B, dtype=torch.int32, device=dev)
         # one pre-bound C-ABI call per pool entry: the timed loop issues mpc_b200_tron1_solve_device and nothing else
         calls = [eng.bind_solve(p["x0"], p["x_ref"], p["feet"], it=p["iter"], forces=forces, status=status, iters=iters) for p in pool]
-        step = lambda i: calls[i % pool_n]()
+        # the timed loop works through a queue of independent batches: mpc_b200_tron1_solve_device_pipelined lets the CTAs of
+        # batch k+1 fill the slots the last multi-iteration instances of batch k leave idle; one join before the closing event.
+        # --serialized times the stream-ordered entry instead (every batch waits for the previous one to drain).
+        pcalls = [eng.bind_solve(p["x0"], p["x_ref"], p["feet"], it=p["iter"], forces=forces, status=status, iters=iters, pipelined=True)
+                  for p in pool]
+        use = calls if args.serialized else pcalls
+        step = lambda i: use[i % pool_n]()
         l2_note = f"rotating pool of {pool_n} distinct input batches ({pool_n * per_batch_in / 1e6:.0f} MB) > 126 MB L2"
     else:
         d = synth_batch(cfg, B, first=first_inst)
@@ -313,6 +319,7 @@ def run_gpu(args, cfg):
 
     for i in range(W):
         step(i)
+    eng.join()
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     l0 = eng.launch_count()
@@ -321,10 +328,25 @@ def run_gpu(args, cfg):
     e0.record()
     for i in range(K):
         step(W + i)
+    eng.join()          # the current stream waits for every pipelined batch: e1 is behind all K steps
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
     launches = eng.launch_count() - l0
+    ms_serial = None
+    if not rollout and not args.serialized:
+        # the same K steps through the stream-ordered entry (one batch at a time): the latency-bound figure
+        for i in range(min(W, 10)):
+            calls[i % pool_n]()
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        Ks = min(K, 500)
+        s0.record()
+        for i in range(Ks):
+            calls[(W + i) % pool_n]()
+        s1.record()
+        torch.cuda.synchronize()
+        ms_serial = s0.elapsed_time(s1) / Ks
     ms_max = max_over_ranks(ms)
     if rollout:
         solves_per_step = B_total * cfg["steps"]
@@ -426,15 +448,18 @@ def run_gpu(args, cfg):
                 pl.append({k: torch.from_numpy(dd[k]).to(dev) for k in ("x0", "x_ref", "feet", "iter")})
             F2 = torch.empty((B, N, 6), dtype=torch.float64, device=dev)
             s2 = torch.empty(B, dtype=torch.int32, device=dev); i2 = torch.empty(B, dtype=torch.int32, device=dev)
-            cl = [eng2.bind_solve(p["x0"], p["x_ref"], p["feet"], it=p["iter"], forces=F2, status=s2, iters=i2) for p in pl]
+            cl = [eng2.bind_solve(p["x0"], p["x_ref"], p["feet"], it=p["iter"], forces=F2, status=s2, iters=i2,
+                                  pipelined=not args.serialized) for p in pl]
             for i in range(8):
                 cl[i]()
+            eng2.join()
             torch.cuda.synchronize()
             a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             reps = 200
             a0.record()
             for i in range(reps):
                 cl[i % 8]()
+            eng2.join()
             a1.record()
             torch.cuda.synchronize()
             extra[key] = {"value": B * reps / (a0.elapsed_time(a1) * 1e-3), "unit": "solves/s", "config_id": cid,
@@ -442,6 +467,8 @@ def run_gpu(args, cfg):
                           "unsolved": int((s2 != 0).sum().item()), "workload": workload_name(c2, 1)}
             eng2.close()
 
+    ms_serial_max = max_over_ranks(ms_serial) if ms_serial is not None else None
+    max_over_ranks_host = lambda _x: ms_serial_max
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -526,6 +553,10 @@ def run_gpu(args, cfg):
                    "parallelism": f"instance-sharded x{world}, no collective", "instances_per_gpu": B,
                    "mean_iters": mean_iters, "unsolved": n_bad},
         "clocks": clocks,
+        "serialized": None if ms_serial is None else {
+            "value": B_total * 1e3 / max_over_ranks_host(ms_serial), "unit": "solves/s", "ms_per_step": ms_serial,
+            "what": "the same steps through mpc_b200_tron1_solve_device, every batch stream-ordered behind the previous one "
+                    "(value uses mpc_b200_tron1_solve_device_pipelined: independent batches overlap on engine-owned streams)"},
         "e2e": e2e,
         "gpu_launches": int(launches),
         "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
@@ -535,7 +566,9 @@ def run_gpu(args, cfg):
                                     "tools/microbench/chol_dmma_bench.cu)",
                      "flops_per_solve": f_exec, "tensor_flops_per_solve": f_tensor, "kernel": kname, "kernel_ms": kernel_ms,
                      "what": "achieved = FP64 operations the kernel EXECUTES per solve (hand-counted structured formula, "
-                             "bench.py:structured_flops, DESIGN.md section 4) x instances / CUDA-event time of the launch",
+                             "bench.py:structured_flops, DESIGN.md section 4) x instances per step / CUDA-event time per step "
+                             "(consecutive launches overlap on the pipelined entry, so this is the sustained rate of the kernel, "
+                             "not one launch in isolation; `serialized` has the isolated-launch time)",
                      "ncu_check": ncu_exec,
                      "dense_equiv": {"flops_per_solve": f_dense, "achieved": f_dense * B / (kernel_ms * 1e-3) / 1e12, "unit": "TFLOP/s",
                                      "what": "SURVEY 8d DENSE accounting (n^2 p condensing, n^3/3 Cholesky): how fast the PROBLEM is "
@@ -566,6 +599,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--latency-calls", type=int, default=10000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--serialized", action="store_true", help="time the stream-ordered device entry instead of the pipelined one")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -30,6 +30,9 @@ using namespace mpcb200;
 
 // horizon 50 uses the tiled storage + tensor-core Cholesky (tron1_core.cuh: chol_tiled); the shorter horizons keep the
 // packed triangle and the register-resident eliminations
+#ifndef MPC_LANES
+#define MPC_LANES 3          // engine-owned streams of the pipelined device entry (2, 3 and 4 measured: see DESIGN.md section 4)
+#endif
 #ifndef MPC_DYNAMIC
 // direct class: 1 = persistent grid, groups pull instances from an atomic counter.  Built, parity
 // green and MEASURED (profiles/r2_dynamic_vs_static.log): 7-10 % SLOWER than the static one-CTA-per-four-instances
@@ -108,6 +111,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 
 #if defined(MPC_PHASE_TIMING)
 __device__ unsigned long long g_cta_trace[4 * 16384];   // per CTA: start ns, end ns, SM id, inputs-arrived ns (profiling build only)
+__device__ unsigned long long g_cta_trace2[4 * 16384];  // per CTA: copies issued, schedule evaluated, CTA barrier passed, (unused)
+extern "C" int mpc_b200_debug_cta_trace2(unsigned long long* out, int n) {
+    return cudaMemcpyFromSymbol(out, g_cta_trace2, sizeof(unsigned long long) * 4 * n) == cudaSuccess ? 0 : -3;
+}
 extern "C" int mpc_b200_debug_cta_trace(unsigned long long* out, int n) {
     return cudaMemcpyFromSymbol(out, g_cta_trace, sizeof(unsigned long long) * 4 * n) == cudaSuccess ? 0 : -3;
 }
@@ -360,13 +367,22 @@ tron1_solve_kernel(const __grid_constant__ Tron1Const P, int B, const double* __
             for (int i = threadIdx.x; i < valid * 13; i += blockDim.x) st.x0[i] = g0[i];
             for (int i = threadIdx.x; i < valid * fstride; i += blockDim.x) st.feet[i] = gf[i];
         }
+#if defined(MPC_PHASE_TIMING)
+        if (threadIdx.x == 0 && blockIdx.x < 16384) g_cta_trace2[4 * blockIdx.x] = gtime_ns();
+#endif
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the overflow grid may queue up behind us
         // the contact schedule is evaluated while the copies are in flight
         const bool mine = g.gid < valid;
         const int b = first + g.gid;
         int nc = 0;
         if (mine) nc = load_contact(b);
+#if defined(MPC_PHASE_TIMING)
+        if (threadIdx.x == 0 && blockIdx.x < 16384) g_cta_trace2[4 * blockIdx.x + 1] = gtime_ns();
+#endif
         __syncthreads();   // barrier init / plain stores visible
+#if defined(MPC_PHASE_TIMING)
+        if (threadIdx.x == 0 && blockIdx.x < 16384) g_cta_trace2[4 * blockIdx.x + 2] = gtime_ns();
+#endif
         if (bulk) mbar_wait(&st.bar, 0);
 #if defined(MPC_PHASE_TIMING)
         if (threadIdx.x == 0 && blockIdx.x < 16384) g_cta_trace[4 * blockIdx.x + 3] = gtime_ns();
@@ -594,6 +610,13 @@ struct mpc_b200_engine {
     static constexpr int kZeroCopyB = 8;                     // below this the kernels read/write the pinned staging directly
     cudaStream_t pipe[kPipe] = {};
     unsigned char *h_small = nullptr, *d_small = nullptr;    // pinned / device staging of the packed path
+    // pipelined device entry (mpc_b200_tron1_solve_device_pipelined): consecutive independent batches run on alternating
+    // engine-owned streams so that the CTAs of batch k+1 fill the slots the stragglers of batch k leave idle
+    static constexpr int kLanes = MPC_LANES;
+    cudaStream_t lane[kLanes] = {};
+    cudaEvent_t lane_in[kLanes] = {}, lane_done[kLanes] = {};
+    bool lane_busy[kLanes] = {};
+    unsigned lane_next = 0;
     double* d_condense_ws = nullptr;                         // horizon-50 parity dump: packed 300 x 300 workspace, grown on demand
     size_t condense_ws_bytes = 0;
     double* d_extA = nullptr;                                // global-memory factor slabs (N = 50 double support)
@@ -694,7 +717,7 @@ static int dispatch_solve(mpc_b200_engine* e, int B, const double* x0, const dou
                           const uint8_t* contact, const int32_t* iter, double* forces, int32_t* status,
                           int32_t* iters, cudaStream_t s, int slot = 0, int list_offset = 0,
                           const double* cmd_oy = nullptr, const double* cmd_vx = nullptr, int first_only = 0, int cls_hint = 1) {
-    if (B + list_offset > e->max_batch) return set_err(e, MPC_B200_ECAPACITY, "solve: B > max_batch");
+    if (B + (list_offset % e->max_batch) > e->max_batch || B > e->max_batch) return set_err(e, MPC_B200_ECAPACITY, "solve: B > max_batch");
     int32_t* ol = e->d_ovf_list + list_offset;
     int32_t* oc = e->d_ovf_count + 4 * slot;
     switch (e->N) {
@@ -771,14 +794,18 @@ int mpc_b200_create(const mpc_b200_tron1_params* p, int horizon, int max_batch, 
               cudaMalloc(&e->d_iter, sizeof(int32_t) * max_batch) == cudaSuccess &&
               cudaMalloc(&e->d_status, sizeof(int32_t) * max_batch) == cudaSuccess &&
               cudaMalloc(&e->d_iters, sizeof(int32_t) * max_batch) == cudaSuccess &&
-              cudaMalloc(&e->d_ovf_list, sizeof(int32_t) * max_batch) == cudaSuccess &&
-              cudaMalloc(&e->d_ovf_count, 4 * (mpc_b200_engine::kPipe + 1) * sizeof(int32_t)) == cudaSuccess &&
-              cudaMemset(e->d_ovf_count, 0, 4 * (mpc_b200_engine::kPipe + 1) * sizeof(int32_t)) == cudaSuccess &&
+              cudaMalloc(&e->d_ovf_list, sizeof(int32_t) * (size_t)max_batch * (1 + mpc_b200_engine::kLanes)) == cudaSuccess &&
+              cudaMalloc(&e->d_ovf_count, 4 * (mpc_b200_engine::kPipe + 1 + mpc_b200_engine::kLanes) * sizeof(int32_t)) == cudaSuccess &&
+              cudaMemset(e->d_ovf_count, 0, 4 * (mpc_b200_engine::kPipe + 1 + mpc_b200_engine::kLanes) * sizeof(int32_t)) == cudaSuccess &&
               cudaMalloc(&e->d_oy, sizeof(double) * max_batch) == cudaSuccess &&
               cudaMalloc(&e->d_vx, sizeof(double) * max_batch) == cudaSuccess &&
               cudaMalloc(&e->d_u0, sizeof(double) * 6 * max_batch) == cudaSuccess;
     for (int i = 0; ok && i < mpc_b200_engine::kPipe; ++i)
         ok = cudaStreamCreateWithFlags(&e->pipe[i], cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; ok && i < mpc_b200_engine::kLanes; ++i)
+        ok = cudaStreamCreateWithFlags(&e->lane[i], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&e->lane_in[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&e->lane_done[i], cudaEventDisableTiming) == cudaSuccess;
     // packed staging of the small-batch path: inputs and outputs of kSmallB instances, 16-byte aligned segments
     e->small_bytes = (size_t)mpc_b200_engine::kSmallB * (sizeof(double) * (13 + 13 * (N + 1) + fstride + 2 + 6 * N) + 2 * N + 16) + 1024;
     ok = ok && cudaHostAlloc((void**)&e->h_small, e->small_bytes, cudaHostAllocMapped) == cudaSuccess &&
@@ -812,6 +839,11 @@ int mpc_b200_destroy(mpc_b200_engine* e) {
     cudaFree(e->d_small);
     cudaFree(e->d_extA);
     cudaFree(e->d_condense_ws);
+    for (int i = 0; i < mpc_b200_engine::kLanes; ++i) {
+        if (e->lane[i]) { cudaStreamSynchronize(e->lane[i]); cudaStreamDestroy(e->lane[i]); }
+        if (e->lane_in[i]) cudaEventDestroy(e->lane_in[i]);
+        if (e->lane_done[i]) cudaEventDestroy(e->lane_done[i]);
+    }
     if (e->extA_free) cudaEventDestroy(e->extA_free);
     delete e;
     return MPC_B200_OK;
@@ -858,6 +890,38 @@ int mpc_b200_tron1_solve_device(mpc_b200_engine* e, int B, const double* d_x0, c
         return set_err(e, MPC_B200_EINVAL, "solve: pointers must be 8-byte aligned");
     CU(e, cudaSetDevice(e->device));
     return dispatch_solve(e, B, d_x0, d_x_ref, d_feet, d_contact, d_iter, d_forces, d_status, d_iters, (cudaStream_t)stream);
+}
+
+int mpc_b200_tron1_solve_device_pipelined(mpc_b200_engine* e, int B, const double* d_x0, const double* d_x_ref,
+                                          const double* d_feet, const uint8_t* d_contact, const int32_t* d_iter,
+                                          double* d_forces, int32_t* d_status, int32_t* d_iters, void* stream) {
+    if (!e || !d_x0 || !d_x_ref || !d_feet || !d_forces || B < 1) return set_err(e, MPC_B200_EINVAL, "solve_pipelined: bad argument");
+    if ((d_contact == nullptr) == (d_iter == nullptr)) return set_err(e, MPC_B200_EINVAL, "solve_pipelined: pass exactly one of contact / iter");
+    if (((uintptr_t)d_x0 | (uintptr_t)d_x_ref | (uintptr_t)d_feet | (uintptr_t)d_forces) & 7)
+        return set_err(e, MPC_B200_EINVAL, "solve_pipelined: pointers must be 8-byte aligned");
+    CU(e, cudaSetDevice(e->device));
+    const int l = (int)(e->lane_next++ % mpc_b200_engine::kLanes);
+    // ordered after everything already queued on the caller's stream (its inputs are ready) and, by stream order of the
+    // lane, after the batch that used this lane before; NOT ordered against the other lanes: that is the overlap
+    CU(e, cudaEventRecord(e->lane_in[l], (cudaStream_t)stream));
+    CU(e, cudaStreamWaitEvent(e->lane[l], e->lane_in[l], 0));
+    const int rc = dispatch_solve(e, B, d_x0, d_x_ref, d_feet, d_contact, d_iter, d_forces, d_status, d_iters, e->lane[l],
+                                  mpc_b200_engine::kPipe + 1 + l, (1 + l) * e->max_batch);
+    if (rc) return rc;
+    e->lane_busy[l] = true;
+    return MPC_B200_OK;
+}
+
+int mpc_b200_join(mpc_b200_engine* e, void* stream) {
+    if (!e) return MPC_B200_EINVAL;
+    CU(e, cudaSetDevice(e->device));
+    for (int l = 0; l < mpc_b200_engine::kLanes; ++l) {
+        if (!e->lane_busy[l]) continue;
+        CU(e, cudaEventRecord(e->lane_done[l], e->lane[l]));
+        CU(e, cudaStreamWaitEvent((cudaStream_t)stream, e->lane_done[l], 0));
+        e->lane_busy[l] = false;
+    }
+    return MPC_B200_OK;
 }
 
 namespace {

@@ -98,7 +98,11 @@ class Engine:
         _capi.check(rc, self.h)
         return forces, status, iters
 
-    def bind_solve(self, x0, x_ref, feet, contact=None, it=None, forces=None, status=None, iters=None):
+    def join(self):
+        """Make torch's current stream wait for every pipelined solve issued so far (mpc_b200_join)."""
+        _capi.check(self.lib.mpc_b200_join(self.h, self._stream()), self.h)
+
+    def bind_solve(self, x0, x_ref, feet, contact=None, it=None, forces=None, status=None, iters=None, pipelined=False):
         """Validate the tensors once and return a zero-overhead callable that issues exactly one
         mpc_b200_tron1_solve_device call on torch's current stream (for hot loops: the Python-side
         checks and pointer marshalling of solve() cost more than a 4096-instance batch takes on the GPU).
@@ -116,7 +120,9 @@ class Engine:
                 self._check_dev(t, dt, n, nm)
         args = (self.h, B, _ptr(x0), _ptr(x_ref), _ptr(feet), _ptr(contact), _ptr(it), _ptr(forces), _ptr(status), _ptr(iters),
                 self._stream())
-        fn = self.lib.mpc_b200_tron1_solve_device
+        # pipelined=True: mpc_b200_tron1_solve_device_pipelined -- independent batches overlap on engine-owned streams; call
+        # join() before anything on the current stream reads the results
+        fn = self.lib.mpc_b200_tron1_solve_device_pipelined if pipelined else self.lib.mpc_b200_tron1_solve_device
         keep = (x0, x_ref, feet, contact, it, forces, status, iters)
 
         def call(_fn=fn, _args=args, _keep=keep):

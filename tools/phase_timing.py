@@ -54,6 +54,17 @@ def cta_trace(label):
         print(f"  later CTAs: {(~first).sum()}, start mean {st_[~first].mean():.1f} us, input wait mean {w[~first].mean():.1f} max {w[~first].max():.1f}, duration mean {dur[~first].mean():.1f} us, end mean {en_[~first].mean():.1f} max {en_[~first].max():.1f} us")
     q = np.argsort(st_)
     print("  input-arrival time by CTA start order (deciles):", np.round(np.percentile(arr[q][:first.sum()], [0, 10, 25, 50, 75, 90, 100]), 1))
+    try:
+        tr2 = (C.c_ulonglong * (4 * nb))()
+        L.mpc_b200_debug_cta_trace2(tr2, nb)
+        tr2 = np.array(list(tr2), dtype=np.float64).reshape(nb, 4)
+        for nm, sel in (("first wave", first), ("later CTAs", ~first)):
+            if sel.any():
+                a = (tr2[sel, 0] - tr[sel, 0]) / 1e3; b_ = (tr2[sel, 1] - tr[sel, 0]) / 1e3; c_ = (tr2[sel, 2] - tr[sel, 0]) / 1e3
+                print(f"  {nm}: since CTA start (us, mean/max): copies issued {a.mean():.2f}/{a.max():.2f}, schedule evaluated {b_.mean():.2f}/{b_.max():.2f}, "
+                      f"CTA barrier passed {c_.mean():.2f}/{c_.max():.2f}, inputs arrived {w[sel].mean():.2f}/{w[sel].max():.2f}")
+    except Exception as ex:
+        print("  (no prologue trace:", ex, ")")
     per_sm = np.bincount(tr[:, 2].astype(int), minlength=148)
     print(f"  CTAs per SM: min {per_sm.min()} max {per_sm.max()}")
 
