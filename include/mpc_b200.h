@@ -105,11 +105,11 @@ int mpc_b200_tron1_solve_device(mpc_b200_engine *e, int B, const double *d_x0, c
 
 /* Pipelined variant for streams of INDEPENDENT batches (a server working through a queue, a benchmark loop): the solve
  * is ordered after everything already queued on `stream` at the time of the call (so its inputs are ready), but it runs
- * on one of three engine-owned streams, used in rotation, and is NOT ordered against the previous pipelined calls: the
+ * on one of six engine-owned streams, used in rotation, and is NOT ordered against the previous pipelined calls: the
  * CTAs of batch k+1 fill the SM slots that the last, multi-iteration instances of batch k leave idle (at B = 4096 a third
  * of a batch's time is that tail).  Results become visible to `stream` only after mpc_b200_join(e, stream); a batch that
  * consumes the previous batch's forces must use mpc_b200_tron1_solve_device (or join in between).  Output buffers of
- * calls that may overlap (three consecutive calls) must be distinct if all of them are wanted. */
+ * calls that may overlap (six consecutive calls) must be distinct if all of them are wanted. */
 int mpc_b200_tron1_solve_device_pipelined(mpc_b200_engine *e, int B, const double *d_x0, const double *d_x_ref,
                                           const double *d_feet, const uint8_t *d_contact, const int32_t *d_iter,
                                           double *d_forces, int32_t *d_status, int32_t *d_iters, void *stream);

@@ -31,7 +31,7 @@ using namespace mpcb200;
 // horizon 50 uses the tiled storage + tensor-core Cholesky (tron1_core.cuh: chol_tiled); the shorter horizons keep the
 // packed triangle and the register-resident eliminations
 #ifndef MPC_LANES
-#define MPC_LANES 3          // engine-owned streams of the pipelined device entry (2, 3 and 4 measured: see DESIGN.md section 4)
+#define MPC_LANES 6          // engine-owned streams of the pipelined device entry (2, 3, 4, 6 measured: profiles/r2_pipelined_lanes.log)
 #endif
 #ifndef MPC_DYNAMIC
 // direct class: 1 = persistent grid, groups pull instances from an atomic counter.  Built, parity

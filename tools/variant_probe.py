@@ -12,6 +12,7 @@ import torch
 from mpc_limx_control_b200.engine import Engine
 N, TS = (50 if "n50" in args else 20 if "n20" in args else 10), 0.005
 standing = "standing" in args
+pipelined = "pipelined" in args
 Bs = [int(a) for a in args if a.isdigit()] or [4096, 65536]
 eng = Engine(horizon=N, max_batch=max(Bs))
 out = []
@@ -20,7 +21,7 @@ for B in Bs:
     t = {k: torch.from_numpy(d[k]).cuda() for k in ("x0", "x_ref", "feet", "iter")}
     F = torch.empty((B, N, 6), dtype=torch.float64, device="cuda")
     st = torch.empty(B, dtype=torch.int32, device="cuda"); it = torch.empty(B, dtype=torch.int32, device="cuda")
-    call = eng.bind_solve(t["x0"], t["x_ref"], t["feet"], it=t["iter"], forces=F, status=st, iters=it)
+    call = eng.bind_solve(t["x0"], t["x_ref"], t["feet"], it=t["iter"], forces=F, status=st, iters=it, pipelined=pipelined)
     for _ in range(10):
         call()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -30,7 +31,9 @@ for B in Bs:
         torch.cuda.synchronize(); e0.record()
         for _ in range(n):
             call()
+        if pipelined:
+            eng.join()
         e1.record(); torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1) * 1e3 / n)
     out.append(f"B {B}: {best:.2f} us {B/best:.1f} M/s (bad {int((st != 0).sum())})")
-print(os.path.basename(_capi.LIB_PATH), f"N={N} standing={standing}", " | ".join(out))
+print(os.path.basename(_capi.LIB_PATH), f"N={N} standing={standing} pipelined={pipelined}", " | ".join(out))
