@@ -379,10 +379,32 @@ def run_gpu(args, cfg):
             host_calls[j % nh]()      # one mpc_b200_tron1_solve_host: inputs over PCIe, solve, results back, sync
         torch.cuda.synchronize()
         te = max_over_ranks(time.perf_counter() - t0)
-        e2e = {"value": B_total * Ke / te, "unit": "solves/s", "h2d_bytes_per_step": B_total * (104 + 104 * (N + 1) + 48 + 4),
+        sync_value = B_total * Ke / te
+        sync_path = "zero-copy (kernel reads/writes the pinned host buffers over PCIe)" if eng.last_host_path() else "staged copies"
+        # the same batches through the asynchronous host entry: queue Ke independent batches (pinned host inputs read by the
+        # kernels over PCIe, results through per-lane device buffers + copy engine into the pinned host outputs), wait once.
+        # Every input byte crosses PCIe and every result byte is back in host memory inside the timed region.
+        from mpc_limx_control_b200.engine import wait as eng_wait
+        acalls = [bind_solve_host(eng, pj["x0"], pj["x_ref"], pj["feet"], it=pj["iter"], forces=out[0], status=out[1], iters=out[2],
+                                  asynchronous=True) for (dj, pj, out) in keep]
+        for j in range(max(3, min(W, 8))):
+            acalls[j % nh]()
+        eng_wait(eng)
+        barrier()
+        t0 = time.perf_counter()
+        for j in range(Ke):
+            acalls[j % nh]()
+        eng_wait(eng)
+        te = max_over_ranks(time.perf_counter() - t0)
+        async_value = B_total * Ke / te
+        async_path = ("mpc_b200_tron1_solve_host_async x steps + mpc_b200_wait: pinned host inputs read by the kernels over PCIe, results "
+                      "through device buffers + copy engine into pinned host outputs, consecutive batches overlapped")
+        # both are public entry points; the headline is the one a caller with this batch shape would use (the better one)
+        e2e = {"value": max(async_value, sync_value), "unit": "solves/s", "h2d_bytes_per_step": B_total * (104 + 104 * (N + 1) + 48 + 4),
                "d2h_bytes_per_step": B_total * (48 * N + 8), "steps": Ke,
-               "path": "zero-copy (kernel reads/writes the pinned host buffers over PCIe)" if eng.last_host_path() else "staged copies",
-               "host_batches": f"{nh} distinct pinned input/output batches in rotation"}
+               "path": async_path if async_value >= sync_value else "mpc_b200_tron1_solve_host per step: " + sync_path,
+               "host_batches": f"{nh} distinct pinned input/output batches in rotation",
+               "asynchronous_entry_value": async_value, "synchronous_entry_value": sync_value, "synchronous_entry_path": sync_path}
         if N == 10:
             # the same call forced onto the staged-copy path (what a caller with pageable buffers gets), for comparison
             eng.set_host_mode(Engine.HOST_STAGED)
@@ -438,7 +460,7 @@ def run_gpu(args, cfg):
     clocks = sampler.stop() if sampler else None
 
     # ---- the other two regimes of the headline workload, first-class (config 2 only): short device-timed runs ----
-    if args.config == "2" and rank == 0:
+    if args.config == "2" and rank == 0 and not args.no_extras:
         for key, cid in (("standing", "2s"), ("stressed", "2x")):
             c2 = CONFIGS[cid]
             eng2 = Engine(horizon=N, max_batch=B, device=local, Ts=c2["Ts"], mu=c2["mu"])
@@ -476,7 +498,7 @@ def run_gpu(args, cfg):
 
     # ---- single-instance latency: host call -> forces on host, B = 1 (horizon 10 configs) ----------------
     latency = None
-    if N == 10 and not rollout:
+    if N == 10 and not rollout and not args.no_extras:
         dj, pj, out = keep[0]
         one = {k: torch.from_numpy(dj[k][:1].copy()).pin_memory() for k in ("x0", "x_ref", "feet", "iter")}
         F1 = torch.empty((1, N, 6), dtype=torch.float64).pin_memory()
@@ -524,9 +546,10 @@ def run_gpu(args, cfg):
         if ent and ent.get("batch") == B:
             traffic = ent.get("dram_bytes_per_launch")
             if ent.get("executed_fp64_flops_per_launch"):
-                ncu_exec = {"flops_per_solve": ent["executed_fp64_flops_per_launch"] / B, "source": ent.get("source"),
+                per_launch = B * (cfg["steps"] if rollout else 1)      # solves one launch performs
+                ncu_exec = {"flops_per_solve": ent["executed_fp64_flops_per_launch"] / per_launch, "source": ent.get("source"),
                             "counts": "thread-level DFMA x2 + DMUL + DADD (DMMA is not in these counters)",
-                            "formula_over_ncu": (f_exec - f_tensor) / (ent["executed_fp64_flops_per_launch"] / B)}
+                            "formula_over_ncu": (f_exec - f_tensor) / (ent["executed_fp64_flops_per_launch"] / per_launch)}
     except Exception:
         pass
 
@@ -599,6 +622,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--latency-calls", type=int, default=10000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the standing / stressed / latency sections (profiling runs)")
     ap.add_argument("--serialized", action="store_true", help="time the stream-ordered device entry instead of the pipelined one")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -138,6 +138,16 @@ int mpc_b200_tron1_solve_host(mpc_b200_engine *e, int B, const double *x0, const
                               const double *feet, const uint8_t *contact, const int32_t *iter,
                               double *forces, int32_t *status, int32_t *iters);
 
+/* Asynchronous host-buffer entry for a stream of independent batches (SURVEY.md section 8b "async enqueue + wait pair"):
+ * returns as soon as the work is queued on one of the engine's six lanes; mpc_b200_wait blocks until every queued batch
+ * is solved and its results are in the caller's arrays.  Every buffer must be pinned / registered.  Inputs are read
+ * zero-copy by the kernel; results go through per-lane device buffers and the copy engine, so that one batch's
+ * copy-back overlaps the next batch's reads.  Buffers of a batch must not be touched between the call and the wait. */
+int mpc_b200_tron1_solve_host_async(mpc_b200_engine *e, int B, const double *x0, const double *x_ref, const double *feet,
+                                    const uint8_t *contact, const int32_t *iter, double *forces, int32_t *status,
+                                    int32_t *iters);
+int mpc_b200_wait(mpc_b200_engine *e);
+
 /* Single-process multi-GPU batch entry (the reference has no counterpart: it solves one robot per
  * call, include/mpcQP.h:63,113).  engines[0..G) are engines of the SAME horizon and parameters on DIFFERENT devices, each
  * with max_batch >= its share.  The batch is block-partitioned by instance -- GPU g owns [g*B/G + min(g, B%G), ...), the

@@ -617,6 +617,9 @@ struct mpc_b200_engine {
     cudaEvent_t lane_in[kLanes] = {}, lane_done[kLanes] = {};
     bool lane_busy[kLanes] = {};
     unsigned lane_next = 0;
+    // asynchronous host entry (mpc_b200_tron1_solve_host_async): per-lane device result buffers, allocated on first use
+    double* d_lane_forces = nullptr;
+    int32_t *d_lane_status = nullptr, *d_lane_iters = nullptr;
     double* d_condense_ws = nullptr;                         // horizon-50 parity dump: packed 300 x 300 workspace, grown on demand
     size_t condense_ws_bytes = 0;
     double* d_extA = nullptr;                                // global-memory factor slabs (N = 50 double support)
@@ -839,6 +842,7 @@ int mpc_b200_destroy(mpc_b200_engine* e) {
     cudaFree(e->d_small);
     cudaFree(e->d_extA);
     cudaFree(e->d_condense_ws);
+    cudaFree(e->d_lane_forces); cudaFree(e->d_lane_status); cudaFree(e->d_lane_iters);
     for (int i = 0; i < mpc_b200_engine::kLanes; ++i) {
         if (e->lane[i]) { cudaStreamSynchronize(e->lane[i]); cudaStreamDestroy(e->lane[i]); }
         if (e->lane_in[i]) cudaEventDestroy(e->lane_in[i]);
@@ -1146,6 +1150,63 @@ int mpc_b200_tron1_solve_host_multi(mpc_b200_engine* const* engines, int G, int 
     work(0);
     for (auto& t : th) t.join();
     for (int g = 0; g < G; ++g) if (rc[g]) return rc[g];
+    return MPC_B200_OK;
+}
+
+int mpc_b200_tron1_solve_host_async(mpc_b200_engine* e, int B, const double* x0, const double* x_ref, const double* feet,
+                                    const uint8_t* contact, const int32_t* iter, double* forces, int32_t* status, int32_t* iters) {
+    if (!e || !x0 || !x_ref || !feet || !forces || B < 1) return set_err(e, MPC_B200_EINVAL, "solve_host_async: bad argument");
+    if ((contact == nullptr) == (iter == nullptr)) return set_err(e, MPC_B200_EINVAL, "solve_host_async: pass exactly one of contact / iter");
+    if (B > e->max_batch) return set_err(e, MPC_B200_ECAPACITY, "solve_host_async: B > max_batch");
+    CU(e, cudaSetDevice(e->device));
+    const int N = e->N;
+    const size_t fstride = (e->C.per_step_feet && e->C.ltv) ? 6 * (size_t)N : 6;
+    const void* a0 = device_view(x0);
+    const void* a1 = device_view(x_ref);
+    const void* a3 = device_view(feet);
+    const void* a4 = contact ? device_view(contact) : device_view(iter);
+    if (!a0 || !a1 || !a3 || !a4 || !device_view(forces) || (status && !device_view(status)) || (iters && !device_view(iters)))
+        return set_err(e, MPC_B200_EINVAL, "solve_host_async: every buffer must be pinned (cudaHostAlloc / mpc_b200_pin_host_buffer)");
+    (void)fstride;
+    if (!e->d_lane_forces) {
+        const size_t L = mpc_b200_engine::kLanes, mb = (size_t)e->max_batch;
+        if (cudaMalloc(&e->d_lane_forces, sizeof(double) * 6 * N * mb * L) != cudaSuccess ||
+            cudaMalloc(&e->d_lane_status, sizeof(int32_t) * mb * L) != cudaSuccess ||
+            cudaMalloc(&e->d_lane_iters, sizeof(int32_t) * mb * L) != cudaSuccess) {
+            cudaGetLastError();
+            cudaFree(e->d_lane_forces); cudaFree(e->d_lane_status); cudaFree(e->d_lane_iters);
+            e->d_lane_forces = nullptr; e->d_lane_status = e->d_lane_iters = nullptr;
+            return set_err(e, MPC_B200_ENOMEM, "solve_host_async: result buffers");
+        }
+    }
+    const int l = (int)(e->lane_next++ % mpc_b200_engine::kLanes);
+    const size_t mb = (size_t)e->max_batch;
+    double* dF = e->d_lane_forces + 6 * (size_t)N * mb * l;
+    int32_t* dS = e->d_lane_status + mb * l;
+    int32_t* dI = e->d_lane_iters + mb * l;
+    const int cls = schedule_large_class(e, B, contact, iter);
+    // inputs: read by the kernel straight from the pinned host arrays (TMA bulk copies over PCIe).  Results: device buffers
+    // of this lane, then the copy engine (SM-issued stores to host memory are 4x slower than the copy engine on the measured
+    // hosts); lanes overlap, so one lane's copy-back runs under another lane's reads -- PCIe is full duplex.
+    const int rc = dispatch_solve(e, B, (const double*)a0, (const double*)a1, (const double*)a3, contact ? (const uint8_t*)a4 : nullptr,
+                                  contact ? nullptr : (const int32_t*)a4, dF, dS, dI, e->lane[l], mpc_b200_engine::kPipe + 1 + l,
+                                  (1 + l) * e->max_batch, nullptr, nullptr, 0, cls);
+    if (rc) return rc;
+    e->lane_busy[l] = true;
+    CU(e, cudaMemcpyAsync(forces, dF, sizeof(double) * 6 * N * (size_t)B, cudaMemcpyDeviceToHost, e->lane[l]));
+    if (status) CU(e, cudaMemcpyAsync(status, dS, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, e->lane[l]));
+    if (iters) CU(e, cudaMemcpyAsync(iters, dI, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, e->lane[l]));
+    return MPC_B200_OK;
+}
+
+int mpc_b200_wait(mpc_b200_engine* e) {
+    if (!e) return MPC_B200_EINVAL;
+    CU(e, cudaSetDevice(e->device));
+    for (int l = 0; l < mpc_b200_engine::kLanes; ++l) {
+        if (!e->lane_busy[l]) continue;
+        CU(e, cudaStreamSynchronize(e->lane[l]));
+        e->lane_busy[l] = false;
+    }
     return MPC_B200_OK;
 }
 

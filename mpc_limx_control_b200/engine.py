@@ -233,13 +233,19 @@ def _host_ptr(a):
     return C.c_void_p(a.ctypes.data)
 
 
-def bind_solve_host(eng, x0, x_ref, feet, contact=None, it=None, forces=None, status=None, iters=None):
+def wait(eng):
+    """Block until every batch queued with the asynchronous host entry is solved and copied back (mpc_b200_wait)."""
+    _capi.check(eng.lib.mpc_b200_wait(eng.h), eng.h)
+
+
+def bind_solve_host(eng, x0, x_ref, feet, contact=None, it=None, forces=None, status=None, iters=None, asynchronous=False):
     """Pre-marshalled mpc_b200_tron1_solve_host call (buffers: contiguous float64/uint8/int32 numpy arrays or
-    CPU torch tensors, pinned recommended; they must stay alive and unmoved)."""
+    CPU torch tensors, pinned recommended; they must stay alive and unmoved).  asynchronous=True binds
+    mpc_b200_tron1_solve_host_async (pinned buffers required; results valid after wait(eng))."""
     B = x0.shape[0]
     args = (eng.h, B, _host_ptr(x0), _host_ptr(x_ref), _host_ptr(feet), _host_ptr(contact), _host_ptr(it), _host_ptr(forces),
             _host_ptr(status), _host_ptr(iters))
-    fn = eng.lib.mpc_b200_tron1_solve_host
+    fn = eng.lib.mpc_b200_tron1_solve_host_async if asynchronous else eng.lib.mpc_b200_tron1_solve_host
     keep = (x0, x_ref, feet, contact, it, forces, status, iters)
 
     def call(_fn=fn, _args=args, _keep=keep):

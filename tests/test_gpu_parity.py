@@ -709,3 +709,42 @@ def test_pipelined_device_entry_matches_ordered_calls(torch_cuda, N, B, standing
     torch.cuda.synchronize()
     assert np.array_equal(F.cpu().numpy(), want[0][0])
     eng.close()
+
+
+@pytest.mark.parametrize("N,B,standing_every", [(10, 2000, 4), (50, 260, 3)])
+def test_async_host_entry_matches_device(torch_cuda, N, B, standing_every):
+    """mpc_b200_tron1_solve_host_async + mpc_b200_wait: nine independent batches in pinned host arrays queued back to back
+    (more than the six lanes: a lane's buffers are reused in stream order), results bit-identical to the device call;
+    pageable buffers are refused."""
+    torch = torch_cuda
+    from mpc_limx_control_b200 import _capi
+    from mpc_limx_control_b200.engine import bind_solve_host, wait
+    Ts = 0.005
+    eng = make_engine(N, B, Ts=Ts)
+    want, calls, outs = [], [], []
+    for k in range(9):
+        d = synth.tron1_batch(700 + k, B, N, Ts)
+        d["iter"][k % standing_every::standing_every] = -1
+        t = to_dev(torch, d)
+        F, st, it = eng.solve(t["x0"], t["x_ref"], t["feet"], it=t["iter"])
+        torch.cuda.synchronize()
+        want.append((F.cpu().numpy(), st.cpu().numpy(), it.cpu().numpy()))
+        pin = {k2: torch.from_numpy(np.ascontiguousarray(d[k2])).pin_memory() for k2 in ("x0", "x_ref", "feet", "iter")}
+        o = (torch.zeros((B, N, 6), dtype=torch.float64).pin_memory(), torch.full((B,), -5, dtype=torch.int32).pin_memory(),
+             torch.zeros(B, dtype=torch.int32).pin_memory())
+        outs.append((pin, o))
+        calls.append(bind_solve_host(eng, pin["x0"], pin["x_ref"], pin["feet"], it=pin["iter"], forces=o[0], status=o[1], iters=o[2],
+                                     asynchronous=True))
+    for rep in range(2):
+        for c in calls:
+            c()
+        wait(eng)
+        for (F, st, it), (_, o) in zip(want, outs):
+            assert np.array_equal(o[0].numpy(), F) and np.array_equal(o[1].numpy(), st) and np.array_equal(o[2].numpy(), it)
+            o[0].zero_(); o[1].fill_(-5)
+    # pageable buffers: refused (the asynchronous entry has no staging)
+    d = synth.tron1_batch(1, 8, N, Ts)
+    with pytest.raises(_capi.MpcB200Error):
+        bind_solve_host(eng, d["x0"], d["x_ref"], d["feet"], it=d["iter"], forces=np.zeros((8, N, 6)), status=np.zeros(8, np.int32),
+                        iters=np.zeros(8, np.int32), asynchronous=True)()
+    eng.close()

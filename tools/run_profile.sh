@@ -8,7 +8,7 @@ python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/${T}_bench_re
 for c in 2s 2x 3 4 5; do
   python bench.py --config $c > gpurun_out/${T}_bench_config$c.json 2> gpurun_out/${T}_bench_config$c.err
 done
-SHORT="--steps 5 --warmup 3 --latency-calls 10 --no-cpu-baseline"
+SHORT="--steps 5 --warmup 3 --latency-calls 10 --no-cpu-baseline --no-extras"
 python bench.py $SHORT > gpurun_out/${T}_plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${T}_launches.csv python bench.py $SHORT > gpurun_out/${T}_ncu_1.log 2>&1
 python bench.py $SHORT > gpurun_out/${T}_plain.log 2>&1 && \
