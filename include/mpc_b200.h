@@ -146,6 +146,11 @@ int mpc_b200_tron1_solve_host(mpc_b200_engine *e, int B, const double *x0, const
 int mpc_b200_tron1_solve_host_async(mpc_b200_engine *e, int B, const double *x0, const double *x_ref, const double *feet,
                                     const uint8_t *contact, const int32_t *iter, double *forces, int32_t *status,
                                     int32_t *iters);
+/* controller-shaped counterpart (arguments as mpc_b200_tron1_control_host): 228 bytes per instance cross PCIe, the first-step
+ * forces are written by the kernel straight into the pinned u0 array */
+int mpc_b200_tron1_control_host_async(mpc_b200_engine *e, int B, const double *x0, const double *omega_yaw,
+                                      const double *velocity_x, const double *feet, const uint8_t *contact,
+                                      const int32_t *iter, double *u0, int32_t *status, int32_t *iters);
 int mpc_b200_wait(mpc_b200_engine *e);
 
 /* Single-process multi-GPU batch entry (the reference has no counterpart: it solves one robot per

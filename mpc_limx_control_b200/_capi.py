@@ -17,7 +17,7 @@ SYMBOLS = [
     "mpc_b200_version", "mpc_b200_strerror", "mpc_b200_device_count", "mpc_b200_measure_fp64_peak",
     "mpc_b200_tron1_default_params", "mpc_b200_create", "mpc_b200_destroy", "mpc_b200_last_error",
     "mpc_b200_launch_count", "mpc_b200_set_host_mode", "mpc_b200_last_host_path", "mpc_b200_pin_host_buffer", "mpc_b200_unpin_host_buffer", "mpc_b200_contact_schedule_device", "mpc_b200_tron1_solve_device",
-    "mpc_b200_tron1_solve_host", "mpc_b200_tron1_solve_device_pipelined", "mpc_b200_join", "mpc_b200_tron1_solve_host_async", "mpc_b200_wait", "mpc_b200_tron1_solve_host_multi", "mpc_b200_tron1_condense_device",
+    "mpc_b200_tron1_solve_host", "mpc_b200_tron1_solve_device_pipelined", "mpc_b200_join", "mpc_b200_tron1_solve_host_async", "mpc_b200_tron1_control_host_async", "mpc_b200_wait", "mpc_b200_tron1_solve_host_multi", "mpc_b200_tron1_condense_device",
     "mpc_b200_tron1_reference_device", "mpc_b200_tron1_rollout_device", "mpc_b200_tron1_control_host",
     "mpc_b200_leg_default_model", "mpc_b200_swing_default_params", "mpc_b200_leg_fk_device", "mpc_b200_swing_step_device",
     "mpc_b200_grf_to_torque_device", "mpc_b200_leg_fk_host", "mpc_b200_swing_step_host", "mpc_b200_grf_to_torque_host",
@@ -101,6 +101,7 @@ def lib():
         L.mpc_b200_join.argtypes = [vp, vp]
         L.mpc_b200_tron1_solve_host_async.argtypes = [vp, ip, vp, vp, vp, vp, vp, vp, vp, vp]
         L.mpc_b200_wait.argtypes = [vp]
+        L.mpc_b200_tron1_control_host_async.argtypes = [vp, ip] + [vp] * 9
         L.mpc_b200_tron1_solve_host_multi.argtypes = [C.POINTER(vp), ip, ip, vp, vp, vp, vp, vp, vp, vp, vp]
         L.mpc_b200_tron1_condense_device.argtypes = [vp, ip, vp, vp, vp, vp, vp, vp, vp, vp]
         L.mpc_b200_tron1_reference_device.argtypes = [vp, ip, vp, vp, vp, vp, vp]

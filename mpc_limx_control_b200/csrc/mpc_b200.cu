@@ -1153,21 +1153,32 @@ int mpc_b200_tron1_solve_host_multi(mpc_b200_engine* const* engines, int G, int 
     return MPC_B200_OK;
 }
 
-int mpc_b200_tron1_solve_host_async(mpc_b200_engine* e, int B, const double* x0, const double* x_ref, const double* feet,
-                                    const uint8_t* contact, const int32_t* iter, double* forces, int32_t* status, int32_t* iters) {
-    if (!e || !x0 || !x_ref || !feet || !forces || B < 1) return set_err(e, MPC_B200_EINVAL, "solve_host_async: bad argument");
-    if ((contact == nullptr) == (iter == nullptr)) return set_err(e, MPC_B200_EINVAL, "solve_host_async: pass exactly one of contact / iter");
-    if (B > e->max_batch) return set_err(e, MPC_B200_ECAPACITY, "solve_host_async: B > max_batch");
-    CU(e, cudaSetDevice(e->device));
+// shared body of the two asynchronous host entries (cmd: controller-shaped, x_ref generated on the device, u0 out)
+static int solve_host_async_impl(mpc_b200_engine* e, int B, const double* x0, const double* x_ref, const double* oy, const double* vx,
+                                 const double* feet, const uint8_t* contact, const int32_t* iter, double* out, int32_t* status,
+                                 int32_t* iters, bool cmd) {
     const int N = e->N;
-    const size_t fstride = (e->C.per_step_feet && e->C.ltv) ? 6 * (size_t)N : 6;
     const void* a0 = device_view(x0);
-    const void* a1 = device_view(x_ref);
+    const void* a1 = cmd ? device_view(oy) : device_view(x_ref);
+    const void* a2 = cmd ? device_view(vx) : a1;
     const void* a3 = device_view(feet);
     const void* a4 = contact ? device_view(contact) : device_view(iter);
-    if (!a0 || !a1 || !a3 || !a4 || !device_view(forces) || (status && !device_view(status)) || (iters && !device_view(iters)))
-        return set_err(e, MPC_B200_EINVAL, "solve_host_async: every buffer must be pinned (cudaHostAlloc / mpc_b200_pin_host_buffer)");
-    (void)fstride;
+    void* o0 = device_view(out);
+    void* o1 = status ? device_view(status) : nullptr;
+    void* o2 = iters ? device_view(iters) : nullptr;
+    if (!a0 || !a1 || !a2 || !a3 || !a4 || !o0 || (status && !o1) || (iters && !o2))
+        return set_err(e, MPC_B200_EINVAL, "asynchronous host entry: every buffer must be pinned (cudaHostAlloc / mpc_b200_pin_host_buffer)");
+    const int l = (int)(e->lane_next++ % mpc_b200_engine::kLanes);
+    const int cls = schedule_large_class(e, B, contact, iter);
+    if (cmd) {
+        // 56 result bytes per instance: written by the kernel straight into the pinned host arrays
+        const int rc = dispatch_solve(e, B, (const double*)a0, nullptr, (const double*)a3, contact ? (const uint8_t*)a4 : nullptr,
+                                      contact ? nullptr : (const int32_t*)a4, (double*)o0, (int32_t*)o1, (int32_t*)o2, e->lane[l],
+                                      mpc_b200_engine::kPipe + 1 + l, (1 + l) * e->max_batch, (const double*)a1, (const double*)a2, 1, cls);
+        if (rc) return rc;
+        e->lane_busy[l] = true;
+        return MPC_B200_OK;
+    }
     if (!e->d_lane_forces) {
         const size_t L = mpc_b200_engine::kLanes, mb = (size_t)e->max_batch;
         if (cudaMalloc(&e->d_lane_forces, sizeof(double) * 6 * N * mb * L) != cudaSuccess ||
@@ -1176,15 +1187,13 @@ int mpc_b200_tron1_solve_host_async(mpc_b200_engine* e, int B, const double* x0,
             cudaGetLastError();
             cudaFree(e->d_lane_forces); cudaFree(e->d_lane_status); cudaFree(e->d_lane_iters);
             e->d_lane_forces = nullptr; e->d_lane_status = e->d_lane_iters = nullptr;
-            return set_err(e, MPC_B200_ENOMEM, "solve_host_async: result buffers");
+            return set_err(e, MPC_B200_ENOMEM, "asynchronous host entry: result buffers");
         }
     }
-    const int l = (int)(e->lane_next++ % mpc_b200_engine::kLanes);
     const size_t mb = (size_t)e->max_batch;
     double* dF = e->d_lane_forces + 6 * (size_t)N * mb * l;
     int32_t* dS = e->d_lane_status + mb * l;
     int32_t* dI = e->d_lane_iters + mb * l;
-    const int cls = schedule_large_class(e, B, contact, iter);
     // inputs: read by the kernel straight from the pinned host arrays (TMA bulk copies over PCIe).  Results: device buffers
     // of this lane, then the copy engine (SM-issued stores to host memory are 4x slower than the copy engine on the measured
     // hosts); lanes overlap, so one lane's copy-back runs under another lane's reads -- PCIe is full duplex.
@@ -1193,10 +1202,29 @@ int mpc_b200_tron1_solve_host_async(mpc_b200_engine* e, int B, const double* x0,
                                   (1 + l) * e->max_batch, nullptr, nullptr, 0, cls);
     if (rc) return rc;
     e->lane_busy[l] = true;
-    CU(e, cudaMemcpyAsync(forces, dF, sizeof(double) * 6 * N * (size_t)B, cudaMemcpyDeviceToHost, e->lane[l]));
+    CU(e, cudaMemcpyAsync(out, dF, sizeof(double) * 6 * N * (size_t)B, cudaMemcpyDeviceToHost, e->lane[l]));
     if (status) CU(e, cudaMemcpyAsync(status, dS, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, e->lane[l]));
     if (iters) CU(e, cudaMemcpyAsync(iters, dI, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, e->lane[l]));
     return MPC_B200_OK;
+}
+
+int mpc_b200_tron1_solve_host_async(mpc_b200_engine* e, int B, const double* x0, const double* x_ref, const double* feet,
+                                    const uint8_t* contact, const int32_t* iter, double* forces, int32_t* status, int32_t* iters) {
+    if (!e || !x0 || !x_ref || !feet || !forces || B < 1) return set_err(e, MPC_B200_EINVAL, "solve_host_async: bad argument");
+    if ((contact == nullptr) == (iter == nullptr)) return set_err(e, MPC_B200_EINVAL, "solve_host_async: pass exactly one of contact / iter");
+    if (B > e->max_batch) return set_err(e, MPC_B200_ECAPACITY, "solve_host_async: B > max_batch");
+    CU(e, cudaSetDevice(e->device));
+    return solve_host_async_impl(e, B, x0, x_ref, nullptr, nullptr, feet, contact, iter, forces, status, iters, false);
+}
+
+int mpc_b200_tron1_control_host_async(mpc_b200_engine* e, int B, const double* x0, const double* omega_yaw, const double* velocity_x,
+                                      const double* feet, const uint8_t* contact, const int32_t* iter, double* u0, int32_t* status,
+                                      int32_t* iters) {
+    if (!e || !x0 || !omega_yaw || !velocity_x || !feet || !u0 || B < 1) return set_err(e, MPC_B200_EINVAL, "control_host_async: bad argument");
+    if ((contact == nullptr) == (iter == nullptr)) return set_err(e, MPC_B200_EINVAL, "control_host_async: pass exactly one of contact / iter");
+    if (B > e->max_batch) return set_err(e, MPC_B200_ECAPACITY, "control_host_async: B > max_batch");
+    CU(e, cudaSetDevice(e->device));
+    return solve_host_async_impl(e, B, x0, nullptr, omega_yaw, velocity_x, feet, contact, iter, u0, status, iters, true);
 }
 
 int mpc_b200_wait(mpc_b200_engine* e) {

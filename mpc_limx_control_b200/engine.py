@@ -255,12 +255,12 @@ def bind_solve_host(eng, x0, x_ref, feet, contact=None, it=None, forces=None, st
     return call
 
 
-def bind_control_host(eng, x0, omega_yaw, velocity_x, feet, contact=None, it=None, u0=None, status=None, iters=None):
-    """Pre-marshalled mpc_b200_tron1_control_host call (see bind_solve_host)."""
+def bind_control_host(eng, x0, omega_yaw, velocity_x, feet, contact=None, it=None, u0=None, status=None, iters=None, asynchronous=False):
+    """Pre-marshalled mpc_b200_tron1_control_host call (see bind_solve_host); asynchronous=True binds the _async entry."""
     B = x0.shape[0]
     args = (eng.h, B, _host_ptr(x0), _host_ptr(omega_yaw), _host_ptr(velocity_x), _host_ptr(feet), _host_ptr(contact),
             _host_ptr(it), _host_ptr(u0), _host_ptr(status), _host_ptr(iters))
-    fn = eng.lib.mpc_b200_tron1_control_host
+    fn = eng.lib.mpc_b200_tron1_control_host_async if asynchronous else eng.lib.mpc_b200_tron1_control_host
     keep = (x0, omega_yaw, velocity_x, feet, contact, it, u0, status, iters)
 
     def call(_fn=fn, _args=args, _keep=keep):

@@ -748,3 +748,30 @@ def test_async_host_entry_matches_device(torch_cuda, N, B, standing_every):
         bind_solve_host(eng, d["x0"], d["x_ref"], d["feet"], it=d["iter"], forces=np.zeros((8, N, 6)), status=np.zeros(8, np.int32),
                         iters=np.zeros(8, np.int32), asynchronous=True)()
     eng.close()
+
+
+def test_async_control_entry_matches_synchronous(torch_cuda):
+    """mpc_b200_tron1_control_host_async: controller-shaped batches queued on the lanes, first-step forces written by the
+    kernels straight into pinned host arrays; bit-identical to the synchronous controller-shaped call."""
+    torch = torch_cuda
+    from mpc_limx_control_b200.engine import bind_control_host, wait
+    N, B, Ts = 10, 1200, 0.005
+    eng = make_engine(N, B, Ts=Ts)
+    sets = []
+    for k in range(8):
+        d = synth.tron1_batch(800 + k, B, N, Ts)
+        d["iter"][k % 5::5] = -1
+        pin = {k2: torch.from_numpy(np.ascontiguousarray(d[k2])).pin_memory() for k2 in ("x0", "feet", "iter", "omega_yaw", "velocity_x")}
+        u_s = torch.zeros((B, 6), dtype=torch.float64).pin_memory(); s_s = torch.zeros(B, dtype=torch.int32).pin_memory(); i_s = torch.zeros(B, dtype=torch.int32).pin_memory()
+        bind_control_host(eng, pin["x0"], pin["omega_yaw"], pin["velocity_x"], pin["feet"], it=pin["iter"], u0=u_s, status=s_s, iters=i_s)()
+        u_a = torch.zeros((B, 6), dtype=torch.float64).pin_memory(); s_a = torch.full((B,), -3, dtype=torch.int32).pin_memory(); i_a = torch.zeros(B, dtype=torch.int32).pin_memory()
+        call = bind_control_host(eng, pin["x0"], pin["omega_yaw"], pin["velocity_x"], pin["feet"], it=pin["iter"], u0=u_a, status=s_a, iters=i_a,
+                                 asynchronous=True)
+        sets.append((pin, (u_s, s_s, i_s), (u_a, s_a, i_a), call))
+    for _, _, _, call in sets:
+        call()
+    wait(eng)
+    for _, (u_s, s_s, i_s), (u_a, s_a, i_a), _ in sets:
+        assert (s_s.numpy() == 0).all()
+        assert np.array_equal(u_a.numpy(), u_s.numpy()) and np.array_equal(s_a.numpy(), s_s.numpy()) and np.array_equal(i_a.numpy(), i_s.numpy())
+    eng.close()
