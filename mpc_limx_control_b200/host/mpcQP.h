@@ -131,6 +131,18 @@ public:
         return true;
     }
 
+    // asynchronous batch entry for queues of independent batches (pinned buffers; up to six batches in flight): queue with
+    // solveBatchAsync, collect with waitAll
+    void solveBatchAsync(int B, const double* x0s, const double* x_refs, const double* feets, const uint8_t* contacts,
+                         const int32_t* iters_in, double* forces_out, int32_t* status_out, int32_t* iters_out) {
+        int rc = mpc_b200_tron1_solve_host_async(eng, B, x0s, x_refs, feets, contacts, iters_in, forces_out, status_out, iters_out);
+        if (rc) throw DeviceError(rc, std::string("mpcQP::solveBatchAsync: ") + mpc_b200_strerror(rc) + " (" + mpc_b200_last_error(eng) + ")");
+    }
+    void waitAll() {
+        int rc = mpc_b200_wait(eng);
+        if (rc) throw DeviceError(rc, std::string("mpcQP::waitAll: ") + mpc_b200_strerror(rc) + " (" + mpc_b200_last_error(eng) + ")");
+    }
+
     // reference-literal continuous model (include/mpcQP.h:139-181): Ac 13x13, Bc 13x3, one support foot
     static void literalModel(const Vector3d& pos, const Vector3d& foot, double mass, MatrixXd& Ac, MatrixXd& Bc) {
         const double dx = foot(0) - pos(0), dy = foot(1) - pos(1), dz = foot(2) - pos(2);
