@@ -98,7 +98,10 @@ int mpc_b200_contact_schedule_device(mpc_b200_engine *e, int B, const int32_t *d
  * d_status / d_iters may be NULL.
  * Stream contract: an engine is single-caller.  All calls on ONE engine must be stream-ordered and must not
  * overlap (same stream, or streams ordered by events): the capacity-overflow list, its counters and (horizon 50)
- * the global factor slabs are per-engine scratch.  Use one engine per concurrent stream. */
+ * the global factor slabs are per-engine scratch.  Use one engine per concurrent stream.
+ * Small batches: with B <= the device's SM count, double-support instances of horizon 10 (a standing robot) are
+ * solved by a latency-oriented kernel class (8 warps per instance).  Their forces agree with those of the same
+ * instance inside a larger batch to rounding, not bit for bit; all other results are independent of B. */
 int mpc_b200_tron1_solve_device(mpc_b200_engine *e, int B, const double *d_x0, const double *d_x_ref,
                                 const double *d_feet, const uint8_t *d_contact, const int32_t *d_iter,
                                 double *d_forces, int32_t *d_status, int32_t *d_iters, void *stream);

@@ -59,8 +59,16 @@ using namespace mpcb200;
 #ifndef MPC_TILED_N50
 #define MPC_TILED_N50 1
 #endif
-template <int N, int NC, bool AINL = true>
-using SolveWork = Tron1Work<N, NC, AINL, (N == 50 && MPC_TILED_N50 != 0)>;
+#ifndef MPC_N10_WPI_LAT
+// latency class of the double-support instances of horizon 10 (a standing robot, BASELINE configs[0]): batches that leave
+// SMs idle anyway (B <= number of SMs) run one instance per CTA on MPC_N10_WPI_LAT warps with the tiled tensor-core
+// factorisation instead of two warps on the register elimination.  Host call B = 1, standing: 37.6 -> 30.4 us p50
+// (profiles/r2_latency_class.log); at throughput batch sizes the two-warp class wins (same file).
+#define MPC_N10_WPI_LAT 8
+#endif
+// storage rule: tiled 8x8 layout (DMMA Cholesky) for horizon 50 and for groups of >= 4 warps on the 60-variable class of horizon 10
+template <int N, int NC, bool AINL = true, int WPI = 1>
+using SolveWork = Tron1Work<N, NC, AINL, ((N == 50 && MPC_TILED_N50 != 0) || (N == 10 && NC == 60 && WPI >= 4))>;
 
 // ------------------------------------------------------------------------------------------------
 // thread group = WPI warps cooperating on one instance
@@ -163,7 +171,7 @@ tron1_solve_kernel(const __grid_constant__ Tron1Const P, int B, const double* __
     // first_step_only: write u_0 (6 doubles per instance, include/mpcQP.h:118) instead of the whole horizon
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using Stage = CtaStage<N, IPC>;
-    using Work = SolveWork<N, NC, AINL>;
+    using Work = SolveWork<N, NC, AINL, WPI>;
     Stage& st = *reinterpret_cast<Stage*>(smem_raw);
     constexpr size_t stage_bytes = (sizeof(Stage) + 15) & ~size_t(15);
     Work* works = reinterpret_cast<Work*>(smem_raw + stage_bytes);
@@ -662,8 +670,8 @@ static int launch_solve(mpc_b200_engine* e, int B, const double* x0, const doubl
     // 1 = mixed / unknown (device entry point)
     auto ks = tron1_solve_kernel<N, 3 * N, WPI_S, IPC_S, MINB_S, false, true, MPC_DYNAMIC != 0>;
     auto kl = tron1_solve_kernel<N, 6 * N, WPI_L, IPC_L, MINB_L, true, AINL_L>;
-    const size_t smem_s = ((sizeof(CtaStage<N, IPC_S>) + 15) & ~size_t(15)) + sizeof(SolveWork<N, 3 * N, true>) * IPC_S;
-    const size_t smem_l = ((sizeof(CtaStage<N, IPC_L>) + 15) & ~size_t(15)) + sizeof(SolveWork<N, 6 * N, AINL_L>) * IPC_L;
+    const size_t smem_s = ((sizeof(CtaStage<N, IPC_S>) + 15) & ~size_t(15)) + sizeof(SolveWork<N, 3 * N, true, WPI_S>) * IPC_S;
+    const size_t smem_l = ((sizeof(CtaStage<N, IPC_L>) + 15) & ~size_t(15)) + sizeof(SolveWork<N, 6 * N, AINL_L, WPI_L>) * IPC_L;
     static std::atomic<bool> configured[64];      // per device; setting the attribute twice is harmless, so a lost race is too
     if (!configured[e->device & 63].load(std::memory_order_acquire)) {
         CU(e, cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
@@ -724,7 +732,10 @@ static int dispatch_solve(mpc_b200_engine* e, int B, const double* x0, const dou
     int32_t* ol = e->d_ovf_list + list_offset;
     int32_t* oc = e->d_ovf_count + 4 * slot;
     switch (e->N) {
-        case 10: return launch_solve<10, 1, 4, 4, 2, MPC_N10_IPC_L, true, MPC_N10_MINB_L>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only, cls_hint);
+        case 10:
+            if (B <= e->num_sms && cls_hint != 0)     // latency class for the double-support instances (see MPC_N10_WPI_LAT)
+                return launch_solve<10, 1, 4, 4, MPC_N10_WPI_LAT, 1, true, 1>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only, cls_hint);
+            return launch_solve<10, 1, 4, 4, 2, MPC_N10_IPC_L, true, MPC_N10_MINB_L>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only, cls_hint);
         case 20: return launch_solve<20, 2, 2, 2, 2, 2>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only, cls_hint);
         case 50: return launch_solve<50, MPC_N50_WPI_S, 1, 1, MPC_N50_WPI_L, 1, false, MPC_N50_MINB_L>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only, cls_hint);
         default: return set_err(e, MPC_B200_EINVAL, "unsupported horizon");

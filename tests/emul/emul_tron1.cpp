@@ -20,13 +20,13 @@ struct GrpSerial {
     void sync() const {}
 };
 
-template <int N, int NC>
+template <int N, int NC, bool TILED = (N == 50)>
 static int run_solve_nc(const Tron1Const& P, const double* x0, const double* xref, const double* feet,
                         const uint8_t* contact, double* forces, int* iters) {
     // same storage rule as the kernel wrapper (mpc_b200.cu: SolveWork): horizon 50 uses the tiled layout, so this build
     // checks the tile indexing, the blocked triangular solves and the padding (the tensor-core factorisation itself is
     // device code; chol_tiled_generic stands in with the same result layout)
-    using Work = Tron1Work<N, NC, true, (N == 50)>;
+    using Work = Tron1Work<N, NC, true, TILED>;
     auto* S = new Work();
     S->Aext = nullptr;
     S->x0 = x0;
@@ -133,6 +133,14 @@ int emul_tron1_solve(const mpc_b200_tron1_params* prm, int N, const double* x0, 
         case 50: return run_solve<50>(P, x0, xref, feet, contact, forces, iters);
         default: return -2;
     }
+}
+
+// the latency class of horizon 10 (mpc_b200.cu: MPC_N10_WPI_LAT) keeps the 60-variable system in the tiled layout
+int emul_tron1_solve_tiled60(const mpc_b200_tron1_params* prm, const double* x0, const double* xref,
+                             const double* feet, const uint8_t* contact, double* forces, int* iters) {
+    Tron1Const P;
+    if (make_tron1_const(*prm, P)) return -1;
+    return run_solve_nc<10, 60, true>(P, x0, xref, feet, contact, forces, iters);
 }
 
 int emul_tron1_dump(const mpc_b200_tron1_params* prm, int N, const double* x0, const double* xref,

@@ -57,6 +57,18 @@ def solve(p, N, x0, x_ref, feet, contact):
     return forces, st, it.value
 
 
+def solve_tiled60(p, x0, x_ref, feet, contact):
+    """Horizon 10, 60-variable capacity class in the tiled 8x8 storage (the latency class of the kernel wrapper)."""
+    N = 10
+    x0 = np.ascontiguousarray(x0, np.float64); x_ref = np.ascontiguousarray(x_ref, np.float64)
+    feet = np.ascontiguousarray(feet, np.float64); contact = np.ascontiguousarray(contact, np.uint8)
+    forces = np.zeros((N, 6)); it = C.c_int(0)
+    st = lib().emul_tron1_solve_tiled60(C.byref(p), x0.ctypes.data_as(_dp), x_ref.ctypes.data_as(_dp),
+                                        feet.ctypes.data_as(_dp), contact.ctypes.data_as(_u8),
+                                        forces.ctypes.data_as(_dp), C.byref(it))
+    return forces, st, it.value
+
+
 def dump(p, N, x0, x_ref, feet):
     x0 = np.ascontiguousarray(x0, np.float64); x_ref = np.ascontiguousarray(x_ref, np.float64)
     feet = np.ascontiguousarray(feet, np.float64)

@@ -73,6 +73,29 @@ def test_admm_fallback_path_tiled_horizon50():
     assert used_admm >= 1
 
 
+@pytest.mark.parametrize("max_newton,scale,mu", [(12, 1, 0.5), (12, 8, 0.2), (1, 8, 0.2)])
+def test_latency_class_tiled_storage_horizon10(max_newton, scale, mu):
+    """Small batches of double-support instances of horizon 10 run in the tiled 8x8 storage (mpc_b200.cu: MPC_N10_WPI_LAT):
+    same forces as the packed-storage path and as the oracle's active set, on the Newton path and (max_newton=1) the ADMM."""
+    N, Ts = 10, 0.02
+    d = synth.tron1_batch(77, 8, N, Ts, standing=True)
+    po = O.tron1_defaults(Ts=Ts, mu=mu); pe = E.default_params(Ts=Ts, mu=mu, max_newton=max_newton)
+    rng = np.random.default_rng(5)
+    for b in range(8):
+        x0 = d["x0"][b].copy(); x0[[0, 1, 6, 7, 8, 9, 10, 11]] *= scale
+        contact = np.ones((N, 2), np.uint8)
+        if b >= 4:                                   # ragged: some foot-steps in swing (nc < 60: padded tiles)
+            contact[rng.integers(0, N, 3), rng.integers(0, 2, 3)] = 0
+        c = O.tron1_condense(po, N, x0, d["x_ref"][b], d["feet"][b], want_pred=False)
+        A, lbA, ubA, lb, ub = O.tron1_constraints(po, N, contact)
+        u, info = O.qp_solve(c["H"], c["f"], A, lbA, ubA, lb, ub)
+        F, st, it = E.solve_tiled60(pe, x0, d["x_ref"][b], d["feet"][b], contact)
+        assert st == 0 and info["status"] == 0
+        assert np.abs(F.reshape(-1) - u).max() / max(1.0, np.abs(u).max()) < 1e-4
+        assert O.tron1_natural_residual(po, N, c["H"], c["f"], contact, F) < 1e-6
+        assert np.all(F.reshape(N, 2, 3)[contact == 0] == 0.0)
+
+
 def test_admm_fallback_path():
     """max_newton=1 forces every instance whose first face guess is wrong through ADMM + polish."""
     N, Ts, B = 10, 0.02, 12

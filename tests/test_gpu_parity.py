@@ -775,3 +775,45 @@ def test_async_control_entry_matches_synchronous(torch_cuda):
         assert (s_s.numpy() == 0).all()
         assert np.array_equal(u_a.numpy(), u_s.numpy()) and np.array_equal(s_a.numpy(), s_s.numpy()) and np.array_equal(i_a.numpy(), i_s.numpy())
     eng.close()
+
+
+@pytest.mark.parametrize("B", [1, 7, 148])
+def test_latency_class_small_standing_batches(torch_cuda, B):
+    """batches no larger than the SM count send their double-support instances to the latency class of horizon 10 (8 warps
+    per instance, tiled tensor-core factorisation; mpc_b200.cu: MPC_N10_WPI_LAT): every instance against the oracle's
+    active set, device and host entry bit-identical, and the same instances inside a large batch (two-warp register
+    elimination) agree to rounding"""
+    torch = torch_cuda
+    N, Ts = 10, 0.02
+    big = 1024
+    d = synth.tron1_batch(4242, big, N, Ts, standing=True)
+    d["x0"][:, [0, 1, 6, 7, 8, 9, 10, 11]] *= 4.0                       # pyramids bind: several Newton iterations
+    if B > 1:
+        d["iter"][1] = 3                                                # mixed batch: one walking instance (small class)
+    po = O.tron1_defaults(Ts=Ts, mu=0.3)
+    eng = make_engine(N, big, Ts=Ts, mu=0.3)
+    t = to_dev(torch, {k: v[:B] for k, v in d.items()})
+    F, st, it = eng.solve(t["x0"], t["x_ref"], t["feet"], it=t["iter"])
+    torch.cuda.synchronize()
+    F = F.cpu().numpy(); st = st.cpu().numpy()
+    assert (st == 0).all()
+    pin = {k: torch.from_numpy(np.ascontiguousarray(d[k][:B])).pin_memory() for k in ("x0", "x_ref", "feet", "iter")}
+    Fh = torch.zeros((B, N, 6), dtype=torch.float64).pin_memory()
+    sh = torch.full((B,), -7, dtype=torch.int32).pin_memory(); ih = torch.zeros(B, dtype=torch.int32).pin_memory()
+    eng.solve_host(pin["x0"], pin["x_ref"], pin["feet"], it=pin["iter"], forces=Fh, status=sh, iters=ih)
+    assert np.array_equal(Fh.numpy(), F) and np.array_equal(sh.numpy(), st)
+    tb = to_dev(torch, d)
+    Fb, sb, _ = eng.solve(tb["x0"], tb["x_ref"], tb["feet"], it=tb["iter"])
+    torch.cuda.synchronize()
+    Fb = Fb.cpu().numpy()[:B]
+    assert (sb.cpu().numpy() == 0).all()
+    assert np.abs(Fb - F).max() / max(1.0, np.abs(Fb).max()) < 1e-7
+    for b in range(B):
+        contact = O.contact_schedule(int(d["iter"][b]), N)
+        c = O.tron1_condense(po, N, d["x0"][b], d["x_ref"][b], d["feet"][b], want_pred=False)
+        A, lbA, ubA, lb, ub = O.tron1_constraints(po, N, contact)
+        u, info = O.qp_solve(c["H"], c["f"], A, lbA, ubA, lb, ub)
+        assert info["status"] == 0
+        assert np.abs(F[b].reshape(-1) - u).max() / max(1.0, np.abs(u).max()) < 1e-4
+        assert O.tron1_natural_residual(po, N, c["H"], c["f"], contact, F[b]) < 1e-6
+    eng.close()

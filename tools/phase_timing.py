@@ -9,7 +9,7 @@ out = os.path.join(ROOT, "gpurun_out", "libmpc_b200_timing.so")
 os.makedirs(os.path.dirname(out), exist_ok=True)
 csrc = os.path.join(ROOT, "mpc_limx_control_b200", "csrc")
 subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-DMPC_PHASE_TIMING",
-                       "-Xcompiler", "-fPIC", "-shared", "-o", out, os.path.join(csrc, "mpc_b200.cu"), os.path.join(csrc, "lti_b200.cu"), os.path.join(csrc, "leg_b200.cu"), os.path.join(csrc, "kf_b200.cu")])
+                       *os.environ.get("MPC_EXTRA_FLAGS", "").split(), "-Xcompiler", "-fPIC", "-shared", "-o", out, os.path.join(csrc, "mpc_b200.cu"), os.path.join(csrc, "lti_b200.cu"), os.path.join(csrc, "leg_b200.cu"), os.path.join(csrc, "kf_b200.cu")])
 from mpc_limx_control_b200 import _capi, synth
 _capi.LIB_PATH = out
 import torch
