@@ -59,6 +59,9 @@ using namespace mpcb200;
 #ifndef MPC_TILED_N50
 #define MPC_TILED_N50 1
 #endif
+#ifndef MPC_PLAIN_LOAD_GRID
+#define MPC_PLAIN_LOAD_GRID 64   // direct class: grids of at most this many CTAs stage their inputs with per-thread asynchronous copies instead of TMA bulk copies
+#endif
 #ifndef MPC_N10_WPI_LAT
 // latency class of the double-support instances of horizon 10 (a standing robot, BASELINE configs[0]): batches that leave
 // SMs idle anyway (B <= number of SMs) run one instance per CTA on MPC_N10_WPI_LAT warps with the tiled tensor-core
@@ -193,11 +196,11 @@ tron1_solve_kernel(const __grid_constant__ Tron1Const P, int B, const double* __
     S.Aext = Work::AINL ? nullptr : ext_A + ((size_t)blockIdx.x * IPC + g.gid) * Work::ASZ;   // one slab per resident group
     const double* xr_s = st.xr + g.gid * XR;
 
-    auto load_contact = [&](int b) {   // fills S.contact, returns the compact size 3 * stance foot-steps
+    auto load_contact = [&](int b, int it0 = 0, bool have_it = false) {   // fills S.contact, returns the compact size 3 * stance foot-steps
         if (contact) {
             for (int s = g.t; s < 2 * N; s += g.size()) S.contact[s] = contact[(size_t)b * 2 * N + s] ? 1 : 0;
         } else {
-            const int it0 = iter[b];
+            if (!have_it) it0 = iter[b];
             for (int k = g.t; k < N; k += g.size()) {
                 int l, r;
                 gait_contact(P, it0 < 0 ? it0 : it0 + k * P.gait_mpc_step, l, r);
@@ -361,7 +364,14 @@ tron1_solve_kernel(const __grid_constant__ Tron1Const P, int B, const double* __
         const uint32_t bx = cmd_oy ? 0u : (uint32_t)(valid * XR * sizeof(double));
         const uint32_t b0 = (uint32_t)(valid * 13 * sizeof(double));
         const uint32_t bf = (uint32_t)(valid * fstride * sizeof(double));
-        const bool bulk = (((cmd_oy ? (uintptr_t)0 : (uintptr_t)gx) | (uintptr_t)g0 | (uintptr_t)gf | bx | b0 | bf) & 15) == 0;
+        // grids that leave SMs idle (a single robot, a handful of robots) are latency-bound on the arrival of the inputs: 8-byte
+        // asynchronous copies issued by every thread arrive sooner than the bulk copies (host call, B = 1, pinned buffers: -2.4 us p50,
+        // profiles/r2_latency_class.log)
+        const bool bulk = (((cmd_oy ? (uintptr_t)0 : (uintptr_t)gx) | (uintptr_t)g0 | (uintptr_t)gf | bx | b0 | bf) & 15) == 0 &&
+                          gridDim.x > MPC_PLAIN_LOAD_GRID;
+        const bool mine = g.gid < valid;
+        const int b = first + g.gid;
+        const int it0 = (mine && !contact) ? iter[b] : 0;    // in flight together with the inputs
         if (bulk) {
             if (threadIdx.x == 0) {
                 mbar_init(&st.bar, 1);
@@ -371,23 +381,25 @@ tron1_solve_kernel(const __grid_constant__ Tron1Const P, int B, const double* __
                 bulk_g2s(st.feet, gf, bf, &st.bar);
             }
         } else {
-            if (!cmd_oy) for (int i = threadIdx.x; i < valid * XR; i += blockDim.x) st.xr[i] = gx[i];
-            for (int i = threadIdx.x; i < valid * 13; i += blockDim.x) st.x0[i] = g0[i];
-            for (int i = threadIdx.x; i < valid * fstride; i += blockDim.x) st.feet[i] = gf[i];
+            auto cp8 = [](double* dst, const double* src) {
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+            };
+            if (!cmd_oy) for (int i = threadIdx.x; i < valid * XR; i += blockDim.x) cp8(st.xr + i, gx + i);
+            for (int i = threadIdx.x; i < valid * 13; i += blockDim.x) cp8(st.x0 + i, g0 + i);
+            for (int i = threadIdx.x; i < valid * fstride; i += blockDim.x) cp8(st.feet + i, gf + i);
         }
 #if defined(MPC_PHASE_TIMING)
         if (threadIdx.x == 0 && blockIdx.x < 16384) g_cta_trace2[4 * blockIdx.x] = gtime_ns();
 #endif
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the overflow grid may queue up behind us
         // the contact schedule is evaluated while the copies are in flight
-        const bool mine = g.gid < valid;
-        const int b = first + g.gid;
         int nc = 0;
-        if (mine) nc = load_contact(b);
+        if (mine) nc = load_contact(b, it0, true);
 #if defined(MPC_PHASE_TIMING)
         if (threadIdx.x == 0 && blockIdx.x < 16384) g_cta_trace2[4 * blockIdx.x + 1] = gtime_ns();
 #endif
-        __syncthreads();   // barrier init / plain stores visible
+        if (!bulk) asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncthreads();   // barrier init / asynchronous copies of every thread visible
 #if defined(MPC_PHASE_TIMING)
         if (threadIdx.x == 0 && blockIdx.x < 16384) g_cta_trace2[4 * blockIdx.x + 2] = gtime_ns();
 #endif
@@ -432,10 +444,11 @@ tron1_solve_kernel(const __grid_constant__ Tron1Const P, int B, const double* __
             double* sx = st.xr + g.gid * XR;
             double* s0 = st.x0 + g.gid * 13;
             double* sf = st.feet + g.gid * fstride;
+            const int it0 = contact ? 0 : iter[b];     // in flight together with the inputs (one round trip when they are in host memory)
             if (!cmd_oy) for (int i = g.t; i < XR; i += g.size()) sx[i] = xref[(size_t)b * XR + i];
             for (int i = g.t; i < 13; i += g.size()) s0[i] = x0[(size_t)b * 13 + i];
             for (int i = g.t; i < fstride; i += g.size()) sf[i] = feet[(size_t)b * fstride + i];
-            load_contact(b);
+            load_contact(b, it0, true);
             finish(b);
             g.sync();
         }
