@@ -371,7 +371,6 @@ tron1_solve_kernel(const __grid_constant__ Tron1Const P, int B, const double* __
                           gridDim.x > MPC_PLAIN_LOAD_GRID;
         const bool mine = g.gid < valid;
         const int b = first + g.gid;
-        const int it0 = (mine && !contact) ? iter[b] : 0;    // in flight together with the inputs
         if (bulk) {
             if (threadIdx.x == 0) {
                 mbar_init(&st.bar, 1);
@@ -393,8 +392,11 @@ tron1_solve_kernel(const __grid_constant__ Tron1Const P, int B, const double* __
 #endif
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the overflow grid may queue up behind us
         // the contact schedule is evaluated while the copies are in flight
+        // (the gait clock is read AFTER the copies have been issued: both kinds of copy are asynchronous, so one round trip covers
+        // everything; reading it first delays the issue of the bulk copies by that round trip whenever the compiler schedules its
+        // first use early -- measured: asynchronous controller-shaped host entry 97 -> 76 M solves/s)
         int nc = 0;
-        if (mine) nc = load_contact(b, it0, true);
+        if (mine) nc = load_contact(b);
 #if defined(MPC_PHASE_TIMING)
         if (threadIdx.x == 0 && blockIdx.x < 16384) g_cta_trace2[4 * blockIdx.x + 1] = gtime_ns();
 #endif
@@ -444,11 +446,17 @@ tron1_solve_kernel(const __grid_constant__ Tron1Const P, int B, const double* __
             double* sx = st.xr + g.gid * XR;
             double* s0 = st.x0 + g.gid * 13;
             double* sf = st.feet + g.gid * fstride;
-            const int it0 = contact ? 0 : iter[b];     // in flight together with the inputs (one round trip when they are in host memory)
+            // latency class (a single robot): the gait clock is requested together with the inputs -- one round trip instead of two
+            // when they are in host memory (-1 us).  Not in the two-warp throughput class: it sits at its 168-register cap and one
+            // more live value costs 80 bytes of spills and 4 % throughput (measured)
+            constexpr bool kPre = (N == 10 && WPI >= 4);
+            const bool pre = kPre && !contact;
+            int it0 = 0;
+            if constexpr (kPre) { if (pre) it0 = iter[b]; }
             if (!cmd_oy) for (int i = g.t; i < XR; i += g.size()) sx[i] = xref[(size_t)b * XR + i];
             for (int i = g.t; i < 13; i += g.size()) s0[i] = x0[(size_t)b * 13 + i];
             for (int i = g.t; i < fstride; i += g.size()) sf[i] = feet[(size_t)b * fstride + i];
-            load_contact(b, it0, true);
+            load_contact(b, it0, pre);
             finish(b);
             g.sync();
         }
