@@ -59,6 +59,14 @@ using namespace mpcb200;
 #ifndef MPC_TILED_N50
 #define MPC_TILED_N50 1
 #endif
+#ifndef MPC_TILED_N20_S
+#define MPC_TILED_N20_S 0    // single-stance class of horizon 20 (60 variables) on the tiled DMMA Cholesky instead of the register elimination
+#endif
+#ifndef MPC_N20_WPI_S
+#define MPC_N20_WPI_S 2
+#define MPC_N20_IPC_S 2
+#define MPC_N20_MINB_S 2
+#endif
 #ifndef MPC_PLAIN_LOAD_GRID
 #define MPC_PLAIN_LOAD_GRID 64   // direct class: grids of at most this many CTAs stage their inputs with per-thread asynchronous copies instead of TMA bulk copies
 #endif
@@ -71,7 +79,7 @@ using namespace mpcb200;
 #endif
 // storage rule: tiled 8x8 layout (DMMA Cholesky) for horizon 50 and for groups of >= 4 warps on the 60-variable class of horizon 10
 template <int N, int NC, bool AINL = true, int WPI = 1>
-using SolveWork = Tron1Work<N, NC, AINL, ((N == 50 && MPC_TILED_N50 != 0) || (N == 10 && NC == 60 && WPI >= 4))>;
+using SolveWork = Tron1Work<N, NC, AINL, ((N == 50 && MPC_TILED_N50 != 0) || (N == 10 && NC == 60 && WPI >= 4) || (N == 20 && NC == 60 && MPC_TILED_N20_S != 0))>;
 
 // ------------------------------------------------------------------------------------------------
 // thread group = WPI warps cooperating on one instance
@@ -757,7 +765,7 @@ static int dispatch_solve(mpc_b200_engine* e, int B, const double* x0, const dou
             if (B <= e->num_sms && cls_hint != 0)     // latency class for the double-support instances (see MPC_N10_WPI_LAT)
                 return launch_solve<10, 1, 4, 4, MPC_N10_WPI_LAT, 1, true, 1>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only, cls_hint);
             return launch_solve<10, 1, 4, 4, 2, MPC_N10_IPC_L, true, MPC_N10_MINB_L>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only, cls_hint);
-        case 20: return launch_solve<20, 2, 2, 2, 2, 2>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only, cls_hint);
+        case 20: return launch_solve<20, MPC_N20_WPI_S, MPC_N20_IPC_S, MPC_N20_MINB_S, 2, 2>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only, cls_hint);
         case 50: return launch_solve<50, MPC_N50_WPI_S, 1, 1, MPC_N50_WPI_L, 1, false, MPC_N50_MINB_L>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only, cls_hint);
         default: return set_err(e, MPC_B200_EINVAL, "unsupported horizon");
     }
