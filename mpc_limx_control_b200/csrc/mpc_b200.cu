@@ -67,6 +67,31 @@ using namespace mpcb200;
 #define MPC_N20_IPC_S 2
 #define MPC_N20_MINB_S 2
 #endif
+// Riccati direct class per horizon (0 = off): active-face solves as O(N) sweeps instead of a dense factorisation
+#ifndef MPC_RIC_N50
+#define MPC_RIC_N50 1
+#endif
+#ifndef MPC_RIC_N20
+#define MPC_RIC_N20 0
+#endif
+#ifndef MPC_RIC_N10
+#define MPC_RIC_N10 0
+#endif
+#ifndef MPC_RIC_WPI
+#define MPC_RIC_WPI 1
+#endif
+#ifndef MPC_RIC_IPC
+#define MPC_RIC_IPC 1
+#endif
+#ifndef MPC_RIC_MINB
+#define MPC_RIC_MINB 6
+#endif
+// Riccati class of horizon 50: the per-step gains (300 x 13 doubles at full capacity) live in global memory, in slabs drawn
+// from a ring of free slabs sized for the resident CTAs (L2-resident working set) -- 1 = external, 0 = inside shared memory
+#ifndef MPC_RIC_EXT_N50
+#define MPC_RIC_EXT_N50 1
+#endif
+#define MPC_RIC_RING_DBL 4096     // doubles reserved in front of the slabs for the ring: head, tail, size, -, entries
 #ifndef MPC_PLAIN_LOAD_GRID
 #define MPC_PLAIN_LOAD_GRID 64   // direct class: grids of at most this many CTAs stage their inputs with per-thread asynchronous copies instead of TMA bulk copies
 #endif
@@ -78,8 +103,8 @@ using namespace mpcb200;
 #define MPC_N10_WPI_LAT 8
 #endif
 // storage rule: tiled 8x8 layout (DMMA Cholesky) for horizon 50 and for groups of >= 4 warps on the 60-variable class of horizon 10
-template <int N, int NC, bool AINL = true, int WPI = 1>
-using SolveWork = Tron1Work<N, NC, AINL, ((N == 50 && MPC_TILED_N50 != 0) || (N == 10 && NC == 60 && WPI >= 4) || (N == 20 && NC == 60 && MPC_TILED_N20_S != 0))>;
+template <int N, int NC, bool AINL = true, int WPI = 1, bool RIC = false>
+using SolveWork = Tron1Work<N, NC, AINL, !RIC && ((N == 50 && MPC_TILED_N50 != 0) || (N == 10 && NC == 60 && WPI >= 4) || (N == 20 && NC == 60 && MPC_TILED_N20_S != 0)), RIC>;
 
 // ------------------------------------------------------------------------------------------------
 // thread group = WPI warps cooperating on one instance
@@ -169,7 +194,7 @@ struct CtaStage {
 // slices are only 8-byte aligned, so the 16-byte bulk copies of the static path cannot address a single instance), and
 // the copy of the NEXT instance is issued as soon as the current one's staged inputs are dead (after setup_instance),
 // i.e. it overlaps the whole elimination.
-template <int N, int NC, int WPI, int IPC, int MINB, bool INDIRECT, bool AINL = true, bool DYNAMIC = false>
+template <int N, int NC, int WPI, int IPC, int MINB, bool INDIRECT, bool AINL = true, bool DYNAMIC = false, bool RIC = false>
 __global__ void __launch_bounds__(32 * WPI * IPC, MINB)
 tron1_solve_kernel(const __grid_constant__ Tron1Const P, int B, const double* __restrict__ x0,
                    const double* __restrict__ xref, const double* __restrict__ feet,
@@ -182,7 +207,7 @@ tron1_solve_kernel(const __grid_constant__ Tron1Const P, int B, const double* __
     // first_step_only: write u_0 (6 doubles per instance, include/mpcQP.h:118) instead of the whole horizon
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using Stage = CtaStage<N, IPC>;
-    using Work = SolveWork<N, NC, AINL, WPI>;
+    using Work = SolveWork<N, NC, AINL, WPI, RIC>;
     Stage& st = *reinterpret_cast<Stage*>(smem_raw);
     constexpr size_t stage_bytes = (sizeof(Stage) + 15) & ~size_t(15);
     Work* works = reinterpret_cast<Work*>(smem_raw + stage_bytes);
@@ -201,8 +226,13 @@ tron1_solve_kernel(const __grid_constant__ Tron1Const P, int B, const double* __
     Work& S = works[g.gid];
     S.x0 = st.x0 + g.gid * 13;
     S.feet = st.feet + g.gid * fstride;
-    S.Aext = Work::AINL ? nullptr : ext_A + ((size_t)blockIdx.x * IPC + g.gid) * Work::ASZ;   // one slab per resident group
+    S.Aext = (Work::AINL || RIC) ? nullptr : ext_A + ((size_t)blockIdx.x * IPC + g.gid) * Work::ASZ;   // one slab per resident group
     const double* xr_s = st.xr + g.gid * XR;
+    if constexpr (RIC) {
+        // the staged inputs are dead once the instance is set up: the adjoint scratch of the gradient passes reuses them
+        static_assert(IPC == 1 && sizeof(Stage) >= sizeof(double) * 18 * (N + 1) + 16, "adjoint scratch inside the input staging area");
+        S.adjx = st.xr;
+    }
 
     auto load_contact = [&](int b, int it0 = 0, bool have_it = false) {   // fills S.contact, returns the compact size 3 * stance foot-steps
         if (contact) {
@@ -240,6 +270,14 @@ tron1_solve_kernel(const __grid_constant__ Tron1Const P, int B, const double* __
         MPC_TICK(S, g, 13);
         if (g.t == 0) for (int i = 0; i < 16; ++i) atomicAdd(&g_phase_cycles[i], (unsigned long long)S.prof[i]);
 #endif
+        if (RIC && code == ST_DEFER) {
+            // Riccati class: the active-face iteration did not certify -> the dense class solves the instance from scratch
+            if (g.t == 0) {
+                if (ovf_list) ovf_list[atomicAdd(ovf_count, 1)] = b;
+                else if (status) status[b] = ST_FAILED;
+            }
+            return;
+        }
         if (first_step_only) {
             if (g.t < 6) forces[(size_t)b * 6 + g.t] = S.u[g.t];
         } else {
@@ -425,6 +463,29 @@ tron1_solve_kernel(const __grid_constant__ Tron1Const P, int B, const double* __
             }
             return;
         }
+        if constexpr (RIC && !AINL) {
+            // gain slab for the lifetime of this instance: pop a free slab index from the ring (entries are taken with an exchange and
+            // returned with a compare-and-swap, so a slot is never read before it was refilled nor refilled before it was taken)
+            static_assert(IPC == 1, "one instance per CTA owns the slab");
+            int32_t* ring = reinterpret_cast<int32_t*>(ext_A);
+            int slab = 0;
+            if (g.t == 0) {
+                const unsigned h = atomicAdd(reinterpret_cast<unsigned*>(ring), 1u) % (unsigned)ring[2];
+                int v;
+                do { v = atomicExch(ring + 4 + h, -1); } while (v < 0);
+                slab = v;
+                st.bar = (uint64_t)v;             // the staging barrier is dead: broadcast slot
+            }
+            g.sync();
+            slab = (int)st.bar;
+            S.Aext = ext_A + MPC_RIC_RING_DBL + (size_t)slab * Work::ASZ;
+            finish(b);
+            g.sync();
+            if (g.t == 0) {
+                const unsigned t = atomicAdd(reinterpret_cast<unsigned*>(ring) + 1, 1u) % (unsigned)ring[2];
+                while (atomicCAS(ring + 4 + t, -1, slab) != -1) { }
+            }
+        } else
         finish(b);
     } else {
         // launched with programmatic stream serialisation: this grid may start while the DIRECT grid
@@ -661,6 +722,7 @@ struct mpc_b200_engine {
     size_t condense_ws_bytes = 0;
     double* d_extA = nullptr;                                // global-memory factor slabs (N = 50 double support)
     int extA_slabs = 0;
+    double* d_ricK = nullptr;                                // Riccati class of horizon 50: ring of free slabs + gain slabs
     cudaEvent_t extA_free = nullptr;                         // recorded behind every kernel that uses the slabs: the next user
                                                              // (possibly on another pipe stream) waits on it
     size_t small_bytes = 0;
@@ -690,16 +752,20 @@ static size_t solve_smem_bytes() {
 }
 
 // small class (direct, TMA-staged) followed by the large class (indirect, overflow list)
-template <int N, int WPI_S, int IPC_S, int MINB_S, int WPI_L, int IPC_L, bool AINL_L = true, int MINB_L = 1>
+template <int N, int WPI_S, int IPC_S, int MINB_S, int WPI_L, int IPC_L, bool AINL_L = true, int MINB_L = 1, bool RIC_S = false, bool AINL_S = true>
 static int launch_solve(mpc_b200_engine* e, int B, const double* x0, const double* xref, const double* feet,
                         const uint8_t* contact, const int32_t* iter, double* forces, int32_t* status,
                         int32_t* iters, cudaStream_t s, int32_t* ovf_list, int32_t* ovf_count,
                         const double* cmd_oy, const double* cmd_vx, int first_only, int cls_hint) {
     // cls_hint (host entry points have seen the schedule): 0 = no instance needs the large class, 2 = every instance does,
     // 1 = mixed / unknown (device entry point)
-    auto ks = tron1_solve_kernel<N, 3 * N, WPI_S, IPC_S, MINB_S, false, true, MPC_DYNAMIC != 0>;
+    // RIC_S: the direct class is the Riccati work type with full capacity (every contact pattern), the list-driven dense class
+    // behind it takes the instances whose active-face iteration did not certify -- both kernels always run
+    constexpr int NC_S = RIC_S ? 6 * N : 3 * N;
+    auto ks = tron1_solve_kernel<N, NC_S, WPI_S, IPC_S, MINB_S, false, AINL_S, (MPC_DYNAMIC != 0) && !RIC_S, RIC_S>;
     auto kl = tron1_solve_kernel<N, 6 * N, WPI_L, IPC_L, MINB_L, true, AINL_L>;
-    const size_t smem_s = ((sizeof(CtaStage<N, IPC_S>) + 15) & ~size_t(15)) + sizeof(SolveWork<N, 3 * N, true, WPI_S>) * IPC_S;
+    const size_t smem_s = ((sizeof(CtaStage<N, IPC_S>) + 15) & ~size_t(15)) + sizeof(SolveWork<N, NC_S, AINL_S, WPI_S, RIC_S>) * IPC_S;
+    if (RIC_S) cls_hint = 1;
     const size_t smem_l = ((sizeof(CtaStage<N, IPC_L>) + 15) & ~size_t(15)) + sizeof(SolveWork<N, 6 * N, AINL_L, WPI_L>) * IPC_L;
     static std::atomic<bool> configured[64];      // per device; setting the attribute twice is harmless, so a lost race is too
     if (!configured[e->device & 63].load(std::memory_order_acquire)) {
@@ -725,7 +791,7 @@ static int launch_solve(mpc_b200_engine* e, int B, const double* x0, const doubl
     int grid_s = (B + IPC_S - 1) / IPC_S;
     if (MPC_DYNAMIC != 0 && grid_s > e->num_sms * MINB_S) grid_s = e->num_sms * MINB_S;   // persistent: the groups pull instances
     ks<<<grid_s, 32 * WPI_S * IPC_S, smem_s, s>>>(e->C, B, x0, xref, feet, contact, iter, forces, status,
-                                                                 iters, ovf_list, ovf_count, nullptr, cmd_oy, cmd_vx, first_only);
+                                                                 iters, ovf_list, ovf_count, (RIC_S && !AINL_S) ? e->d_ricK : nullptr, cmd_oy, cmd_vx, first_only);
     CU(e, cudaGetLastError());
     if (cls_hint == 0) {   // the host entry point has looked at the schedule: no instance can overflow, the list stays empty
         e->launches += 1;
@@ -762,11 +828,22 @@ static int dispatch_solve(mpc_b200_engine* e, int B, const double* x0, const dou
     int32_t* oc = e->d_ovf_count + 4 * slot;
     switch (e->N) {
         case 10:
+#if MPC_RIC_N10
+            return launch_solve<10, MPC_RIC_WPI, MPC_RIC_IPC, MPC_RIC_MINB, 2, MPC_N10_IPC_L, true, MPC_N10_MINB_L, true>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only, cls_hint);
+#endif
             if (B <= e->num_sms && cls_hint != 0)     // latency class for the double-support instances (see MPC_N10_WPI_LAT)
                 return launch_solve<10, 1, 4, 4, MPC_N10_WPI_LAT, 1, true, 1>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only, cls_hint);
             return launch_solve<10, 1, 4, 4, 2, MPC_N10_IPC_L, true, MPC_N10_MINB_L>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only, cls_hint);
-        case 20: return launch_solve<20, MPC_N20_WPI_S, MPC_N20_IPC_S, MPC_N20_MINB_S, 2, 2>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only, cls_hint);
-        case 50: return launch_solve<50, MPC_N50_WPI_S, 1, 1, MPC_N50_WPI_L, 1, false, MPC_N50_MINB_L>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only, cls_hint);
+        case 20:
+#if MPC_RIC_N20
+            return launch_solve<20, MPC_RIC_WPI, MPC_RIC_IPC, MPC_RIC_MINB, 2, 2, true, 1, true>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only, cls_hint);
+#endif
+            return launch_solve<20, MPC_N20_WPI_S, MPC_N20_IPC_S, MPC_N20_MINB_S, 2, 2>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only, cls_hint);
+        case 50:
+#if MPC_RIC_N50
+            return launch_solve<50, MPC_RIC_WPI, MPC_RIC_IPC, MPC_RIC_MINB, MPC_N50_WPI_L, 1, false, MPC_N50_MINB_L, true, MPC_RIC_EXT_N50 == 0>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only, cls_hint);
+#endif
+            return launch_solve<50, MPC_N50_WPI_S, 1, 1, MPC_N50_WPI_L, 1, false, MPC_N50_MINB_L>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only, cls_hint);
         default: return set_err(e, MPC_B200_EINVAL, "unsupported horizon");
     }
 }
@@ -860,6 +937,19 @@ int mpc_b200_create(const mpc_b200_tron1_params* p, int horizon, int max_batch, 
         ok = cudaMalloc(&e->d_extA, sizeof(double) * SolveWork<50, 300, false>::ASZ * (size_t)e->extA_slabs) == cudaSuccess &&
              cudaEventCreateWithFlags(&e->extA_free, cudaEventDisableTiming) == cudaSuccess;
     }
+#if MPC_RIC_N50 && MPC_RIC_EXT_N50
+    if (ok && horizon == 50) {
+        const int pool = e->num_sms * 8;            // >= resident CTAs of the Riccati class (fewer would only make CTAs wait for a slab)
+        const size_t slab = SolveWork<50, 300, false, 1, true>::ASZ;
+        std::vector<int32_t> ring(4 + pool);
+        ring[0] = 0; ring[1] = 0; ring[2] = pool; ring[3] = 0;
+        for (int i = 0; i < pool; ++i) ring[4 + i] = i;
+        static_assert(sizeof(int32_t) * (4 + 148 * 8 * 2) <= sizeof(double) * MPC_RIC_RING_DBL, "ring area");
+        ok = (size_t)(4 + pool) * sizeof(int32_t) <= sizeof(double) * MPC_RIC_RING_DBL &&
+             cudaMalloc(&e->d_ricK, sizeof(double) * (MPC_RIC_RING_DBL + slab * (size_t)pool)) == cudaSuccess &&
+             cudaMemcpy(e->d_ricK, ring.data(), ring.size() * sizeof(int32_t), cudaMemcpyHostToDevice) == cudaSuccess;
+    }
+#endif
     if (!ok) {
         cudaGetLastError();
         mpc_b200_destroy(e);
@@ -881,6 +971,7 @@ int mpc_b200_destroy(mpc_b200_engine* e) {
     if (e->h_small) cudaFreeHost(e->h_small);
     cudaFree(e->d_small);
     cudaFree(e->d_extA);
+    cudaFree(e->d_ricK);
     cudaFree(e->d_condense_ws);
     cudaFree(e->d_lane_forces); cudaFree(e->d_lane_status); cudaFree(e->d_lane_iters);
     for (int i = 0; i < mpc_b200_engine::kLanes; ++i) {

@@ -53,7 +53,7 @@ struct Tron1Const {
     double foot_off_l[3], foot_off_r[3];   // nominal base->foot offsets (include/MPCParam.h:64-73)
 };
 
-enum { ST_SOLVED = 0, ST_MAXITER = 1, ST_FAILED = 2 };
+enum { ST_SOLVED = 0, ST_MAXITER = 1, ST_FAILED = 2, ST_DEFER = 3 };   // ST_DEFER: internal (Riccati work type -> dense class), never reported
 
 // ------------------------------------------------------------------------------------------------
 // gait: bit-exact restatement of MPC::calculateGait (include/MPCController.h:61-75) with the float
@@ -95,38 +95,56 @@ MPC_HD void gait_contact(const Tron1Const& P, int iter, int& left_stance, int& r
 // and factorised by the tiled right-looking Cholesky with DMMA trailing updates (chol_tiled, horizon 50).  The
 // right-hand side is then row NC (fixed), rows nc..NC-1 are identity padding, and after the factorisation the diagonal
 // tiles hold inv(L_KK) instead of L_KK.
-template <int N_, int NC_, bool AINL_ = true, bool TILED_ = false>
+// RIC_ = the active-face solves run as a Riccati recursion over the horizon (riccati_face_solve) instead of factorising the
+// condensed Hessian: no matrix storage at all (the struct shrinks to the per-step gains), O(N) work per solve.  Instances
+// whose active-face iteration does not certify are handed to a dense-class work type (ST_DEFER).
+template <int N_, int NC_, bool AINL_ = true, bool TILED_ = false, bool RIC_ = false>
 struct Tron1Work {
     static constexpr int N = N_;
     static constexpr int NC = NC_;
     static constexpr bool AINL = AINL_;
     static constexpr bool TILED = TILED_;
+    static constexpr bool RICCATI = RIC_;
+    static_assert(!(RIC_ && TILED_), "the Riccati work type stores no matrix");
+    static_assert(!RIC_ || NC_ == 6 * N_, "the Riccati work type keeps six gain rows per step");
     static constexpr int NS = 2 * N;     // foot-steps
     static constexpr int NV = 6 * N;     // decision variables (full layout)
     static constexpr int PKN = (NC + 1) * (NC + 2) / 2;  // packed lower triangle incl. rhs row
     static constexpr int NT = (NC + 8) / 8;              // tile rows covering rows 0..NC (row NC = right-hand side)
     static constexpr int TSZ = NT * (NT + 1) / 2 * 64;   // tiled lower triangle
-    static constexpr int ASZ = TILED ? TSZ : PKN;        // doubles of matrix storage per instance
+    static constexpr int ASZ = RIC_ ? NC * 13 : (TILED ? TSZ : PKN);   // doubles of matrix (Riccati: gain) storage per instance
     double* Aext;           // external factor storage (only used when !AINL)
-    alignas(16) double Astore[AINL ? ASZ : 2];   // reduced Hessian / Cholesky factor; the rhs is row nc (packed) or row NC (tiled)
+    alignas(16) double Astore[(AINL && !RIC_) ? ASZ : 2];   // reduced Hessian / Cholesky factor; the rhs is row nc (packed) or row NC (tiled)
     alignas(16) double pbuf[TILED ? NT * 64 + 128 : 2];  // tiled: current panel column + two inverse diagonal tiles (double buffer)
     double xt[TILED ? 8 * NT : 2], st[TILED ? 8 * NT : 2];   // tiled triangular solves: solution blocks, running sums
-    double dinv[NC];        // 1 / L_kk
+    double dinv[RIC_ ? 2 : NC];        // 1 / L_kk
     static constexpr int CBS = (NC + 4) & ~1;   // stride of one broadcast buffer (even: 16-byte aligned halves)
-    alignas(16) double colbuf[2 * CBS];   // double-buffered broadcast copy of the current pivot column
-    double w[NC], z[NC], y[NC];   // compact solve vector, ADMM iterates
+    alignas(16) double colbuf[RIC_ ? 2 : 2 * CBS];   // double-buffered broadcast copy of the current pivot column
+    double w[RIC_ ? 2 : NC], z[RIC_ ? 2 : NC], y[RIC_ ? 2 : NC];   // compact solve vector, ADMM iterates
+    // Riccati work type: saved free-response error e0 [(N+1) x 12], per-variable gain rows [K (12) | kappa] (NC x 13), and
+    // the exchange buffers of one step (riccati_backward_step / riccati_forward_step); one array so that the other work types
+    // carry 8 bytes of it
+    static constexpr int RC_E0 = 0, RC_K = RC_E0 + (N + 1) * 12, RC_XM = RC_K + (AINL ? NC * 13 : 0), RC_U6 = RC_XM + 120,
+                         RC_GH = RC_U6 + 48, RC_KT = RC_GH + 48, RC_WQ = RC_KT + 78, RC_D = RC_WQ + 12,
+                         RC_KF = RC_D + 24, RC_TOTAL = RC_KF + (AINL ? 0 : 4 * 78);
+    double rc[RIC_ ? RC_TOTAL : 1];
     double W[N * 18];       // W[k][foot] 3x3 row-major:  Iw_k^-1 [r]x
     double cs[N * 2];       // cos, sin of yaw_k
     double cc[N + 1], ss[N + 1];   // prefix sums  sum_{k<i} cos / sin
     double dc[N], ds[N];    // D_j = 1/2 Rz_j' - C_{j+1}  (cos-like / sin-like entries)
-    double SW[N * 8];       // suffix sums over i>j of w_i * {1, cc, ss, cc^2, ss^2, cc ss, i, i^2}
-    double f[NV];             // full layout: linear term (live for the whole solve)
+    double SW[RIC_ ? 8 : N * 8];       // suffix sums over i>j of w_i * {1, cc, ss, cc^2, ss^2, cc ss, i, i^2}
+    // Riccati work type: f is never formed (the gradient is the adjoint of the full tracking error), adj lives in the
+    // caller's dead input staging area (adjx), g and res overlay the exchange buffers of the sweeps
+    static constexpr int RC_X = RC_TOTAL - RC_XM;                 // doubles of exchange buffers
+    static constexpr bool GALIAS = RIC_ && (8 * N <= RC_X);
+    double f[RIC_ ? 2 : NV];             // full layout: linear term (live for the whole solve)
     // ee | adj | g are contiguous and dead between the right-hand side of a face solve and the optimality check:
     // the 3x3-block elimination uses them as its broadcast arrays (gj3_solve_regs); u must survive (swing feet stay 0)
     double ee[(N + 1) * 12];  // tracking error: free response during setup, input response later
-    double adj[(N + 1) * 18]; // adjoint terms / suffix sums; first 6(N+1) doubles double as `tau`
-    double g[NV], u[NV];      // full layout: gradient, solution
-    double res[NS];
+    double adj[RIC_ ? 2 : (N + 1) * 18]; // adjoint terms / suffix sums; first 6(N+1) doubles double as `tau`
+    double g[GALIAS ? 2 : NV], u[NV];      // full layout: gradient, solution
+    double res[GALIAS ? 2 : NS];
+    double* adjx;           // Riccati work type: 18 (N + 1) doubles of scratch provided by the caller
     const double* x0;       // 13 doubles (staged by the caller)
     const double* feet;     // 6 or 6N doubles
     int8_t contact[NS], ax[NS], ay[NS], zt[NS], nax[NS], nay[NS], nzt[NS];
@@ -139,7 +157,11 @@ struct Tron1Work {
     long long prof[16];
     long long t_last;
 #endif
-    MPC_HD double* tau() { return adj; }
+    MPC_HD double* adjp() { if constexpr (RIC_) return adjx; else return adj; }
+    MPC_HD double* gp() { if constexpr (GALIAS) return rc + RC_XM; else return g; }
+    MPC_HD double* resp() { if constexpr (GALIAS) return rc + RC_XM + NV; else return res; }
+    MPC_HD double* tau() { return adjp(); }
+    MPC_HD double* Kp() { if constexpr (AINL) return rc + RC_K; else return Aext; }   // Riccati gains: inside the struct or external (global memory)
     // address of the packed factor: a compile-time offset for the shared-memory case, a pointer otherwise
     MPC_HD double* Ap() { if constexpr (AINL) return Astore; else return Aext; }
     // index of entry (i, j), i >= j, of the lower triangle
@@ -154,6 +176,12 @@ struct Tron1Work {
     MPC_HD int rhs_row() const { return TILED ? NC : nc; }
 };
 
+// finer ticks inside the Riccati sweeps (profiling builds: -DMPC_RIC_TICKS=1 backward phases, =2 forward phases)
+#if defined(MPC_RIC_TICKS)
+#define MPC_RTICK(which, S, g, id) do { if (MPC_RIC_TICKS == (which)) MPC_TICK(S, g, id); } while (0)
+#else
+#define MPC_RTICK(which, S, g, id) do { } while (0)
+#endif
 #define MPC_PK(i, j) ((i) * ((i) + 1) / 2 + (j))
 
 // optional per-phase cycle accounting (profiling build only: -DMPC_PHASE_TIMING, tools/phase_timing.py)
@@ -253,6 +281,7 @@ MPC_HD void horizon_sums(const Tron1Const& P, WK& S, const G& g) {
         S.dc[j] = 0.5 * S.cs[2 * j] - S.cc[j + 1];
         S.ds[j] = 0.5 * S.cs[2 * j + 1] - S.ss[j + 1];
     }
+    if constexpr (WK::RICCATI) { g.sync(); return; }   // the suffix sums below feed build_hessian only
     // per-step terms w_i * {1, cc_i, ss_i, cc_i^2, ss_i^2, cc_i ss_i, i, i^2} (parallel over i = 1..N) ...
     for (int i = 1 + g.tid(); i <= N; i += g.size()) {
         double w = step_weight<N>(P, i), cc = S.cc[i], ss = S.ss[i], di = (double)i;
@@ -341,7 +370,7 @@ MPC_HD void adjoint(const Tron1Const& P, WK& S, const double* e, double* out, co
     for (int i = 1 + g.tid(); i <= N; i += g.size()) {
         const double* ei = e + 12 * i;
         double w = step_weight<N>(P, i), cc = S.cc[i], ss = S.ss[i], di = (double)i;
-        double* a = S.adj + 18 * (i - 1);
+        double* a = S.adjp() + 18 * (i - 1);
         double t0 = w * q[0] * ei[0], t1 = w * q[1] * ei[1], t2 = w * q[2] * ei[2];
         a[0] = cc * t0 - ss * t1;   // C_i' Q e_Theta, x
         a[1] = ss * t0 + cc * t1;   //               y
@@ -357,11 +386,11 @@ MPC_HD void adjoint(const Tron1Const& P, WK& S, const double* e, double* out, co
     }
     g.sync();
     // suffix sums over i > j, stored at row j  (row j currently holds step j+1)
-    for (int c = g.tid(); c < 18; c += g.size()) suffix_scan_inplace<N, 18>(S.adj + c);
+    for (int c = g.tid(); c < 18; c += g.size()) suffix_scan_inplace<N, 18>(S.adjp() + c);
     g.sync();
     for (int s = g.tid(); s < 2 * N; s += g.size()) {
         int j = s >> 1;
-        const double* a = S.adj + 18 * j;
+        const double* a = S.adjp() + 18 * j;
         const double* Wj = S.W + 9 * s;
         double dc = S.dc[j], ds = S.ds[j], jh = (double)j + 0.5;
         // sum_i S(i,j)' Q e_Theta
@@ -1325,12 +1354,393 @@ MPC_HD void project_pyramid(double mu, double fmax, const double v[3], double ou
 template <class WK, class G>
 MPC_HD void gradient(const Tron1Const& P, WK& S, const G& g) {
     [[maybe_unused]] constexpr int N = WK::N;
+    if constexpr (WK::RICCATI) {
+        // the forward sweep left the full tracking error e0 + B u in S.ee: g = 2 B' Qbar (e0 + B u) + 2 r u in one adjoint pass
+        adjoint<WK>(P, S, S.ee, S.gp(), g);
+        MPC_TICK(S, g, 11);
+        for (int i = g.tid(); i < 6 * N; i += g.size()) S.gp()[i] += 2.0 * P.r * S.u[i];
+        g.sync();
+        return;
+    }
     input_response<WK>(P, S, S.u, g);
     MPC_TICK(S, g, 10);
-    adjoint<WK>(P, S, S.ee, S.g, g);
+    adjoint<WK>(P, S, S.ee, S.gp(), g);
     MPC_TICK(S, g, 11);
-    for (int i = g.tid(); i < 6 * N; i += g.size()) S.g[i] += S.f[i] + 2.0 * P.r * S.u[i];
+    for (int i = g.tid(); i < 6 * N; i += g.size()) S.gp()[i] += S.f[i] + 2.0 * P.r * S.u[i];
     g.sync();
+}
+
+// ---- Riccati form of the active-face solve (work types with RICCATI = true) ----------------------------------------------
+// The face-restricted problem  min_w  sum_i w_i (d_i + e0_i)' Q (d_i + e0_i) + r sum_k |u_k|^2,  u_k = c_k + Z_k w_k,
+// d_{k+1} = A_k d_k + B_k u_k, d_0 = 0  (d = input response, e0 = free-response error; the same minimiser as the condensed
+// system Z'HZ w = -Z'(f + H c) of face_solve, src/QPSolver.cpp:58-60) is a linear-quadratic tracking problem: one backward
+// sweep over the horizon with a 12 x 12 value matrix, one forward sweep with the stored gains.  O(N) work, no matrix.
+//   A_k = [[I, 0, Ts Rz_k', 0], [0, I, 0, Ts I], [0, 0, I, 0], [0, 0, 0, I]]   on (Theta, p, omega, v)
+//   B_k = [Ts^2/2 Rz_k' W_ka ; Ts^2/(2m) I ; Ts W_ka ; Ts/m I]  per stance foot a       (input_response, same model)
+// Eliminated variables of a face (Z column zero) keep a unit pivot and a zero right-hand side, exactly like build_hessian.
+// Velocity-level form used by the sweeps.  With  beta = Ts (tau ; phi) = Bv u  (6 x 3 per foot: Bv_a = Ts [W_a ; I / m]) the
+// step is  d' = A d + T beta,  T = [Ts/2 D ; I6],  D = blkdiag(Rz', I3),  and the last six columns of A are 2 T - [0 ; I6].
+// Hence every product with A' or T' is the same three-term "left transform" over rows  lt(x)_i = Ts/2 (D' x[0:6])_i + x[6 + i],
+// every product with A or T the same transform along a row.  With the face basis folded into the input matrix
+// (Bz = Bv Z, 6 x mm; beta_c = Bv c) one backward step is
+//   PT = P T,  X = P A = [P[:, 0:6] | 2 PT - P[:, 6:12]],  M = PT Bz,  t = PT beta_c + s                (row-local)
+//   A'X = [X[0:6] ; 2 lt(X) - X[6:12]],  U6 = lt(M) = T'M,  V = A'M = [M[0:6] ; 2 U6 - M[6:12]],  A't likewise   (rows 6..11 read rows 0..5)
+//   G = Bz' U6 + r Z'Z (mm x mm),  h = Bz' lt(t),   [K | kappa] = G^-1 [V' | h]
+//   P_k = w_k Q + A'X - V K,   s_k = w_k Q e0_k + A't - V kappa,   and forward  w = -(K d + kappa).
+// (Z'c = 0 for every face: a fixed component never shares a column with a free one.)
+// Mapping: ONE WARP per instance with fixed lane roles -- lane r < 12 owns row r of the value matrix in registers (and its
+// entry of s), lane a < mm builds row a of G, lanes 0..12 each solve one column of [V' | h] against G (the small LDL'
+// factorisation is repeated per column in registers), and the four exchanges of a step go through a few hundred bytes of shared
+// memory with a warp barrier.  Every loop has a compile-time trip count per stance-foot count (mm = 0, 3, 6); nothing is
+// indexed dynamically.  The host build runs the same phase functions over an array of 32 lane states.
+struct RicLane {
+    double Pr[12];   // row r of P_{k+1}
+    double s;        // s_{k+1}[r]
+    double X[12];    // row r of P A, then of A'PA
+    double M[6];     // row r of M, then of V = A'M
+    double t;        // t[r], then (A't)[r]
+};
+struct RicStep {     // uniform per step
+    int k, f0, sr;   // step, foot-step of the first stance foot (compact columns 0..2), right foot-step (columns 3..5 when both stand)
+    double cz, sz, wk;
+    FaceZ Z[2];      // face basis per compact slot
+    double cfx[2], cfy[2], cfz[2];   // fixed part c of u = c + Z w per slot (non-zero only with the normal force at its upper bound)
+    double* Ku;      // this step's forward gains in force space: 6 rows [Ku (12) | ku0] (left foot xyz, right foot xyz), u = ku0 + Ku d
+};
+
+template <class WK>
+MPC_HD RicStep ric_make_step(const Tron1Const& P, WK& S, int k) {
+    RicStep st;
+    st.k = k; st.sr = 2 * k + 1;
+    st.f0 = S.contact[2 * k] ? 2 * k : 2 * k + 1;
+    st.cz = S.cs[2 * k]; st.sz = S.cs[2 * k + 1];
+    st.wk = step_weight<WK::N>(P, k);
+    for (int a = 0; a < 2; ++a) {
+        const int s_ = a == 0 ? st.f0 : st.sr;
+        st.Z[a] = face_basis(P.mu, S.ax[s_], S.ay[s_], S.zt[s_]);
+        const double fz = S.zt[s_] == 1 ? P.f_max : 0.0;
+        st.cfx[a] = (double)S.ax[s_] * P.mu * fz; st.cfy[a] = (double)S.ay[s_] * P.mu * fz; st.cfz[a] = fz;
+    }
+    st.Ku = S.Kp() + 78 * k;
+    return st;
+}
+
+// run a phase: the device warp calls it once per thread, the host build once per emulated lane
+template <class G, class F>
+MPC_HD void ric_lanes(const G& g, RicLane* L, F f) {
+    if constexpr (G::kThreads == 32) f(g.tid(), L[0]);
+    else for (int l = 0; l < 32; ++l) f(l, L[l]);
+}
+
+template <int MM, class WK, class G>
+MPC_HD bool riccati_backward_step(const Tron1Const& P, WK& S, const G& g, RicLane* LL, int k) {
+    static_assert(G::kThreads == 32 || G::kThreads == 1, "the Riccati class maps one warp to an instance");
+    const RicStep st = ric_make_step<WK>(P, S, k);
+    const double Ts = P.Ts, hTs = 0.5 * P.Ts, im = P.inv_m;
+    double* XM = S.rc + WK::RC_XM;     // rows 0..5 of [X (12) | M (6) | t], stride 20
+    double* U6 = S.rc + WK::RC_U6;     // [U6 row i (6) | lt(t)_i], stride 8
+    double* GH = S.rc + WK::RC_GH;     // [G row a (6) | h_a], stride 8
+    double* KT = S.rc + WK::RC_KT;     // column j of [K | kappa] (6 entries), stride 6
+    const double* wq = S.rc + WK::RC_WQ;   // Q diagonal
+    bool ok = true;
+    // phase A (lanes 0..11, registers only): PT, X = P A, M = PT Bz, t; rows 0..5 are published
+    ric_lanes(g, LL, [&](int lane, RicLane& L) {
+        if (lane >= 12) return;
+        double PT[6];
+        PT[0] = hTs * (st.cz * L.Pr[0] - st.sz * L.Pr[1]) + L.Pr[6];
+        PT[1] = hTs * (st.sz * L.Pr[0] + st.cz * L.Pr[1]) + L.Pr[7];
+        PT[2] = hTs * L.Pr[2] + L.Pr[8];
+#pragma unroll
+        for (int j = 3; j < 6; ++j) PT[j] = hTs * L.Pr[j] + L.Pr[6 + j];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) { L.X[j] = L.Pr[j]; L.X[6 + j] = 2.0 * PT[j] - L.Pr[6 + j]; }
+        double t = L.s;
+#pragma unroll
+        for (int a = 0; a < MM / 3; ++a) {
+            const double* Wa = S.W + 9 * (a == 0 ? st.f0 : st.sr);
+            double Mv[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) Mv[c] = Ts * (PT[0] * Wa[c] + PT[1] * Wa[3 + c] + PT[2] * Wa[6 + c] + im * PT[3 + c]);
+            const FaceZ& Z = st.Z[a];
+            L.M[3 * a] = Z.fx * Mv[0];
+            L.M[3 * a + 1] = Z.fy * Mv[1];
+            L.M[3 * a + 2] = Z.fz * (Z.mx * Mv[0] + Z.my * Mv[1] + Mv[2]);
+            if (st.cfz[a] != 0.0) t += st.cfx[a] * Mv[0] + st.cfy[a] * Mv[1] + st.cfz[a] * Mv[2];   // PT beta_c
+        }
+        L.t = t;
+        if (lane < 6) {
+            double* row = XM + 20 * lane;
+#pragma unroll
+            for (int j = 0; j < 12; ++j) row[j] = L.X[j];
+#pragma unroll
+            for (int b = 0; b < MM; ++b) row[12 + b] = L.M[b];
+            row[18] = t;
+        }
+    });
+    g.sync();
+    MPC_RTICK(1, S, g, 4);
+    // phase B (lanes 6..11): the left transform of rows 0..5 turns X into A'X, M into V and t into A't; U6 and lt(t) are published
+    ric_lanes(g, LL, [&](int lane, RicLane& L) {
+        if (lane < 6 || lane >= 12) return;
+        const int i = lane - 6;
+        const double* ra = XM + 20 * (i < 2 ? 0 : i);
+        const double* rb = XM + 20 * (i < 2 ? 1 : i);
+        const double ca = hTs * (i == 0 ? st.cz : (i == 1 ? st.sz : 1.0)), cb = hTs * (i == 0 ? -st.sz : (i == 1 ? st.cz : 0.0));
+        double* urow = U6 + 8 * i;
+#pragma unroll
+        for (int j = 0; j < 12; ++j) {
+            const double lt = ca * ra[j] + cb * rb[j] + L.X[j];
+            L.X[j] = 2.0 * lt - L.X[j];
+        }
+#pragma unroll
+        for (int b = 0; b < MM; ++b) {
+            const double lt = ca * ra[12 + b] + cb * rb[12 + b] + L.M[b];
+            urow[b] = lt;
+            L.M[b] = 2.0 * lt - L.M[b];
+        }
+        const double lt = ca * ra[18] + cb * rb[18] + L.t;
+        urow[6] = lt;
+        L.t = 2.0 * lt - L.t;
+    });
+    if constexpr (MM > 0) {
+        g.sync();
+        // phase C (lanes a < mm): column a of Bz, row a of G = Bz' U6 + r Z'Z (unit pivot for an eliminated variable), h_a
+        ric_lanes(g, LL, [&](int lane, RicLane&) {
+            if (lane >= MM) return;
+            const int a = lane / 3, c = lane - 3 * a;
+            FaceZ Z;          // selects, not an indexed access: the step record stays in registers
+            Z.fx = a == 0 ? st.Z[0].fx : st.Z[1].fx; Z.fy = a == 0 ? st.Z[0].fy : st.Z[1].fy; Z.fz = a == 0 ? st.Z[0].fz : st.Z[1].fz;
+            Z.mx = a == 0 ? st.Z[0].mx : st.Z[1].mx; Z.my = a == 0 ? st.Z[0].my : st.Z[1].my;
+            const double k0 = c == 0 ? Z.fx : (c == 2 ? Z.fz * Z.mx : 0.0), k1 = c == 1 ? Z.fy : (c == 2 ? Z.fz * Z.my : 0.0),
+                         k2 = c == 2 ? Z.fz : 0.0;
+            const double* Wa = S.W + 9 * (a == 0 ? st.f0 : st.sr);
+            double Bz[6];
+#pragma unroll
+            for (int l = 0; l < 3; ++l) Bz[l] = Ts * (k0 * Wa[3 * l] + k1 * Wa[3 * l + 1] + k2 * Wa[3 * l + 2]);
+            Bz[3] = Ts * im * k0; Bz[4] = Ts * im * k1; Bz[5] = Ts * im * k2;
+            const double zz = k0 * k0 + k1 * k1 + k2 * k2;
+            double* grow = GH + 8 * lane;
+#pragma unroll
+            for (int b = 0; b < MM; ++b) {
+                double v = 0.0;
+#pragma unroll
+                for (int i = 0; i < 6; ++i) v = fma(Bz[i], U6[8 * i + b], v);
+                if (b == lane) v += (zz == 0.0) ? 1.0 : P.r * zz;
+                grow[b] = v;
+            }
+            double h = 0.0;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) h = fma(Bz[i], U6[8 * i + 6], h);
+            grow[6] = h;
+        });
+        g.sync();
+        MPC_RTICK(1, S, g, 5);
+        // phase D (lanes 0..12): one column of [K | kappa] = G^-1 [V' | h] per lane
+        ric_lanes(g, LL, [&](int lane, RicLane& L) {
+            if (lane > 12) return;
+            double a[MM][MM], rhs[MM], inv[MM];
+#pragma unroll
+            for (int i = 0; i < MM; ++i) {
+#pragma unroll
+                for (int j = 0; j <= i; ++j) a[i][j] = GH[8 * i + j];
+                rhs[i] = (lane < 12) ? L.M[i] : GH[8 * i + 6];
+            }
+#pragma unroll
+            for (int p = 0; p < MM; ++p) {
+                if (!(a[p][p] > 0.0)) ok = false;
+                inv[p] = 1.0 / a[p][p];
+#pragma unroll
+                for (int i = MM - 1; i > p; --i) {          // descending: row i reads the unscaled a[j][p] of the rows j <= i
+                    const double l = a[i][p] * inv[p];
+#pragma unroll
+                    for (int j = p + 1; j <= i; ++j) a[i][j] = fma(-l, a[j][p], a[i][j]);
+                    rhs[i] = fma(-l, rhs[p], rhs[i]);
+                    a[i][p] = l;
+                }
+            }
+#pragma unroll
+            for (int p = MM - 1; p >= 0; --p) {
+                double v = rhs[p] * inv[p];
+#pragma unroll
+                for (int i = p + 1; i < MM; ++i) v = fma(-a[i][p], rhs[i], v);
+                rhs[p] = v;
+            }
+#pragma unroll
+            for (int i = 0; i < MM; ++i) KT[6 * lane + i] = rhs[i];      // this step's update reads the compact gains
+            // the forward sweep reads the gains in force space, u = c + Z w = (c - Z kappa) - (Z K) d: no face logic there
+#pragma unroll
+            for (int a = 0; a < MM / 3; ++a) {
+                const FaceZ& Z = st.Z[a];
+                const int ft = (a == 0 ? st.f0 : st.sr) & 1;
+                const double kz = Z.fz * rhs[3 * a + 2];
+                double ux = -(Z.fx * rhs[3 * a] + Z.mx * kz), uy = -(Z.fy * rhs[3 * a + 1] + Z.my * kz), uz = -kz;
+                if (lane == 12) { ux += st.cfx[a]; uy += st.cfy[a]; uz += st.cfz[a]; }
+                double* row = st.Ku + 39 * ft + lane;
+                row[0] = ux; row[13] = uy; row[26] = uz;
+            }
+        });
+    }
+    if (k > 0) {     // step 0 needs neither P_0 nor s_0
+        g.sync();
+        MPC_RTICK(1, S, g, 6);
+        // phase E (lanes 0..11): P_k = w_k Q + A'X - V K,  s_k = w_k Q e0_k + A't - V kappa
+        ric_lanes(g, LL, [&](int lane, RicLane& L) {
+            if (lane >= 12) return;
+            const double wqr = st.wk * wq[lane];
+#pragma unroll
+            for (int j = 0; j < 12; ++j) {
+                double v = L.X[j];
+                if constexpr (MM > 0) {
+#pragma unroll
+                    for (int a = 0; a < MM; ++a) v = fma(-L.M[a], KT[6 * j + a], v);
+                }
+                if (j == lane) v += wqr;
+                L.Pr[j] = v;
+            }
+            double v = L.t;
+            if constexpr (MM > 0) {
+#pragma unroll
+                for (int a = 0; a < MM; ++a) v = fma(-L.M[a], KT[6 * 12 + a], v);
+            }
+            L.s = v + wqr * (S.rc + WK::RC_E0)[12 * k + lane];
+        });
+        g.sync();      // KT / XM are rewritten by the next step
+        MPC_RTICK(1, S, g, 9);
+    }
+    return ok;
+}
+
+// forward sweep, one step: u = ku0 + Ku d (gains in force space), d' = A d + T Bv u; the state is double-buffered in shared
+// memory.  External gains arrive through a four-slot ring in shared memory filled by asynchronous copies three steps ahead.
+template <class WK, class G>
+MPC_HD void ric_fetch_gains(WK& S, const G& g, int k) {
+    if constexpr (!WK::AINL) {
+        if (k < WK::N) {
+            const double* Kn = S.Kp() + 78 * k;
+            double* dst = S.rc + WK::RC_KF + 78 * (k & 3);
+            const bool inl = S.contact[2 * k] != 0, inr = S.contact[2 * k + 1] != 0;
+            for (int it = g.tid(); it < 78; it += G::kThreads) {
+                if (!(it < 39 ? inl : inr)) continue;          // rows of a swing foot are neither written nor read
+#if defined(__CUDA_ARCH__)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst + it)), "l"(Kn + it) : "memory");
+#else
+                dst[it] = Kn[it];
+#endif
+            }
+        }
+#if defined(__CUDA_ARCH__)
+        asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+    }
+}
+
+template <class WK, class G>
+MPC_HD void riccati_forward_step(const Tron1Const& P, WK& S, const G& g, int k) {
+    const double Ts = P.Ts;
+    const double* d = S.rc + WK::RC_D + 12 * (k & 1);
+    double* dn = S.rc + WK::RC_D + 12 * ((k + 1) & 1);
+    const bool inl = S.contact[2 * k] != 0, inr = S.contact[2 * k + 1] != 0;
+    if constexpr (!WK::AINL) {
+#if defined(__CUDA_ARCH__)
+        asm volatile("cp.async.wait_group 2;" ::: "memory");    // the copies of step k have landed (steps k+1, k+2 may be in flight)
+#endif
+        g.sync();
+        ric_fetch_gains<WK>(S, g, k + 3);
+    }
+    MPC_RTICK(2, S, g, 4);
+    double* uk = S.u + 6 * k;
+    {
+        const double* Kk = WK::AINL ? S.Kp() + 78 * k : S.rc + WK::RC_KF + 78 * (k & 3);
+        for (int i = g.tid(); i < 6; i += G::kThreads) {
+            double v = 0.0;
+            if (i < 3 ? inl : inr) {
+                const double* row = Kk + 13 * i;
+                double v0 = row[12], v1 = 0.0;
+#pragma unroll
+                for (int l = 0; l < 12; l += 2) { v0 = fma(row[l], d[l], v0); v1 = fma(row[l + 1], d[l + 1], v1); }
+                v = v0 + v1;
+            }
+            uk[i] = v;
+        }
+        g.sync();
+    }
+    MPC_RTICK(2, S, g, 5);
+    const double cz = S.cs[2 * k], sz = S.cs[2 * k + 1];
+    for (int r = g.tid(); r < 12; r += G::kThreads) {
+        // beta_l = (Bv u)_l, l = r mod 6: rows Theta_l / omega_l use the angular part, p / v the linear part
+        const int l = r < 6 ? r : r - 6;
+        double b, b2 = 0.0;
+        if (l < 3) {
+            const double* W0 = S.W + 18 * k + 3 * l;
+            b = Ts * (W0[0] * uk[0] + W0[1] * uk[1] + W0[2] * uk[2] + W0[9] * uk[3] + W0[10] * uk[4] + W0[11] * uk[5]);
+            if (r < 2) {       // the yaw rotation couples Theta_x and Theta_y: the other angular component as well
+                const double* W1 = S.W + 18 * k + 3 * (1 - l);
+                b2 = Ts * (W1[0] * uk[0] + W1[1] * uk[1] + W1[2] * uk[2] + W1[9] * uk[3] + W1[10] * uk[4] + W1[11] * uk[5]);
+            }
+        } else {
+            b = Ts * P.inv_m * (uk[l - 3] + uk[l]);
+        }
+        double v;
+        if (r < 2) {
+            const double am = d[6 + r] + 0.5 * b, ao = d[7 - r] + 0.5 * b2;     // own and other angular-rate term
+            v = d[r] + Ts * (r == 0 ? (cz * am + sz * ao) : (-sz * ao + cz * am));
+        } else if (r < 6) {
+            v = d[r] + Ts * (d[r + 6] + 0.5 * b);
+        } else {
+            v = d[r] + b;
+        }
+        dn[r] = v;
+        S.ee[12 * (k + 1) + r] = v + (S.rc + WK::RC_E0)[12 * (k + 1) + r];     // full tracking error for the gradient pass
+    }
+    g.sync();
+    MPC_RTICK(2, S, g, 6);
+}
+
+template <class WK, class G>
+MPC_HD bool riccati_face_solve(const Tron1Const& P, WK& S, const G& g) {
+    [[maybe_unused]] constexpr int N = WK::N;
+    RicLane LL[G::kThreads == 32 ? 1 : 32];
+    bool ok = true;
+    {   // terminal value: P_N = w_N Q, s_N = w_N Q e0_N;  d_0 = 0;  the Q diagonal where a lane can index it
+        const double wN = step_weight<N>(P, N);
+        for (int i = g.tid(); i < 12; i += G::kThreads) { (S.rc + WK::RC_WQ)[i] = P.q[i]; (S.rc + WK::RC_D)[i] = 0.0; }
+        g.sync();
+        ric_lanes(g, LL, [&](int lane, RicLane& L) {
+            const int r = lane < 12 ? lane : 0;
+            const double wq = wN * (S.rc + WK::RC_WQ)[r];
+#pragma unroll
+            for (int j = 0; j < 12; ++j) L.Pr[j] = (j == r) ? wq : 0.0;
+            L.s = wq * (S.rc + WK::RC_E0)[12 * N + r];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) L.M[j] = 0.0;
+        });
+    }
+    for (int k = N - 1; k >= 0; --k) {
+        const int nf = (S.contact[2 * k] ? 1 : 0) + (S.contact[2 * k + 1] ? 1 : 0);
+        bool okk;
+        if (nf == 2) okk = riccati_backward_step<6, WK>(P, S, g, LL, k);
+        else if (nf == 1) okk = riccati_backward_step<3, WK>(P, S, g, LL, k);
+        else okk = riccati_backward_step<0, WK>(P, S, g, LL, k);
+        ok = ok && okk;
+    }
+    MPC_TICK(S, g, 7);
+    g.sync();       // the gains of step 0 were written by other lanes
+    ric_fetch_gains<WK>(S, g, 0);
+    ric_fetch_gains<WK>(S, g, 1);
+    ric_fetch_gains<WK>(S, g, 2);
+    for (int k = 0; k < N; ++k) riccati_forward_step<WK>(P, S, g, k);
+#if defined(__CUDA_ARCH__)
+    if constexpr (!WK::AINL) asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+    MPC_TICK(S, g, 8);
+    // the pivots were seen by the lanes that solved: combine
+    if (g.tid() == 0) S.flag = 0;
+    g.sync();
+    if (!ok) S.flag = 1;
+    g.sync();
+    const bool all_ok = S.flag == 0;
+    g.sync();
+    return all_ok;
 }
 
 // ---- one active-face solve: u = argmin q on the affine hull of the current face -------------------
@@ -1338,6 +1748,12 @@ MPC_HD void gradient(const Tron1Const& P, WK& S, const G& g) {
 template <class WK, class G>
 MPC_HD bool face_solve(const Tron1Const& P, WK& S, const G& g) {
     [[maybe_unused]] constexpr int N = WK::N;
+    if constexpr (WK::RICCATI) {
+        if (g.tid() == 0) S.interior = 0;
+        const bool okr = riccati_face_solve<WK>(P, S, g);
+        MPC_TICK(S, g, 7);
+        return okr;
+    } else {
     // fixed part: z = fmax on zt==1 foot-steps
     bool any_fixed = false;
     [[maybe_unused]] bool any_reduced = false;   // some stance foot-step sits on a face other than the interior one
@@ -1373,7 +1789,7 @@ MPC_HD bool face_solve(const Tron1Const& P, WK& S, const G& g) {
     for (int s = g.tid(); s < 2 * N; s += g.size()) {
         if (!S.contact[s]) continue;
         FaceZ Z = face_basis(P.mu, S.ax[s], S.ay[s], S.zt[s]);
-        const double* g0 = any_fixed ? S.g + 3 * s : S.f + 3 * s;
+        const double* g0 = any_fixed ? S.gp() + 3 * s : S.f + 3 * s;
         double* A = S.Ap();
         const int c0 = 3 * S.cidx[s];
         A[WK::pk(R, c0)] = -Z.fx * g0[0];
@@ -1415,6 +1831,7 @@ MPC_HD bool face_solve(const Tron1Const& P, WK& S, const G& g) {
     g.sync();
     MPC_TICK(S, g, 9);
     return ok;
+    }
 }
 
 // ---- optimality check of S.u: natural residual |u - P_C(u - gamma g)|_inf, predicts the next face --
@@ -1450,7 +1867,7 @@ MPC_HD bool check_optimality(const Tron1Const& P, WK& S, const G& g, bool& chang
             }
             if (t < NC) {
                 const int s = S.cinv[t / 3], c = t - 3 * (t / 3);
-                S.g[3 * s + c] = a0 + a1 + S.f[3 * s + c];
+                S.gp()[3 * s + c] = a0 + a1 + S.f[3 * s + c];
             }
             g.sync();
         } else gradient<WK>(P, S, g);
@@ -1466,7 +1883,7 @@ MPC_HD bool check_optimality(const Tron1Const& P, WK& S, const G& g, bool& chang
         if (s < 2 * N && S.contact[s]) {
             double v[3], o[3];
             int ax, ay, zt;
-            for (int c = 0; c < 3; ++c) v[c] = S.u[3 * s + c] - P.gamma * S.g[3 * s + c];
+            for (int c = 0; c < 3; ++c) v[c] = S.u[3 * s + c] - P.gamma * S.gp()[3 * s + c];
             project_pyramid(P.mu, P.f_max, v, o, ax, ay, zt);
             for (int c = 0; c < 3; ++c) {
                 double d = fabs(S.u[3 * s + c] - o[c]);
@@ -1490,14 +1907,14 @@ MPC_HD bool check_optimality(const Tron1Const& P, WK& S, const G& g, bool& chang
         return r <= P.tol * um;
     } else if constexpr (G::kThreads >= 2 * N && G::kThreads > 32) {
         // multi-warp groups: one foot-step per thread, warp-shuffle reductions, the per-warp results combined through
-        // shared memory (S.res is free here), the face-change flag by a reducing barrier
+        // shared memory (S.resp() is free here), the face-change flag by a reducing barrier
         const int s = g.tid();
         double r = 0.0, um = 1.0;
         bool ch = false;
         if (s < 2 * N && S.contact[s]) {
             double v[3], o[3];
             int ax, ay, zt;
-            for (int c = 0; c < 3; ++c) v[c] = S.u[3 * s + c] - P.gamma * S.g[3 * s + c];
+            for (int c = 0; c < 3; ++c) v[c] = S.u[3 * s + c] - P.gamma * S.gp()[3 * s + c];
             project_pyramid(P.mu, P.f_max, v, o, ax, ay, zt);
             for (int c = 0; c < 3; ++c) {
                 double d = fabs(S.u[3 * s + c] - o[c]);
@@ -1515,18 +1932,48 @@ MPC_HD bool check_optimality(const Tron1Const& P, WK& S, const G& g, bool& chang
             um = u2 > um ? u2 : um;
         }
         constexpr int NW = G::kThreads / 32;
-        static_assert(2 * NW <= 2 * N, "S.res holds the per-warp partial results");
-        if ((s & 31) == 0) { S.res[2 * (s >> 5)] = r; S.res[2 * (s >> 5) + 1] = um; }
-        changed = g.any(ch);                  // also the barrier that publishes S.res
-        r = S.res[0]; um = S.res[1];
+        static_assert(2 * NW <= 2 * N, "S.resp() holds the per-warp partial results");
+        if ((s & 31) == 0) { S.resp()[2 * (s >> 5)] = r; S.resp()[2 * (s >> 5) + 1] = um; }
+        changed = g.any(ch);                  // also the barrier that publishes S.resp()
+        r = S.resp()[0]; um = S.resp()[1];
 #pragma unroll
         for (int w = 1; w < NW; ++w) {
-            const double r2 = S.res[2 * w], u2 = S.res[2 * w + 1];
+            const double r2 = S.resp()[2 * w], u2 = S.resp()[2 * w + 1];
             r = (!(r2 <= r) && r == r) ? r2 : r;
             um = u2 > um ? u2 : um;
         }
         resid = r;
-        g.sync();                             // S.res is reused by the next check
+        g.sync();                             // S.resp() is reused by the next check
+        MPC_TICK(S, g, 12);
+        return r <= P.tol * um;
+    } else if constexpr (G::kThreads == 32 && WK::RICCATI) {
+        // one warp, more foot-steps than lanes: strided over the foot-steps, then the same shuffle reductions
+        double r = 0.0, um = 1.0;
+        bool ch = false;
+        for (int s = g.tid(); s < 2 * N; s += 32) {
+            if (!S.contact[s]) continue;
+            double v[3], o[3];
+            int ax, ay, zt;
+            for (int c = 0; c < 3; ++c) v[c] = S.u[3 * s + c] - P.gamma * S.gp()[3 * s + c];
+            project_pyramid(P.mu, P.f_max, v, o, ax, ay, zt);
+            for (int c = 0; c < 3; ++c) {
+                double d = fabs(S.u[3 * s + c] - o[c]);
+                r = (!(d <= r) && r == r) ? d : r;   // NaN-propagating max
+                double a = fabs(S.u[3 * s + c]);
+                um = a > um ? a : um;
+            }
+            S.nax[s] = (int8_t)ax; S.nay[s] = (int8_t)ay; S.nzt[s] = (int8_t)zt;
+            ch = ch || (ax != S.ax[s]) || (ay != S.ay[s]) || (zt != S.zt[s]);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            double r2 = __shfl_xor_sync(0xffffffffu, r, off), u2 = __shfl_xor_sync(0xffffffffu, um, off);
+            r = (!(r2 <= r) && r == r) ? r2 : r;   // NaN-propagating max
+            um = u2 > um ? u2 : um;
+        }
+        changed = __any_sync(0xffffffffu, ch);
+        resid = r;
+        g.sync();
         MPC_TICK(S, g, 12);
         return r <= P.tol * um;
     } else
@@ -1537,7 +1984,7 @@ MPC_HD bool check_optimality(const Tron1Const& P, WK& S, const G& g, bool& chang
         if (S.contact[s]) {
             double v[3], o[3];
             int ax, ay, zt;
-            for (int c = 0; c < 3; ++c) v[c] = S.u[3 * s + c] - P.gamma * S.g[3 * s + c];
+            for (int c = 0; c < 3; ++c) v[c] = S.u[3 * s + c] - P.gamma * S.gp()[3 * s + c];
             project_pyramid(P.mu, P.f_max, v, o, ax, ay, zt);
             for (int c = 0; c < 3; ++c) {
                 double d = fabs(S.u[3 * s + c] - o[c]);
@@ -1547,14 +1994,14 @@ MPC_HD bool check_optimality(const Tron1Const& P, WK& S, const G& g, bool& chang
             }
             S.nax[s] = (int8_t)ax; S.nay[s] = (int8_t)ay; S.nzt[s] = (int8_t)zt;
         }
-        S.res[s] = r;
+        S.resp()[s] = r;
         S.tau()[s] = um;   // scratch: per foot-step |u|_inf
     }
     g.sync();
     double r = 0.0, um = 1.0;
     bool ch = false;
     for (int s = 0; s < 2 * N; ++s) {
-        r = (!(S.res[s] <= r) && r == r) ? S.res[s] : r;   // NaN-propagating max
+        r = (!(S.resp()[s] <= r) && r == r) ? S.resp()[s] : r;   // NaN-propagating max
         um = S.tau()[s] > um ? S.tau()[s] : um;
         if (S.contact[s]) ch |= (S.nax[s] != S.ax[s]) || (S.nay[s] != S.ay[s]) || (S.nzt[s] != S.zt[s]);
     }
@@ -1588,11 +2035,11 @@ MPC_HD void setup_instance(const Tron1Const& P, WK& S, const double* xref, const
         if (in) S.cinv[rank] = (int8_t)s;
         if (s == 0) S.nc = 3 * __popc(mask);
     } else if constexpr (G::kThreads >= 2 * N && G::kThreads > 32) {
-        // multi-warp groups: per-warp ballots, warp offsets from the other warps' masks (through S.res as scratch)
+        // multi-warp groups: per-warp ballots, warp offsets from the other warps' masks (through S.resp() as scratch)
         const int s = g.tid(), wid = s >> 5, lane = s & 31;
         const bool in = s < 2 * N && S.contact[s];
         const unsigned mask = __ballot_sync(0xffffffffu, in);
-        unsigned* masks = reinterpret_cast<unsigned*>(S.res);
+        unsigned* masks = reinterpret_cast<unsigned*>(S.resp());
         if (lane == 0) masks[wid] = mask;
         g.sync();
         int base = 0, total = 0;
@@ -1607,7 +2054,7 @@ MPC_HD void setup_instance(const Tron1Const& P, WK& S, const double* xref, const
         if (s < 2 * N) S.cidx[s] = (int16_t)rank;
         if (in) S.cinv[rank] = (int8_t)s;
         if (s == 0) S.nc = 3 * total;
-        g.sync();                             // S.res is scratch again
+        g.sync();                             // S.resp() is scratch again
     } else
 #endif
     if (g.tid() == 0) {
@@ -1639,8 +2086,12 @@ MPC_HD void setup_instance(const Tron1Const& P, WK& S, const double* xref, const
     horizon_sums<WK>(P, S, g);
     MPC_TICK(S, g, 1);
     free_response<WK>(P, S, xref, g);
+    if constexpr (WK::RICCATI) {   // the gradient passes reuse S.ee: keep the free-response error for the sweeps
+        for (int i = g.tid(); i < 12 * (N + 1); i += g.size()) (S.rc + WK::RC_E0)[i] = S.ee[i];
+        g.sync();
+    }
     MPC_TICK(S, g, 2);
-    adjoint<WK>(P, S, S.ee, S.f, g);   // f = 2 B' Q (A x0 - x_ref)   (src/QPSolver.cpp:59-60)
+    if constexpr (!WK::RICCATI) adjoint<WK>(P, S, S.ee, S.f, g);   // f = 2 B' Q (A x0 - x_ref)   (src/QPSolver.cpp:59-60)
     MPC_TICK(S, g, 3);
 }
 
@@ -1662,6 +2113,10 @@ MPC_HD int solve_instance(const Tron1Const& P, WK& S, const double* xref, const 
     bool bad;
     {
         double acc = 0.0;
+        if constexpr (WK::RICCATI) {      // f is not formed: the free-response error and the lever-arm matrices carry the same inputs
+            for (int i = g.tid(); i < 12 * (N + 1); i += g.size()) acc += S.ee[i] * 0.0;
+            for (int i = g.tid(); i < 18 * N; i += g.size()) acc += S.W[i] * 0.0;
+        } else
         for (int i = g.tid(); i < 6 * N; i += g.size()) acc += S.f[i] * 0.0;   // 0 unless f[i] is NaN/inf
         bad = (acc != 0.0 || acc != acc);
     }
@@ -1697,6 +2152,9 @@ MPC_HD int solve_instance(const Tron1Const& P, WK& S, const double* xref, const 
         if (!changed) break;   // same face predicted but not optimal: numerical stall -> ADMM
         adopt_predicted_face<WK>(S, g);
     }
+    if constexpr (WK::RICCATI) {
+        return ST_DEFER;     // the dense class (factorisation + ADMM) takes over from scratch
+    } else {
     // phase B: ADMM on  min q(u) + I_C(z), u = z  with periodic active-face polish
     const int n = S.nc;
     double hmax = 0.0;
@@ -1791,6 +2249,7 @@ MPC_HD int solve_instance(const Tron1Const& P, WK& S, const double* xref, const 
         for (int c = 0; c < 3; ++c) S.u[3 * s + c] = S.contact[s] ? S.z[3 * S.cidx[s] + c] : 0.0;
     g.sync();
     return ST_MAXITER;
+    }
 }
 
 // ---- reference trajectory of mpcQP (reference include/mpcQP.h:74-97): x_ref 13 x (N+1), step-major ------

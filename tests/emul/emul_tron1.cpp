@@ -6,6 +6,7 @@
 // loudly without CUDA.
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 #include <new>
 
 #include "../../mpc_limx_control_b200/csrc/tron1_core.cuh"
@@ -111,7 +112,54 @@ static int run_rollout(const Tron1Const& P, int steps, double* x, double oy, dou
     return bad;
 }
 
+// the Riccati work type (O(N) active-face solves, no matrix); `deferred` reports whether the instance was handed to the
+// dense class, as the kernel wrapper does for instances whose active-face iteration does not certify
+template <int N, bool AINL>
+static int run_solve_riccati(const Tron1Const& P, const double* x0, const double* xref, const double* feet,
+                             const uint8_t* contact, double* forces, int* iters, int* deferred) {
+    using Work = Tron1Work<N, 6 * N, AINL, false, true>;
+    auto* S = new Work();
+    std::vector<double> gains(AINL ? 1 : Work::ASZ);      // external gain storage (global memory on the device)
+    S->Aext = AINL ? nullptr : gains.data();
+    std::vector<double> adjs(18 * (N + 1));               // adjoint scratch (the dead input staging area on the device)
+    S->adjx = adjs.data();
+    S->x0 = x0;
+    S->feet = feet;
+    for (int s = 0; s < 2 * N; ++s) S->contact[s] = contact[s] ? 1 : 0;
+    GrpSerial g;
+    int it = 0;
+    int st = solve_instance<Work>(P, *S, xref, g, it);
+    std::memcpy(forces, S->u, sizeof(double) * 6 * N);
+    delete S;
+    if (deferred) *deferred = (st == ST_DEFER);
+    if (st == ST_DEFER) {
+        int it2 = 0;
+        st = run_solve<N>(P, x0, xref, feet, contact, forces, &it2);
+        it += it2;
+    }
+    if (iters) *iters = it;
+    return st;
+}
+
 extern "C" {
+
+int emul_tron1_solve_riccati(const mpc_b200_tron1_params* prm, int N, int ext_gains, const double* x0, const double* xref,
+                             const double* feet, const uint8_t* contact, double* forces, int* iters, int* deferred) {
+    Tron1Const P;
+    if (make_tron1_const(*prm, P)) return -1;
+    switch (N) {
+        case 4: return ext_gains ? run_solve_riccati<4, false>(P, x0, xref, feet, contact, forces, iters, deferred)
+                                  : run_solve_riccati<4, true>(P, x0, xref, feet, contact, forces, iters, deferred);
+        case 10: return ext_gains ? run_solve_riccati<10, false>(P, x0, xref, feet, contact, forces, iters, deferred)
+                                  : run_solve_riccati<10, true>(P, x0, xref, feet, contact, forces, iters, deferred);
+        case 20: return ext_gains ? run_solve_riccati<20, false>(P, x0, xref, feet, contact, forces, iters, deferred)
+                                  : run_solve_riccati<20, true>(P, x0, xref, feet, contact, forces, iters, deferred);
+        case 50: return ext_gains ? run_solve_riccati<50, false>(P, x0, xref, feet, contact, forces, iters, deferred)
+                                  : run_solve_riccati<50, true>(P, x0, xref, feet, contact, forces, iters, deferred);
+        default: return -2;
+    }
+}
+
 
 int emul_tron1_rollout(const mpc_b200_tron1_params* prm, int N, int steps, double* x, double oy, double vx, int it0,
                        double* u_traj, int* iters) {

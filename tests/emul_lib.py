@@ -69,6 +69,17 @@ def solve_tiled60(p, x0, x_ref, feet, contact):
     return forces, st, it.value
 
 
+def solve_riccati(p, N, x0, x_ref, feet, contact, ext_gains=False):
+    """Riccati work type (O(N) active-face solves); returns (forces, status, iters, deferred-to-dense flag)."""
+    x0 = np.ascontiguousarray(x0, np.float64); x_ref = np.ascontiguousarray(x_ref, np.float64)
+    feet = np.ascontiguousarray(feet, np.float64); contact = np.ascontiguousarray(contact, np.uint8)
+    forces = np.zeros((N, 6)); it = C.c_int(0); df = C.c_int(0)
+    st = lib().emul_tron1_solve_riccati(C.byref(p), N, int(ext_gains), x0.ctypes.data_as(_dp), x_ref.ctypes.data_as(_dp),
+                                        feet.ctypes.data_as(_dp), contact.ctypes.data_as(_u8),
+                                        forces.ctypes.data_as(_dp), C.byref(it), C.byref(df))
+    return forces, st, it.value, df.value
+
+
 def dump(p, N, x0, x_ref, feet):
     x0 = np.ascontiguousarray(x0, np.float64); x_ref = np.ascontiguousarray(x_ref, np.float64)
     feet = np.ascontiguousarray(feet, np.float64)

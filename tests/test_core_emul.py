@@ -96,6 +96,36 @@ def test_latency_class_tiled_storage_horizon10(max_newton, scale, mu):
         assert np.all(F.reshape(N, 2, 3)[contact == 0] == 0.0)
 
 
+@pytest.mark.parametrize("N,Ts,standing,scale,mu", [(10, 0.005, False, 1, 0.5), (10, 0.02, True, 8, 0.2), (20, 0.05, True, 6, 0.3),
+                                                    (4, 0.01, True, 3, 0.5), (50, 0.01, True, 3, 0.4)])
+def test_riccati_face_solves_match_dense_path_and_oracle(N, Ts, standing, scale, mu):
+    """The Riccati work type (tron1_core.cuh: riccati_face_solve; opt-in on the device, -DMPC_RIC_N*) replaces the factorisation
+    of the condensed Hessian by one backward and one forward sweep over the horizon.  Same faces, same iteration counts and the
+    same forces as the dense path (to rounding), and the oracle's active-set solution within the north_star tolerance."""
+    B = 4 if N < 50 else 1
+    d = synth.tron1_batch(31, B, N, Ts, standing=standing)
+    po = O.tron1_defaults(Ts=Ts, mu=mu); pe = E.default_params(Ts=Ts, mu=mu)
+    rng = np.random.default_rng(N)
+    for b in range(B):
+        x0 = d["x0"][b].copy(); x0[[0, 1, 6, 7, 8, 9, 10, 11]] *= scale
+        contact = O.contact_schedule(int(d["iter"][b]), N)
+        if b == 1:                                   # ragged pattern: flight steps and single support mixed in
+            contact = contact.copy(); contact[rng.integers(0, N, 3), rng.integers(0, 2, 3)] = 0
+        F, st, it, deferred = E.solve_riccati(pe, N, x0, d["x_ref"][b], d["feet"][b], contact)
+        Fx, stx, itx, dfx = E.solve_riccati(pe, N, x0, d["x_ref"][b], d["feet"][b], contact, ext_gains=True)   # gains in external storage
+        assert np.array_equal(F, Fx) and (stx, itx, dfx) == (st, it, deferred)
+        F2, st2, it2 = E.solve(pe, N, x0, d["x_ref"][b], d["feet"][b], contact)
+        assert st == 0 and st2 == 0 and not deferred and it == it2
+        assert np.abs(F - F2).max() / max(1.0, np.abs(F2).max()) < 1e-8
+        c = O.tron1_condense(po, N, x0, d["x_ref"][b], d["feet"][b], want_pred=False)
+        A, lbA, ubA, lb, ub = O.tron1_constraints(po, N, contact)
+        u, info = O.qp_solve(c["H"], c["f"], A, lbA, ubA, lb, ub)
+        assert info["status"] == 0
+        assert np.abs(F.reshape(-1) - u).max() / max(1.0, np.abs(u).max()) < 1e-4
+        assert O.tron1_natural_residual(po, N, c["H"], c["f"], contact, F) < 1e-6
+        assert np.all(F.reshape(N, 2, 3)[contact == 0] == 0.0)
+
+
 def test_admm_fallback_path():
     """max_newton=1 forces every instance whose first face guess is wrong through ADMM + polish."""
     N, Ts, B = 10, 0.02, 12
