@@ -98,8 +98,26 @@ MPC_HD void gait_contact(const Tron1Const& P, int iter, int& left_stance, int& r
 // RIC_ = the active-face solves run as a Riccati recursion over the horizon (riccati_face_solve) instead of factorising the
 // condensed Hessian: no matrix storage at all (the struct shrinks to the per-step gains), O(N) work per solve.  Instances
 // whose active-face iteration does not certify are handed to a dense-class work type (ST_DEFER).
+// storage that only the Riccati work type carries (an empty base for the others: their layout, tuned to the shared-memory
+// budget of four CTAs per SM, stays exactly as it was)
+template <bool RIC_, int RC_TOTAL_>
+struct RicStore {
+    alignas(16) double rc[RC_TOTAL_];   // saved free-response error, gains (when inside the struct), exchange buffers of one step
+    double* adjx;                       // 18 (N + 1) doubles of adjoint scratch provided by the caller
+};
+template <int RC_TOTAL_>
+struct RicStore<false, RC_TOTAL_> {};
+template <int N, int NC, bool AINL>
+struct RicLayout {
+    // saved free-response error e0 [(N+1) x 12], force-space gain rows [Ku (12) | ku0] (6 per step), and the exchange buffers of
+    // one step (riccati_backward_step / riccati_forward_step)
+    static constexpr int RC_E0 = 0, RC_K = RC_E0 + (N + 1) * 12, RC_XM = RC_K + (AINL ? NC * 13 : 0), RC_U6 = RC_XM + 120,
+                         RC_GH = RC_U6 + 48, RC_KT = RC_GH + 48, RC_WQ = RC_KT + 78, RC_D = RC_WQ + 12,
+                         RC_KF = RC_D + 24, RC_TOTAL = RC_KF + (AINL ? 0 : 4 * 78);
+};
+
 template <int N_, int NC_, bool AINL_ = true, bool TILED_ = false, bool RIC_ = false>
-struct Tron1Work {
+struct Tron1Work : RicStore<RIC_, RicLayout<N_, NC_, AINL_>::RC_TOTAL> {
     static constexpr int N = N_;
     static constexpr int NC = NC_;
     static constexpr bool AINL = AINL_;
@@ -121,13 +139,9 @@ struct Tron1Work {
     static constexpr int CBS = (NC + 4) & ~1;   // stride of one broadcast buffer (even: 16-byte aligned halves)
     alignas(16) double colbuf[RIC_ ? 2 : 2 * CBS];   // double-buffered broadcast copy of the current pivot column
     double w[RIC_ ? 2 : NC], z[RIC_ ? 2 : NC], y[RIC_ ? 2 : NC];   // compact solve vector, ADMM iterates
-    // Riccati work type: saved free-response error e0 [(N+1) x 12], per-variable gain rows [K (12) | kappa] (NC x 13), and
-    // the exchange buffers of one step (riccati_backward_step / riccati_forward_step); one array so that the other work types
-    // carry 8 bytes of it
-    static constexpr int RC_E0 = 0, RC_K = RC_E0 + (N + 1) * 12, RC_XM = RC_K + (AINL ? NC * 13 : 0), RC_U6 = RC_XM + 120,
-                         RC_GH = RC_U6 + 48, RC_KT = RC_GH + 48, RC_WQ = RC_KT + 78, RC_D = RC_WQ + 12,
-                         RC_KF = RC_D + 24, RC_TOTAL = RC_KF + (AINL ? 0 : 4 * 78);
-    double rc[RIC_ ? RC_TOTAL : 1];
+    using RL = RicLayout<N_, NC_, AINL_>;
+    static constexpr int RC_E0 = RL::RC_E0, RC_K = RL::RC_K, RC_XM = RL::RC_XM, RC_U6 = RL::RC_U6, RC_GH = RL::RC_GH, RC_KT = RL::RC_KT,
+                         RC_WQ = RL::RC_WQ, RC_D = RL::RC_D, RC_KF = RL::RC_KF, RC_TOTAL = RL::RC_TOTAL;
     double W[N * 18];       // W[k][foot] 3x3 row-major:  Iw_k^-1 [r]x
     double cs[N * 2];       // cos, sin of yaw_k
     double cc[N + 1], ss[N + 1];   // prefix sums  sum_{k<i} cos / sin
@@ -144,7 +158,6 @@ struct Tron1Work {
     double adj[RIC_ ? 2 : (N + 1) * 18]; // adjoint terms / suffix sums; first 6(N+1) doubles double as `tau`
     double g[GALIAS ? 2 : NV], u[NV];      // full layout: gradient, solution
     double res[GALIAS ? 2 : NS];
-    double* adjx;           // Riccati work type: 18 (N + 1) doubles of scratch provided by the caller
     const double* x0;       // 13 doubles (staged by the caller)
     const double* feet;     // 6 or 6N doubles
     int8_t contact[NS], ax[NS], ay[NS], zt[NS], nax[NS], nay[NS], nzt[NS];
@@ -157,11 +170,11 @@ struct Tron1Work {
     long long prof[16];
     long long t_last;
 #endif
-    MPC_HD double* adjp() { if constexpr (RIC_) return adjx; else return adj; }
-    MPC_HD double* gp() { if constexpr (GALIAS) return rc + RC_XM; else return g; }
-    MPC_HD double* resp() { if constexpr (GALIAS) return rc + RC_XM + NV; else return res; }
+    MPC_HD double* adjp() { if constexpr (RIC_) return this->adjx; else return adj; }
+    MPC_HD double* gp() { if constexpr (GALIAS) return this->rc + RC_XM; else return g; }
+    MPC_HD double* resp() { if constexpr (GALIAS) return this->rc + RC_XM + NV; else return res; }
     MPC_HD double* tau() { return adjp(); }
-    MPC_HD double* Kp() { if constexpr (AINL) return rc + RC_K; else return Aext; }   // Riccati gains: inside the struct or external (global memory)
+    MPC_HD double* Kp() { if constexpr (AINL) return this->rc + RC_K; else return Aext; }   // Riccati gains: inside the struct or external (global memory)
     // address of the packed factor: a compile-time offset for the shared-memory case, a pointer otherwise
     MPC_HD double* Ap() { if constexpr (AINL) return Astore; else return Aext; }
     // index of entry (i, j), i >= j, of the lower triangle
