@@ -85,25 +85,27 @@ def structured_flops(N, nc, iters, group_threads):
                                 + gradient + optimality check                         ~ 300 N
       elimination, nc <= 60   : register Gauss-Jordan, EVERY lane of the group carries a row window:
                                 lanes x sum over the 5 stages of (nc/5) columns x (2 W + 10), W = window length
-      factorisation, N = 50   : tiled Cholesky: 512 flops per DMMA.8x8x4 x (2 per trailing tile + 2 per panel tile
-                                + 2 per look-ahead tile) [tensor pipe] + NT diagonal factors x ~300 x 32 lanes + blocked
-                                solves 2 nc^2 [FP64 pipe]
+      horizon 50              : Riccati class (see the branch below); the dense tiled DMMA Cholesky class only takes the
+                                instances whose active-face iteration does not certify (none in the bench workloads)
     Returns (total, tensor_part).  Checked against ncu's executed thread-level DFMA/DMUL/DADD count (which excludes DMMA)
     on the committed captures profiles/r2_c*: config 2 0.999, 2s 1.06, 3 1.01, 4 (non-tensor part) within 10 %."""
     m = nc / 3.0
+    if N == 50:
+        # Riccati class (horizon 50): no matrix, one backward and one forward sweep per active-face solve.  Per step with nf stance
+        # feet (counted per ACTIVE lane of the warp, phases A-E of riccati_backward_step): nf = 0: 888, nf = 1: 3399, nf = 2: 7413
+        # (A: 360 + 372 nf, B: 468 + 108 nf, C: 237 / 690, D: 13 columns x (LDL' + two triangular solves + force-space rows) =
+        # 858 / 3003, E: 12 rows x (26 mm + 5)); forward step 166 + 75 nf; gradient (one adjoint pass) + check ~ 220 N; setup
+        # without f ~ 300 N.  Checked against ncu (profiles/r2b_c4*): 413 k computed against 410 k executed for double support.
+        nf = m / N                                   # stance feet per step (1 trot, 2 double support)
+        back = N * (888.0 + (3399.0 - 888.0) * min(nf, 1.0) + (7413.0 - 3399.0) * max(nf - 1.0, 0.0))
+        fwd = N * (166.0 + 75.0 * nf)
+        return 300.0 * N + iters * (back + fwd + 220.0 * N), 0.0
     setup = 450.0 * N
     hess = 157.0 * m * (m + 1) / 2
     it_rest = 300.0 * N
     tensor = 0.0
-    if N == 50:
-        NT = (int(nc) + 8) // 8
-        tiles = sum(k * (k + 1) // 2 for k in range(1, NT))          # trailing tiles incl. look-ahead
-        panel = NT * (NT - 1) // 2
-        tensor = 512.0 * 2 * (tiles + panel)
-        elim = tensor + NT * 300.0 * 32 + 2.0 * nc * nc
-    else:
-        lanes = group_threads
-        elim = lanes * sum((nc / 5.0) * (2 * (nc - s * nc / 5.0) + 10) for s in range(5))
+    lanes = group_threads
+    elim = lanes * sum((nc / 5.0) * (2 * (nc - s * nc / 5.0) + 10) for s in range(5))
     return setup + iters * (hess + elim + it_rest), iters * tensor
 
 
@@ -544,11 +546,11 @@ def run_gpu(args, cfg):
     fp64_peak = measure_fp64_peak(local)
     kernel_ms = ms / K / (cfg["steps"] if rollout else 1)       # per batch-solve (rollout: per control step)
     if cfg["standing"]:
-        nc, gthreads, kname = 6 * N, {10: 64, 20: 64, 50: 256}[N], {10: "tron1_solve_kernel<10,60,2,2,3,INDIRECT>", 20: "tron1_solve_kernel<20,120,2,2,1,INDIRECT>", 50: "tron1_solve_kernel<50,300,8,1,2,INDIRECT>"}[N]
+        nc, gthreads, kname = 6 * N, {10: 64, 20: 64, 50: 32}[N], {10: "tron1_solve_kernel<10,60,2,2,3,INDIRECT>", 20: "tron1_solve_kernel<20,120,2,2,1,INDIRECT>", 50: "tron1_solve_kernel<50,300,1,1,6,DIRECT,RICCATI>"}[N]
     else:
-        nc, gthreads = 3 * N, {10: 32, 20: 64, 50: 256}[N]
+        nc, gthreads = 3 * N, {10: 32, 20: 64, 50: 32}[N]
         kname = {10: "tron1_solve_kernel<10,30,1,4,4,DIRECT,persistent>", 20: "tron1_solve_kernel<20,60,2,2,2,DIRECT,persistent>",
-                 50: "tron1_solve_kernel<50,150,8,1,1,DIRECT,persistent> (tiled DMMA Cholesky)"}[N]
+                 50: "tron1_solve_kernel<50,300,1,1,6,DIRECT,RICCATI> (one warp per instance, Riccati sweeps)"}[N]
         if rollout:
             kname = "tron1_rollout_kernel<10,30,1,4,4>"
     f_exec, f_tensor = structured_flops(N, nc, max(mean_iters, 1.0), gthreads)

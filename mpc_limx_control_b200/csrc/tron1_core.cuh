@@ -1445,6 +1445,17 @@ MPC_HD void ric_lanes(const G& g, RicLane* L, F f) {
     else for (int l = 0; l < 32; ++l) f(l, L[l]);
 }
 
+// inverse of a symmetric positive definite 3 x 3 matrix by cofactors, lower triangle in the order (0,0) (1,0) (1,1) (2,0) (2,1) (2,2);
+// false when a leading minor is not positive
+MPC_HD bool ric_inv3(const double* a, double* inv) {
+    const double c00 = a[2] * a[5] - a[4] * a[4], c10 = a[4] * a[3] - a[1] * a[5], c20 = a[1] * a[4] - a[2] * a[3];
+    const double c11 = a[0] * a[5] - a[3] * a[3], c21 = a[1] * a[3] - a[0] * a[4], c22 = a[0] * a[2] - a[1] * a[1];
+    const double det = a[0] * c00 + a[1] * c10 + a[3] * c20;
+    const double r = 1.0 / det;
+    inv[0] = c00 * r; inv[1] = c10 * r; inv[2] = c11 * r; inv[3] = c20 * r; inv[4] = c21 * r; inv[5] = c22 * r;
+    return a[0] > 0.0 && c22 > 0.0 && det > 0.0;
+}
+
 template <int MM, class WK, class G>
 MPC_HD bool riccati_backward_step(const Tron1Const& P, WK& S, const G& g, RicLane* LL, int k) {
     static_assert(G::kThreads == 32 || G::kThreads == 1, "the Riccati class maps one warp to an instance");
@@ -1551,32 +1562,52 @@ MPC_HD bool riccati_backward_step(const Tron1Const& P, WK& S, const G& g, RicLan
         // phase D (lanes 0..12): one column of [K | kappa] = G^-1 [V' | h] per lane
         ric_lanes(g, LL, [&](int lane, RicLane& L) {
             if (lane > 12) return;
-            double a[MM][MM], rhs[MM], inv[MM];
+            // 3 x 3 blocks with cofactor inverses (one reciprocal per block, shallow dependency chains) instead of a scalar LDL'
+            // with six reciprocals in sequence:  G = [[A, B'], [B, C]],  T = B A^-1,  S = C - T B',
+            // x2 = S^-1 (r2 - T r1),  x1 = A^-1 r1 - T' x2
+            double rhs[MM];
 #pragma unroll
-            for (int i = 0; i < MM; ++i) {
+            for (int i = 0; i < MM; ++i) rhs[i] = (lane < 12) ? L.M[i] : GH[8 * i + 6];
+            double A[6], iA[6];
+            A[0] = GH[0]; A[1] = GH[8]; A[2] = GH[9]; A[3] = GH[16]; A[4] = GH[17]; A[5] = GH[18];
+            if (!ric_inv3(A, iA)) ok = false;
+            if constexpr (MM == 3) {
+                const double r0 = rhs[0], r1 = rhs[1], r2 = rhs[2];
+                rhs[0] = iA[0] * r0 + iA[1] * r1 + iA[3] * r2;
+                rhs[1] = iA[1] * r0 + iA[2] * r1 + iA[4] * r2;
+                rhs[2] = iA[3] * r0 + iA[4] * r1 + iA[5] * r2;
+            } else {
+                double B[3][3], T[3][3], C[6], iS[6];
 #pragma unroll
-                for (int j = 0; j <= i; ++j) a[i][j] = GH[8 * i + j];
-                rhs[i] = (lane < 12) ? L.M[i] : GH[8 * i + 6];
-            }
+                for (int i = 0; i < 3; ++i) {
 #pragma unroll
-            for (int p = 0; p < MM; ++p) {
-                if (!(a[p][p] > 0.0)) ok = false;
-                inv[p] = 1.0 / a[p][p];
-#pragma unroll
-                for (int i = MM - 1; i > p; --i) {          // descending: row i reads the unscaled a[j][p] of the rows j <= i
-                    const double l = a[i][p] * inv[p];
-#pragma unroll
-                    for (int j = p + 1; j <= i; ++j) a[i][j] = fma(-l, a[j][p], a[i][j]);
-                    rhs[i] = fma(-l, rhs[p], rhs[i]);
-                    a[i][p] = l;
+                    for (int j = 0; j < 3; ++j) B[i][j] = GH[8 * (3 + i) + j];
                 }
-            }
 #pragma unroll
-            for (int p = MM - 1; p >= 0; --p) {
-                double v = rhs[p] * inv[p];
+                for (int i = 0; i < 3; ++i) {
+                    T[i][0] = B[i][0] * iA[0] + B[i][1] * iA[1] + B[i][2] * iA[3];
+                    T[i][1] = B[i][0] * iA[1] + B[i][1] * iA[2] + B[i][2] * iA[4];
+                    T[i][2] = B[i][0] * iA[3] + B[i][1] * iA[4] + B[i][2] * iA[5];
+                }
+                int q = 0;
 #pragma unroll
-                for (int i = p + 1; i < MM; ++i) v = fma(-a[i][p], rhs[i], v);
-                rhs[p] = v;
+                for (int i = 0; i < 3; ++i) {
+#pragma unroll
+                    for (int j = 0; j <= i; ++j, ++q)
+                        C[q] = GH[8 * (3 + i) + 3 + j] - (T[i][0] * B[j][0] + T[i][1] * B[j][1] + T[i][2] * B[j][2]);
+                }
+                if (!ric_inv3(C, iS)) ok = false;
+                const double r0 = rhs[0], r1 = rhs[1], r2 = rhs[2];
+                const double s0 = rhs[3] - (T[0][0] * r0 + T[0][1] * r1 + T[0][2] * r2);
+                const double s1 = rhs[4] - (T[1][0] * r0 + T[1][1] * r1 + T[1][2] * r2);
+                const double s2 = rhs[5] - (T[2][0] * r0 + T[2][1] * r1 + T[2][2] * r2);
+                const double x3 = iS[0] * s0 + iS[1] * s1 + iS[3] * s2;
+                const double x4 = iS[1] * s0 + iS[2] * s1 + iS[4] * s2;
+                const double x5 = iS[3] * s0 + iS[4] * s1 + iS[5] * s2;
+                rhs[0] = iA[0] * r0 + iA[1] * r1 + iA[3] * r2 - (T[0][0] * x3 + T[1][0] * x4 + T[2][0] * x5);
+                rhs[1] = iA[1] * r0 + iA[2] * r1 + iA[4] * r2 - (T[0][1] * x3 + T[1][1] * x4 + T[2][1] * x5);
+                rhs[2] = iA[3] * r0 + iA[4] * r1 + iA[5] * r2 - (T[0][2] * x3 + T[1][2] * x4 + T[2][2] * x5);
+                rhs[3] = x3; rhs[4] = x4; rhs[5] = x5;
             }
 #pragma unroll
             for (int i = 0; i < MM; ++i) KT[6 * lane + i] = rhs[i];      // this step's update reads the compact gains
@@ -1617,7 +1648,7 @@ MPC_HD bool riccati_backward_step(const Tron1Const& P, WK& S, const G& g, RicLan
             }
             L.s = v + wqr * (S.rc + WK::RC_E0)[12 * k + lane];
         });
-        g.sync();      // KT / XM are rewritten by the next step
+        // no barrier here: the rows stay in their lanes' registers, and every exchange buffer is next written behind another barrier
         MPC_RTICK(1, S, g, 9);
     }
     return ok;
@@ -1629,15 +1660,14 @@ template <class WK, class G>
 MPC_HD void ric_fetch_gains(WK& S, const G& g, int k) {
     if constexpr (!WK::AINL) {
         if (k < WK::N) {
+            // the whole 78-double block of the step, 16 bytes per copy (rows of a swing foot hold stale data and are never read)
             const double* Kn = S.Kp() + 78 * k;
             double* dst = S.rc + WK::RC_KF + 78 * (k & 3);
-            const bool inl = S.contact[2 * k] != 0, inr = S.contact[2 * k + 1] != 0;
-            for (int it = g.tid(); it < 78; it += G::kThreads) {
-                if (!(it < 39 ? inl : inr)) continue;          // rows of a swing foot are neither written nor read
+            for (int it = g.tid(); it < 39; it += G::kThreads) {
 #if defined(__CUDA_ARCH__)
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst + it)), "l"(Kn + it) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst + 2 * it)), "l"(Kn + 2 * it) : "memory");
 #else
-                dst[it] = Kn[it];
+                dst[2 * it] = Kn[2 * it]; dst[2 * it + 1] = Kn[2 * it + 1];
 #endif
             }
         }
@@ -1668,40 +1698,37 @@ MPC_HD void riccati_forward_step(const Tron1Const& P, WK& S, const G& g, int k) 
             double v = 0.0;
             if (i < 3 ? inl : inr) {
                 const double* row = Kk + 13 * i;
-                double v0 = row[12], v1 = 0.0;
+                double v0 = row[12], v1 = 0.0, v2 = 0.0;
 #pragma unroll
-                for (int l = 0; l < 12; l += 2) { v0 = fma(row[l], d[l], v0); v1 = fma(row[l + 1], d[l + 1], v1); }
-                v = v0 + v1;
+                for (int l = 0; l < 12; l += 3) { v0 = fma(row[l], d[l], v0); v1 = fma(row[l + 1], d[l + 1], v1); v2 = fma(row[l + 2], d[l + 2], v2); }
+                v = v0 + (v1 + v2);
             }
             uk[i] = v;
         }
         g.sync();
     }
     MPC_RTICK(2, S, g, 5);
+    // d'[r] = d[r] + gam (rho . d_omega) + mu d[9 + c] + al (rho . tau) + lam (uL[c] + uR[c]),  tau = sum_a W_a u_a: the same code in
+    // every lane, the row's coefficients selected without branches
+    //   Theta rows: rho = row r of Rz', gam = Ts, al = Ts^2/2;  p rows: mu = Ts, lam = Ts^2/(2m);  omega rows: rho = e_c, al = Ts;  v rows: lam = Ts/m
     const double cz = S.cs[2 * k], sz = S.cs[2 * k + 1];
     for (int r = g.tid(); r < 12; r += G::kThreads) {
-        // beta_l = (Bv u)_l, l = r mod 6: rows Theta_l / omega_l use the angular part, p / v the linear part
-        const int l = r < 6 ? r : r - 6;
-        double b, b2 = 0.0;
-        if (l < 3) {
-            const double* W0 = S.W + 18 * k + 3 * l;
-            b = Ts * (W0[0] * uk[0] + W0[1] * uk[1] + W0[2] * uk[2] + W0[9] * uk[3] + W0[10] * uk[4] + W0[11] * uk[5]);
-            if (r < 2) {       // the yaw rotation couples Theta_x and Theta_y: the other angular component as well
-                const double* W1 = S.W + 18 * k + 3 * (1 - l);
-                b2 = Ts * (W1[0] * uk[0] + W1[1] * uk[1] + W1[2] * uk[2] + W1[9] * uk[3] + W1[10] * uk[4] + W1[11] * uk[5]);
-            }
-        } else {
-            b = Ts * P.inv_m * (uk[l - 3] + uk[l]);
-        }
-        double v;
-        if (r < 2) {
-            const double am = d[6 + r] + 0.5 * b, ao = d[7 - r] + 0.5 * b2;     // own and other angular-rate term
-            v = d[r] + Ts * (r == 0 ? (cz * am + sz * ao) : (-sz * ao + cz * am));
-        } else if (r < 6) {
-            v = d[r] + Ts * (d[r + 6] + 0.5 * b);
-        } else {
-            v = d[r] + b;
-        }
+        const int c = r % 3, blk = r / 3;      // blk: 0 Theta, 1 p, 2 omega, 3 v
+        const double* W0 = S.W + 18 * k;
+        double tau[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+            tau[i] = (W0[3 * i] * uk[0] + W0[3 * i + 1] * uk[1] + W0[3 * i + 2] * uk[2]) + (W0[9 + 3 * i] * uk[3] + W0[10 + 3 * i] * uk[4] + W0[11 + 3 * i] * uk[5]);
+        const bool rot = blk == 0;
+        const double rho0 = rot ? (c == 0 ? cz : (c == 1 ? -sz : 0.0)) : (c == 0 ? 1.0 : 0.0);
+        const double rho1 = rot ? (c == 0 ? sz : (c == 1 ? cz : 0.0)) : (c == 1 ? 1.0 : 0.0);
+        const double rho2 = c == 2 ? 1.0 : 0.0;
+        const double gam = blk == 0 ? Ts : 0.0, mu = blk == 1 ? Ts : 0.0;
+        const double al = blk == 0 ? 0.5 * Ts * Ts : (blk == 2 ? Ts : 0.0);
+        const double lam = blk == 1 ? 0.5 * Ts * Ts * P.inv_m : (blk == 3 ? Ts * P.inv_m : 0.0);
+        const double rw = rho0 * d[6] + rho1 * d[7] + rho2 * d[8];
+        const double rt = rho0 * tau[0] + rho1 * tau[1] + rho2 * tau[2];
+        const double v = d[r] + gam * rw + mu * d[9 + c] + al * rt + lam * (uk[c] + uk[3 + c]);
         dn[r] = v;
         S.ee[12 * (k + 1) + r] = v + (S.rc + WK::RC_E0)[12 * (k + 1) + r];     // full tracking error for the gradient pass
     }
