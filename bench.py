@@ -92,13 +92,14 @@ def structured_flops(N, nc, iters, group_threads):
     m = nc / 3.0
     if N == 50:
         # Riccati class (horizon 50): no matrix, one backward and one forward sweep per active-face solve.  Per step with nf stance
-        # feet (counted per ACTIVE lane of the warp, phases A-E of riccati_backward_step): nf = 0: 888, nf = 1: 3399, nf = 2: 7413
-        # (A: 360 + 372 nf, B: 468 + 108 nf, C: 237 / 690, D: 13 columns x (LDL' + two triangular solves + force-space rows) =
-        # 858 / 3003, E: 12 rows x (26 mm + 5)); forward step 166 + 75 nf; gradient (one adjoint pass) + check ~ 220 N; setup
-        # without f ~ 300 N.  Checked against ncu (profiles/r2b_c4*): 413 k computed against 410 k executed for double support.
+        # feet (counted per ACTIVE lane of the warp, phases A-E of riccati_backward_step): nf = 0: 888, nf = 1: 3373, nf = 2: 7595
+        # (A: 360 + 372 nf, B: 468 + 108 nf, C: 237 / 690, D: 13 columns x (3x3-block cofactor inverses + solves + force-space
+        # rows) = 832 / 3185, E: 12 rows x (26 mm + 5)); forward step 12 lanes x 53 + 81 nf; gradient (one adjoint pass) + check
+        # ~ 220 N; setup without f ~ 300 N.  Checked against ncu: 233.6 k computed against 246.5 k executed per trot solve
+        # (profiles/r2c_c4_solve_kernel.json), 413 k against 410 k per double-support solve with the first forward step version.
         nf = m / N                                   # stance feet per step (1 trot, 2 double support)
-        back = N * (888.0 + (3399.0 - 888.0) * min(nf, 1.0) + (7413.0 - 3399.0) * max(nf - 1.0, 0.0))
-        fwd = N * (166.0 + 75.0 * nf)
+        back = N * (888.0 + (3373.0 - 888.0) * min(nf, 1.0) + (7595.0 - 3373.0) * max(nf - 1.0, 0.0))
+        fwd = N * (636.0 + 81.0 * nf)
         return 300.0 * N + iters * (back + fwd + 220.0 * N), 0.0
     setup = 450.0 * N
     hess = 157.0 * m * (m + 1) / 2
