@@ -51,7 +51,8 @@ CONFIGS = {
     "3": dict(N=20, B=65536, seed=1002, Ts=0.005, standing=False, scale=1.0, mu=0.5, kind="solve", scaling="strong",
               what="randomised yaw / foot positions / gait phase, sharded by instance (BASELINE configs[2])"),
     "4": dict(N=50, B=8192, seed=1003, Ts=0.005, standing=False, scale=1.0, mu=0.5, kind="solve", scaling="strong",
-              what="long horizon, reduced Hessian 150x150 per instance, tensor-core Cholesky (BASELINE configs[3])"),
+              what="long horizon, trot gait (150 of the 300 condensed variables active per instance), active-face solves as Riccati sweeps; "
+                   "the tiled FP64 tensor-core Cholesky class runs behind it for uncertified instances (BASELINE configs[3])"),
     "5": dict(N=10, B=16384, seed=1004, Ts=0.005, standing=False, scale=1.0, mu=0.5, kind="rollout", steps=1000, scaling="strong",
               what="closed loop: linearise -> condense -> solve -> integrate, warm-started, state resident on the GPU (BASELINE configs[4])"),
 }
