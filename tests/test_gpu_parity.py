@@ -647,6 +647,40 @@ def test_every_instance_vs_oracle_horizons_20_50(torch_cuda, N, B, standing_ever
     eng.close()
 
 
+def test_horizon50_riccati_class_hands_uncertified_instances_to_the_dense_class(torch_cuda):
+    """Horizon 50 runs its active-face solves as Riccati sweeps (one warp per instance); an instance whose active-face iteration
+    does not certify within max_newton solves is appended to the overflow list and solved from scratch by the dense
+    tensor-core class behind it.  max_newton = 1 forces that hand-over for every instance that leaves the interior face; the
+    same batch with the default cap is solved by the Riccati class alone.  Both must agree with the oracle."""
+    torch = torch_cuda
+    N, B, Ts = 50, 96, 0.005
+    d = synth.tron1_batch(777, B, N, Ts)
+    d["iter"][::3] = -1                                      # every third robot stands: two stance feet per step
+    d["x0"][:, [0, 1, 6, 7, 8, 9, 10, 11]] *= 3.0            # many instances leave the interior face
+    t = to_dev(torch, d)
+    po = O.tron1_defaults(Ts=Ts, mu=0.3)
+    c_ref = np.stack([O.contact_schedule(int(i), N) for i in d["iter"]])
+    Fo, so, _ = O.tron1_solve_batch(po, N, d["x0"], d["x_ref"], d["feet"], c_ref, nthreads=os.cpu_count() or 8)
+    assert (so == 0).all()
+    scale = np.maximum(1.0, np.abs(Fo).reshape(B, -1).max(1))
+    res = {}
+    for cap in (8, 1):
+        eng = make_engine(N, B, Ts=Ts, mu=0.3, max_newton=cap)
+        F, st, it = eng.solve(t["x0"], t["x_ref"], t["feet"], it=t["iter"])
+        torch.cuda.synchronize()
+        F, st, it = F.cpu().numpy(), st.cpu().numpy(), it.cpu().numpy()
+        res[cap] = (F, st, it)
+        assert np.isin(st, (0, 1)).all() and np.isfinite(F).all()
+        ok = st == 0
+        assert ok.mean() > 0.9                               # the dense class polishes its ADMM iterates on the active face
+        err = np.abs(F - Fo).reshape(B, -1).max(1) / scale
+        assert err[ok].max() < 1e-4, (cap, int(err.argmax()), float(err.max()))
+        assert np.all(F.reshape(B, N, 2, 3)[c_ref == 0] == 0.0)
+        eng.close()
+    assert res[8][2].max() > 1 and (res[8][1] == 0).all()     # several faces per instance inside the Riccati class
+    assert (res[1][2] > 1).any()                              # handed over: the dense class iterated (ADMM) on them
+
+
 @pytest.mark.parametrize("N,B,standing_every", [(10, 3001, 0), (10, 4096, 3), (20, 2048, 0), (50, 2100, 6)])
 def test_host_auto_path_large_batches(torch_cuda, N, B, standing_every):
     """Pinned buffers at full batch sizes through the host entry (AUTO and forced zero-copy), mixed capacity classes,
