@@ -84,7 +84,7 @@ using namespace mpcb200;
 #define MPC_RIC_IPC 1
 #endif
 #ifndef MPC_RIC_MINB
-#define MPC_RIC_MINB 6
+#define MPC_RIC_MINB 7
 #endif
 // Riccati class of horizon 50: the per-step gains (300 x 13 doubles at full capacity) live in global memory, in slabs drawn
 // from a ring of free slabs sized for the resident CTAs (L2-resident working set) -- 1 = external, 0 = inside shared memory
@@ -265,7 +265,24 @@ tron1_solve_kernel(const __grid_constant__ Tron1Const P, int B, const double* __
         if (g.t == 0) { for (int i = 0; i < 16; ++i) S.prof[i] = 0; S.t_last = clock64(); }
         g.sync();
 #endif
-        int code = solve_instance<Work>(P, S, xr_s, g, its);
+        // Riccati work type: a further active-face iteration needs the inputs again (plain loads: rare); the staging area has
+        // been the adjoint scratch of the gradient pass in between
+        auto restage = [&]() {
+            if constexpr (RIC) {
+                g.sync();
+                double* sx = st.xr + g.gid * XR; double* s0 = st.x0 + g.gid * 13; double* sf = st.feet + g.gid * fstride;
+                for (int i = g.t; i < 13; i += g.size()) s0[i] = x0[(size_t)b * 13 + i];
+                for (int i = g.t; i < fstride; i += g.size()) sf[i] = feet[(size_t)b * fstride + i];
+                if (cmd_oy) {
+                    g.sync();
+                    make_reference(s0, cmd_oy[b], cmd_vx[b], P.Ts, N, sx, g);
+                } else {
+                    for (int i = g.t; i < XR; i += g.size()) sx[i] = xref[(size_t)b * XR + i];
+                }
+                g.sync();
+            }
+        };
+        int code = solve_instance<Work>(P, S, xr_s, g, its, false, NoHook(), restage);
 #if defined(MPC_PHASE_TIMING)
         MPC_TICK(S, g, 13);
         if (g.t == 0) for (int i = 0; i < 16; ++i) atomicAdd(&g_phase_cycles[i], (unsigned long long)S.prof[i]);

@@ -109,9 +109,9 @@ template <int RC_TOTAL_>
 struct RicStore<false, RC_TOTAL_> {};
 template <int N, int NC, bool AINL>
 struct RicLayout {
-    // saved free-response error e0 [(N+1) x 12], force-space gain rows [Ku (12) | ku0] (6 per step), and the exchange buffers of
-    // one step (riccati_backward_step / riccati_forward_step)
-    static constexpr int RC_E0 = 0, RC_K = RC_E0 + (N + 1) * 12, RC_XM = RC_K + (AINL ? NC * 13 : 0), RC_U6 = RC_XM + 120,
+    // force-space gain rows [Ku (12) | ku0] (6 per step, when inside the struct) and the exchange buffers of one step
+    // (riccati_backward_step / riccati_forward_step)
+    static constexpr int RC_K = 0, RC_XM = RC_K + (AINL ? NC * 13 : 0), RC_U6 = RC_XM + 120,
                          RC_GH = RC_U6 + 48, RC_KT = RC_GH + 48, RC_WQ = RC_KT + 78, RC_D = RC_WQ + 12,
                          RC_KF = RC_D + 24, RC_TOTAL = RC_KF + (AINL ? 0 : 4 * 78);
 };
@@ -140,7 +140,7 @@ struct Tron1Work : RicStore<RIC_, RicLayout<N_, NC_, AINL_>::RC_TOTAL> {
     alignas(16) double colbuf[RIC_ ? 2 : 2 * CBS];   // double-buffered broadcast copy of the current pivot column
     double w[RIC_ ? 2 : NC], z[RIC_ ? 2 : NC], y[RIC_ ? 2 : NC];   // compact solve vector, ADMM iterates
     using RL = RicLayout<N_, NC_, AINL_>;
-    static constexpr int RC_E0 = RL::RC_E0, RC_K = RL::RC_K, RC_XM = RL::RC_XM, RC_U6 = RL::RC_U6, RC_GH = RL::RC_GH, RC_KT = RL::RC_KT,
+    static constexpr int RC_K = RL::RC_K, RC_XM = RL::RC_XM, RC_U6 = RL::RC_U6, RC_GH = RL::RC_GH, RC_KT = RL::RC_KT,
                          RC_WQ = RL::RC_WQ, RC_D = RL::RC_D, RC_KF = RL::RC_KF, RC_TOTAL = RL::RC_TOTAL;
     double W[N * 18];       // W[k][foot] 3x3 row-major:  Iw_k^-1 [r]x
     double cs[N * 2];       // cos, sin of yaw_k
@@ -148,7 +148,9 @@ struct Tron1Work : RicStore<RIC_, RicLayout<N_, NC_, AINL_>::RC_TOTAL> {
     double dc[N], ds[N];    // D_j = 1/2 Rz_j' - C_{j+1}  (cos-like / sin-like entries)
     double SW[RIC_ ? 8 : N * 8];       // suffix sums over i>j of w_i * {1, cc, ss, cc^2, ss^2, cc ss, i, i^2}
     // Riccati work type: f is never formed (the gradient is the adjoint of the full tracking error), adj lives in the
-    // caller's dead input staging area (adjx), g and res overlay the exchange buffers of the sweeps
+    // caller's dead input staging area (adjx), g and res overlay the exchange buffers of the sweeps, and ee holds the
+    // free-response error e0 until the forward sweep adds the input response in place (a further active-face iteration
+    // rebuilds e0 from the re-staged inputs)
     static constexpr int RC_X = RC_TOTAL - RC_XM;                 // doubles of exchange buffers
     static constexpr bool GALIAS = RIC_ && (8 * N <= RC_X);
     double f[RIC_ ? 2 : NV];             // full layout: linear term (live for the whole solve)
@@ -1646,7 +1648,7 @@ MPC_HD bool riccati_backward_step(const Tron1Const& P, WK& S, const G& g, RicLan
 #pragma unroll
                 for (int a = 0; a < MM; ++a) v = fma(-L.M[a], KT[6 * 12 + a], v);
             }
-            L.s = v + wqr * (S.rc + WK::RC_E0)[12 * k + lane];
+            L.s = v + wqr * S.ee[12 * k + lane];
         });
         // no barrier here: the rows stay in their lanes' registers, and every exchange buffer is next written behind another barrier
         MPC_RTICK(1, S, g, 9);
@@ -1730,7 +1732,7 @@ MPC_HD void riccati_forward_step(const Tron1Const& P, WK& S, const G& g, int k) 
         const double rt = rho0 * tau[0] + rho1 * tau[1] + rho2 * tau[2];
         const double v = d[r] + gam * rw + mu * d[9 + c] + al * rt + lam * (uk[c] + uk[3 + c]);
         dn[r] = v;
-        S.ee[12 * (k + 1) + r] = v + (S.rc + WK::RC_E0)[12 * (k + 1) + r];     // full tracking error for the gradient pass
+        S.ee[12 * (k + 1) + r] += v;     // e0 + B u: the full tracking error for the gradient pass (e0 is rebuilt for a further face)
     }
     g.sync();
     MPC_RTICK(2, S, g, 6);
@@ -1750,7 +1752,7 @@ MPC_HD bool riccati_face_solve(const Tron1Const& P, WK& S, const G& g) {
             const double wq = wN * (S.rc + WK::RC_WQ)[r];
 #pragma unroll
             for (int j = 0; j < 12; ++j) L.Pr[j] = (j == r) ? wq : 0.0;
-            L.s = wq * (S.rc + WK::RC_E0)[12 * N + r];
+            L.s = wq * S.ee[12 * N + r];
 #pragma unroll
             for (int j = 0; j < 6; ++j) L.M[j] = 0.0;
         });
@@ -2126,10 +2128,6 @@ MPC_HD void setup_instance(const Tron1Const& P, WK& S, const double* xref, const
     horizon_sums<WK>(P, S, g);
     MPC_TICK(S, g, 1);
     free_response<WK>(P, S, xref, g);
-    if constexpr (WK::RICCATI) {   // the gradient passes reuse S.ee: keep the free-response error for the sweeps
-        for (int i = g.tid(); i < 12 * (N + 1); i += g.size()) (S.rc + WK::RC_E0)[i] = S.ee[i];
-        g.sync();
-    }
     MPC_TICK(S, g, 2);
     if constexpr (!WK::RICCATI) adjoint<WK>(P, S, S.ee, S.f, g);   // f = 2 B' Q (A x0 - x_ref)   (src/QPSolver.cpp:59-60)
     MPC_TICK(S, g, 3);
@@ -2140,9 +2138,12 @@ MPC_HD void setup_instance(const Tron1Const& P, WK& S, const double* xref, const
 // `after_setup` runs once the staged inputs (xref, S.x0, S.feet) are dead: everything the iterations need has been
 // condensed into S by then, so a persistent kernel starts fetching its next instance into the same staging area there.
 struct NoHook { MPC_HD void operator()() const {} };
-template <class WK, class G, class Hook = NoHook>
+// `restage` (Riccati work type only) brings the instance's inputs (S.x0, S.feet, xref) back before a further active-face
+// iteration: that work type keeps no copy of the free-response error once the forward sweep has run, and its caller has
+// reused the input staging area in between.
+template <class WK, class G, class Hook = NoHook, class Hook2 = NoHook>
 MPC_HD int solve_instance(const Tron1Const& P, WK& S, const double* xref, const G& g, int& iters, bool warm = false,
-                          Hook after_setup = Hook()) {
+                          Hook after_setup = Hook(), Hook2 restage = Hook2()) {
     [[maybe_unused]] constexpr int N = WK::N;
     setup_instance<WK>(P, S, xref, g, warm);
     after_setup();
@@ -2187,6 +2188,12 @@ MPC_HD int solve_instance(const Tron1Const& P, WK& S, const double* xref, const 
     // phase A: active-face (semismooth Newton) iterations, cold start from the interior face
     for (int it = 0; it < P.max_newton; ++it) {
         ++iters;
+        if constexpr (WK::RICCATI) {
+            if (it > 0) {         // S.ee holds e0 + B u of the previous face: rebuild e0
+                restage();
+                free_response<WK>(P, S, xref, g);
+            }
+        }
         if (!face_solve<WK>(P, S, g)) return ST_FAILED;
         if (check_optimality<WK>(P, S, g, changed, resid)) return ST_SOLVED;
         if (!changed) break;   // same face predicted but not optimal: numerical stall -> ADMM
