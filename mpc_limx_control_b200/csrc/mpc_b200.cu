@@ -74,6 +74,11 @@ using namespace mpcb200;
 #ifndef MPC_RIC_N20
 #define MPC_RIC_N20 0
 #endif
+// horizon 20: Riccati work type as the LIST-DRIVEN class (double support: 18 against 1.9 M solves/s for the packed Cholesky), the dense
+// class behind it on a second list
+#ifndef MPC_RIC_L_N20
+#define MPC_RIC_L_N20 1
+#endif
 #ifndef MPC_RIC_N10
 #define MPC_RIC_N10 0
 #endif
@@ -288,9 +293,13 @@ tron1_solve_kernel(const __grid_constant__ Tron1Const P, int B, const double* __
         if (g.t == 0) for (int i = 0; i < 16; ++i) atomicAdd(&g_phase_cycles[i], (unsigned long long)S.prof[i]);
 #endif
         if (RIC && code == ST_DEFER) {
-            // Riccati class: the active-face iteration did not certify -> the dense class solves the instance from scratch
+            // Riccati class: the active-face iteration did not certify -> the dense class solves the instance from scratch.
+            // As the direct class it appends to the overflow list; as the list-driven class it appends to the SECOND list
+            // (ext_A carries it: this instantiation keeps its gains in shared memory), counters ovf_count[2..3]
             if (g.t == 0) {
-                if (ovf_list) ovf_list[atomicAdd(ovf_count, 1)] = b;
+                int32_t* dl = INDIRECT ? reinterpret_cast<int32_t*>(ext_A) : ovf_list;
+                int32_t* dc = INDIRECT ? ovf_count + 2 : ovf_count;
+                if (dl) dl[atomicAdd(dc, 1)] = b;
                 else if (status) status[b] = ST_FAILED;
             }
             return;
@@ -718,6 +727,7 @@ struct mpc_b200_engine {
     double *d_x0 = nullptr, *d_xref = nullptr, *d_feet = nullptr, *d_forces = nullptr;
     uint8_t* d_contact = nullptr;
     int32_t *d_iter = nullptr, *d_status = nullptr, *d_iters = nullptr;
+    int32_t* d_ovf_list2 = nullptr;                          // second overflow list (instances the list-driven Riccati class hands to the dense class)
     int32_t *d_ovf_list = nullptr, *d_ovf_count = nullptr;   // per slot: {overflow length, readers, next instance, finished CTAs}
     double *d_oy = nullptr, *d_vx = nullptr, *d_u0 = nullptr; // controller-shaped entry: commands in, first-step force out
     static constexpr int kPipe = 8;                          // streams used by the host-buffer entry
@@ -769,7 +779,10 @@ static size_t solve_smem_bytes() {
 }
 
 // small class (direct, TMA-staged) followed by the large class (indirect, overflow list)
-template <int N, int WPI_S, int IPC_S, int MINB_S, int WPI_L, int IPC_L, bool AINL_L = true, int MINB_L = 1, bool RIC_S = false, bool AINL_S = true>
+// RIC_L: the list-driven class is the Riccati work type (gains in shared memory); the instances it does not certify go to a second
+// list and a third, dense list-driven launch <WPI_D, IPC_D, MINB_D> (always launched: it also resets the second list's counters)
+template <int N, int WPI_S, int IPC_S, int MINB_S, int WPI_L, int IPC_L, bool AINL_L = true, int MINB_L = 1, bool RIC_S = false, bool AINL_S = true,
+          bool RIC_L = false, int WPI_D = 2, int IPC_D = 2, int MINB_D = 1>
 static int launch_solve(mpc_b200_engine* e, int B, const double* x0, const double* xref, const double* feet,
                         const uint8_t* contact, const int32_t* iter, double* forces, int32_t* status,
                         int32_t* iters, cudaStream_t s, int32_t* ovf_list, int32_t* ovf_count,
@@ -780,14 +793,34 @@ static int launch_solve(mpc_b200_engine* e, int B, const double* x0, const doubl
     // behind it takes the instances whose active-face iteration did not certify -- both kernels always run
     constexpr int NC_S = RIC_S ? 6 * N : 3 * N;
     auto ks = tron1_solve_kernel<N, NC_S, WPI_S, IPC_S, MINB_S, false, AINL_S, (MPC_DYNAMIC != 0) && !RIC_S, RIC_S>;
-    auto kl = tron1_solve_kernel<N, 6 * N, WPI_L, IPC_L, MINB_L, true, AINL_L>;
+    auto kl = tron1_solve_kernel<N, 6 * N, WPI_L, IPC_L, MINB_L, true, AINL_L, false, RIC_L>;
+    auto kd = tron1_solve_kernel<N, 6 * N, WPI_D, IPC_D, MINB_D, true, true>;
+    static_assert(!RIC_L || (AINL_L && MPC_DYNAMIC == 0), "the second overflow list uses the counters of the dynamic scheduler");
+    const size_t smem_d = ((sizeof(CtaStage<N, IPC_D>) + 15) & ~size_t(15)) + sizeof(SolveWork<N, 6 * N, true, WPI_D>) * IPC_D;
+    int32_t* ovf2 = RIC_L ? e->d_ovf_list2 + (ovf_list - e->d_ovf_list) : nullptr;
+    auto launch_dense_behind = [&]() -> int {     // third launch: the dense class over the second list
+        int grid_d = (B + IPC_D - 1) / IPC_D;
+        if (grid_d > e->num_sms * (MINB_D > 2 ? MINB_D : 2)) grid_d = e->num_sms * (MINB_D > 2 ? MINB_D : 2);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid_d); cfg.blockDim = dim3(32 * WPI_D * IPC_D); cfg.dynamicSmemBytes = smem_d; cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        CU(e, cudaLaunchKernelEx(&cfg, kd, e->C, B, x0, xref, feet, contact, iter, forces, status, iters, ovf2, ovf_count + 2,
+                                 (double*)nullptr, cmd_oy, cmd_vx, first_only));
+        CU(e, cudaGetLastError());
+        e->launches += 1;
+        return MPC_B200_OK;
+    };
     const size_t smem_s = ((sizeof(CtaStage<N, IPC_S>) + 15) & ~size_t(15)) + sizeof(SolveWork<N, NC_S, AINL_S, WPI_S, RIC_S>) * IPC_S;
     if (RIC_S) cls_hint = 1;
-    const size_t smem_l = ((sizeof(CtaStage<N, IPC_L>) + 15) & ~size_t(15)) + sizeof(SolveWork<N, 6 * N, AINL_L, WPI_L>) * IPC_L;
+    const size_t smem_l = ((sizeof(CtaStage<N, IPC_L>) + 15) & ~size_t(15)) + sizeof(SolveWork<N, 6 * N, AINL_L, WPI_L, RIC_L>) * IPC_L;
     static std::atomic<bool> configured[64];      // per device; setting the attribute twice is harmless, so a lost race is too
     if (!configured[e->device & 63].load(std::memory_order_acquire)) {
         CU(e, cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
         CU(e, cudaFuncSetAttribute(kl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l));
+        if (RIC_L) CU(e, cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d));
         configured[e->device & 63].store(true, std::memory_order_release);
     }
     // the large class of horizon 50 keeps its factors in ONE set of global slabs indexed by CTA: two such kernels must
@@ -799,10 +832,11 @@ static int launch_solve(mpc_b200_engine* e, int B, const double* x0, const doubl
         if (!AINL_L && grid > e->num_sms * MINB_L) grid = e->num_sms * MINB_L;     // slab class: only the resident CTAs (L2 working set)
         if (!AINL_L && grid * IPC_L > e->extA_slabs) grid = e->extA_slabs / IPC_L;
         kl<<<grid, 32 * WPI_L * IPC_L, smem_l, s>>>(e->C, B, x0, xref, feet, contact, iter, forces, status, iters, nullptr, ovf_count,
-                                                  AINL_L ? nullptr : e->d_extA, cmd_oy, cmd_vx, first_only);
+                                                  RIC_L ? reinterpret_cast<double*>(ovf2) : (AINL_L ? nullptr : e->d_extA), cmd_oy, cmd_vx, first_only);
         CU(e, cudaGetLastError());
         if (!AINL_L) CU(e, cudaEventRecord(e->extA_free, s));
         e->launches += 1;
+        if (RIC_L) return launch_dense_behind();
         return MPC_B200_OK;
     }
     int grid_s = (B + IPC_S - 1) / IPC_S;
@@ -825,13 +859,14 @@ static int launch_solve(mpc_b200_engine* e, int B, const double* x0, const doubl
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        double* ext = AINL_L ? nullptr : e->d_extA;
+        double* ext = RIC_L ? reinterpret_cast<double*>(ovf2) : (AINL_L ? nullptr : e->d_extA);
         CU(e, cudaLaunchKernelEx(&cfg, kl, e->C, B, x0, xref, feet, contact, iter, forces, status, iters, ovf_list, ovf_count, ext,
                                  cmd_oy, cmd_vx, first_only));
     }
     CU(e, cudaGetLastError());
     if (!AINL_L) CU(e, cudaEventRecord(e->extA_free, s));
     e->launches += 2;
+    if (RIC_L) return launch_dense_behind();
     return MPC_B200_OK;
 }
 
@@ -854,6 +889,9 @@ static int dispatch_solve(mpc_b200_engine* e, int B, const double* x0, const dou
         case 20:
 #if MPC_RIC_N20
             return launch_solve<20, MPC_RIC_WPI, MPC_RIC_IPC, MPC_RIC_MINB, 2, 2, true, 1, true>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only, cls_hint);
+#endif
+#if MPC_RIC_L_N20
+            return launch_solve<20, MPC_N20_WPI_S, MPC_N20_IPC_S, MPC_N20_MINB_S, 1, 1, true, 8, false, true, true, 2, 2, 1>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only, cls_hint);
 #endif
             return launch_solve<20, MPC_N20_WPI_S, MPC_N20_IPC_S, MPC_N20_MINB_S, 2, 2>(e, B, x0, xref, feet, contact, iter, forces, status, iters, s, ol, oc, cmd_oy, cmd_vx, first_only, cls_hint);
         case 50:
@@ -932,6 +970,7 @@ int mpc_b200_create(const mpc_b200_tron1_params* p, int horizon, int max_batch, 
               cudaMalloc(&e->d_status, sizeof(int32_t) * max_batch) == cudaSuccess &&
               cudaMalloc(&e->d_iters, sizeof(int32_t) * max_batch) == cudaSuccess &&
               cudaMalloc(&e->d_ovf_list, sizeof(int32_t) * (size_t)max_batch * (1 + mpc_b200_engine::kLanes)) == cudaSuccess &&
+              cudaMalloc(&e->d_ovf_list2, sizeof(int32_t) * (size_t)max_batch * (1 + mpc_b200_engine::kLanes)) == cudaSuccess &&
               cudaMalloc(&e->d_ovf_count, 4 * (mpc_b200_engine::kPipe + 1 + mpc_b200_engine::kLanes) * sizeof(int32_t)) == cudaSuccess &&
               cudaMemset(e->d_ovf_count, 0, 4 * (mpc_b200_engine::kPipe + 1 + mpc_b200_engine::kLanes) * sizeof(int32_t)) == cudaSuccess &&
               cudaMalloc(&e->d_oy, sizeof(double) * max_batch) == cudaSuccess &&
@@ -982,7 +1021,7 @@ int mpc_b200_destroy(mpc_b200_engine* e) {
     if (e->stream) { cudaStreamSynchronize(e->stream); cudaStreamDestroy(e->stream); }
     cudaFree(e->d_x0); cudaFree(e->d_xref); cudaFree(e->d_feet); cudaFree(e->d_forces);
     cudaFree(e->d_contact); cudaFree(e->d_iter); cudaFree(e->d_status); cudaFree(e->d_iters);
-    cudaFree(e->d_ovf_list); cudaFree(e->d_ovf_count);
+    cudaFree(e->d_ovf_list); cudaFree(e->d_ovf_list2); cudaFree(e->d_ovf_count);
     cudaFree(e->d_oy); cudaFree(e->d_vx); cudaFree(e->d_u0);
     for (int i = 0; i < mpc_b200_engine::kPipe; ++i) if (e->pipe[i]) { cudaStreamSynchronize(e->pipe[i]); cudaStreamDestroy(e->pipe[i]); }
     if (e->h_small) cudaFreeHost(e->h_small);

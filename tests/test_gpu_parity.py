@@ -486,7 +486,8 @@ def test_host_paths_all_double_support_batches(torch_cuda):
             ip = torch.zeros(B, dtype=torch.int32).pin_memory()
             l1 = eng.launch_count()
             eng.solve_host(pin["x0"], pin["x_ref"], pin["feet"], contact=pin["contact"], forces=Fp, status=sp, iters=ip)   # pinned
-            assert eng.last_host_path() == 1 and eng.launch_count() - l1 == 1                          # one kernel, not two
+            # no direct pass: the list-driven class alone (horizon 20: the Riccati list class plus the dense class behind it on its second list)
+            assert eng.last_host_path() == 1 and eng.launch_count() - l1 == (1 if N == 10 else 2)
             assert np.array_equal(Fp.numpy(), F) and np.array_equal(sp.numpy(), st)
             eng.close()
 
