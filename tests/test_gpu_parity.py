@@ -648,13 +648,16 @@ def test_every_instance_vs_oracle_horizons_20_50(torch_cuda, N, B, standing_ever
     eng.close()
 
 
-def test_horizon50_riccati_class_hands_uncertified_instances_to_the_dense_class(torch_cuda):
+@pytest.mark.parametrize("N", [50, 20])
+def test_horizon50_riccati_class_hands_uncertified_instances_to_the_dense_class(torch_cuda, N):
     """Horizon 50 runs its active-face solves as Riccati sweeps (one warp per instance); an instance whose active-face iteration
     does not certify within max_newton solves is appended to the overflow list and solved from scratch by the dense
     tensor-core class behind it.  max_newton = 1 forces that hand-over for every instance that leaves the interior face; the
-    same batch with the default cap is solved by the Riccati class alone.  Both must agree with the oracle."""
+    same batch with the default cap is solved by the Riccati class alone.  Both must agree with the oracle.
+    Horizon 20: the Riccati work type is the LIST-DRIVEN class (the standing third of the batch); its hand-over goes through the
+    second overflow list to a third, dense launch."""
     torch = torch_cuda
-    N, B, Ts = 50, 96, 0.005
+    B, Ts = 96, 0.005
     d = synth.tron1_batch(777, B, N, Ts)
     d["iter"][::3] = -1                                      # every third robot stands: two stance feet per step
     d["x0"][:, [0, 1, 6, 7, 8, 9, 10, 11]] *= 3.0            # many instances leave the interior face
