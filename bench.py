@@ -616,7 +616,13 @@ def run_gpu(args, cfg):
                      "ncu_check": ncu_exec,
                      "dense_equiv": {"flops_per_solve": f_dense, "achieved": f_dense * B / (kernel_ms * 1e-3) / 1e12, "unit": "TFLOP/s",
                                      "what": "SURVEY 8d DENSE accounting (n^2 p condensing, n^3/3 Cholesky): how fast the PROBLEM is "
-                                             "solved relative to a dense evaluation; can exceed the peak, not a hardware fraction"}},
+                                             "solved relative to a dense evaluation; can exceed the peak, not a hardware fraction"},
+                     "replaced_kernel": None if N != 50 else {
+                         "kernel": "tron1_solve_kernel<50,150,8,1,1,DIRECT> / <50,300,16,1,1,INDIRECT> (tiled DMMA Cholesky of the condensed Hessian)",
+                         "value": 3.26e6, "double_support_value": 0.65e6, "unit": "solves/s", "flops_per_solve": 1.81e6, "frac": 0.19,
+                         "source": "profiles/r2_bench_config4.json, profiles/r2_c4_solve_kernel.json (same box class, same workload)",
+                         "what": "the O(n^3) class this kernel replaced as the direct class of horizon 50 (-DMPC_RIC_N50=0 restores it): "
+                                 "8x the executed arithmetic at 5x the pipe utilisation, 0.55x the throughput (double support: 0.1x)"}},
         "roofline_hbm": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved_gbs / hbm_peak, "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
