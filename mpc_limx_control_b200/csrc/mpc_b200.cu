@@ -89,7 +89,7 @@ using namespace mpcb200;
 #define MPC_RIC_IPC 1
 #endif
 #ifndef MPC_RIC_MINB
-#define MPC_RIC_MINB 7
+#define MPC_RIC_MINB 8
 #endif
 // Riccati class of horizon 50: the per-step gains (300 x 13 doubles at full capacity) live in global memory, in slabs drawn
 // from a ring of free slabs sized for the resident CTAs (L2-resident working set) -- 1 = external, 0 = inside shared memory
@@ -305,10 +305,10 @@ tron1_solve_kernel(const __grid_constant__ Tron1Const P, int B, const double* __
             return;
         }
         if (first_step_only) {
-            if (g.t < 6) forces[(size_t)b * 6 + g.t] = S.u[g.t];
+            if (g.t < 6) forces[(size_t)b * 6 + g.t] = S.up()[g.t];
         } else {
             double* out = forces + (size_t)b * 6 * N;
-            for (int i = g.t; i < 6 * N; i += g.size()) out[i] = S.u[i];
+            for (int i = g.t; i < 6 * N; i += g.size()) out[i] = S.up()[i];
         }
         if (g.t == 0) {
             if (status) status[b] = code;
@@ -406,10 +406,10 @@ tron1_solve_kernel(const __grid_constant__ Tron1Const P, int B, const double* __
                 }
                 const int code = solve_instance<Work>(P, S, sx, g, its, false, prefetch_next);
                 if (first_step_only) {
-                    if (g.t < 6) forces[(size_t)b * 6 + g.t] = S.u[g.t];
+                    if (g.t < 6) forces[(size_t)b * 6 + g.t] = S.up()[g.t];
                 } else {
                     double* out = forces + (size_t)b * 6 * N;
-                    for (int i = g.t; i < 6 * N; i += g.size()) out[i] = S.u[i];
+                    for (int i = g.t; i < 6 * N; i += g.size()) out[i] = S.up()[i];
                 }
                 if (g.t == 0) {
                     if (status) status[b] = code;
@@ -631,7 +631,7 @@ tron1_rollout_kernel(const __grid_constant__ Tron1Const P, int B, int steps, dou
         g.sync();
         int its = 0;
         const int code = solve_instance<Work>(P, S, xr, g, its, s > 0);
-        if (u_traj && g.t < 6) u_traj[((size_t)b * steps + s) * 6 + g.t] = S.u[g.t];
+        if (u_traj && g.t < 6) u_traj[((size_t)b * steps + s) * 6 + g.t] = S.up()[g.t];
         bad += code != 0;
         tot += its;
         integrate_state<Work>(P, S, xs, g);

@@ -113,7 +113,7 @@ struct RicLayout {
     // (riccati_backward_step / riccati_forward_step)
     static constexpr int RC_K = 0, RC_XM = RC_K + (AINL ? NC * 13 : 0), RC_U6 = RC_XM + 120,
                          RC_GH = RC_U6 + 48, RC_KT = RC_GH + 48, RC_WQ = RC_KT + 78, RC_D = RC_WQ + 12,
-                         RC_KF = RC_D + 24, RC_TOTAL = RC_KF + (AINL ? 0 : 4 * 78);
+                         RC_UK = RC_D + 24, RC_KF = RC_UK + 6, RC_TOTAL = RC_KF + (AINL ? 0 : 4 * 78);
 };
 
 template <int N_, int NC_, bool AINL_ = true, bool TILED_ = false, bool RIC_ = false>
@@ -130,7 +130,8 @@ struct Tron1Work : RicStore<RIC_, RicLayout<N_, NC_, AINL_>::RC_TOTAL> {
     static constexpr int PKN = (NC + 1) * (NC + 2) / 2;  // packed lower triangle incl. rhs row
     static constexpr int NT = (NC + 8) / 8;              // tile rows covering rows 0..NC (row NC = right-hand side)
     static constexpr int TSZ = NT * (NT + 1) / 2 * 64;   // tiled lower triangle
-    static constexpr int ASZ = RIC_ ? NC * 13 : (TILED ? TSZ : PKN);   // doubles of matrix (Riccati: gain) storage per instance
+    static constexpr bool UEXT = RIC_ && !AINL_;         // Riccati work type with external gains: the forces live behind the gains in the same slab
+    static constexpr int ASZ = RIC_ ? NC * 13 + (UEXT ? 6 * N : 0) : (TILED ? TSZ : PKN);   // doubles of matrix (Riccati: gain + force) storage per instance
     double* Aext;           // external factor storage (only used when !AINL)
     alignas(16) double Astore[(AINL && !RIC_) ? ASZ : 2];   // reduced Hessian / Cholesky factor; the rhs is row nc (packed) or row NC (tiled)
     alignas(16) double pbuf[TILED ? NT * 64 + 128 : 2];  // tiled: current panel column + two inverse diagonal tiles (double buffer)
@@ -141,11 +142,11 @@ struct Tron1Work : RicStore<RIC_, RicLayout<N_, NC_, AINL_>::RC_TOTAL> {
     double w[RIC_ ? 2 : NC], z[RIC_ ? 2 : NC], y[RIC_ ? 2 : NC];   // compact solve vector, ADMM iterates
     using RL = RicLayout<N_, NC_, AINL_>;
     static constexpr int RC_K = RL::RC_K, RC_XM = RL::RC_XM, RC_U6 = RL::RC_U6, RC_GH = RL::RC_GH, RC_KT = RL::RC_KT,
-                         RC_WQ = RL::RC_WQ, RC_D = RL::RC_D, RC_KF = RL::RC_KF, RC_TOTAL = RL::RC_TOTAL;
+                         RC_WQ = RL::RC_WQ, RC_D = RL::RC_D, RC_UK = RL::RC_UK, RC_KF = RL::RC_KF, RC_TOTAL = RL::RC_TOTAL;
     double W[N * 18];       // W[k][foot] 3x3 row-major:  Iw_k^-1 [r]x
     double cs[N * 2];       // cos, sin of yaw_k
     double cc[N + 1], ss[N + 1];   // prefix sums  sum_{k<i} cos / sin
-    double dc[N], ds[N];    // D_j = 1/2 Rz_j' - C_{j+1}  (cos-like / sin-like entries)
+    double dc[RIC_ ? 1 : N], ds[RIC_ ? 1 : N];    // D_j = 1/2 Rz_j' - C_{j+1}  (cos-like / sin-like entries; the Riccati work type forms them on the fly)
     double SW[RIC_ ? 8 : N * 8];       // suffix sums over i>j of w_i * {1, cc, ss, cc^2, ss^2, cc ss, i, i^2}
     // Riccati work type: f is never formed (the gradient is the adjoint of the full tracking error), adj lives in the
     // caller's dead input staging area (adjx), g and res overlay the exchange buffers of the sweeps, and ee holds the
@@ -158,7 +159,7 @@ struct Tron1Work : RicStore<RIC_, RicLayout<N_, NC_, AINL_>::RC_TOTAL> {
     // the 3x3-block elimination uses them as its broadcast arrays (gj3_solve_regs); u must survive (swing feet stay 0)
     double ee[(N + 1) * 12];  // tracking error: free response during setup, input response later
     double adj[RIC_ ? 2 : (N + 1) * 18]; // adjoint terms / suffix sums; first 6(N+1) doubles double as `tau`
-    double g[GALIAS ? 2 : NV], u[NV];      // full layout: gradient, solution
+    double g[GALIAS ? 2 : NV], u[UEXT ? 2 : NV];      // full layout: gradient, solution
     double res[GALIAS ? 2 : NS];
     const double* x0;       // 13 doubles (staged by the caller)
     const double* feet;     // 6 or 6N doubles
@@ -175,6 +176,7 @@ struct Tron1Work : RicStore<RIC_, RicLayout<N_, NC_, AINL_>::RC_TOTAL> {
     MPC_HD double* adjp() { if constexpr (RIC_) return this->adjx; else return adj; }
     MPC_HD double* gp() { if constexpr (GALIAS) return this->rc + RC_XM; else return g; }
     MPC_HD double* resp() { if constexpr (GALIAS) return this->rc + RC_XM + NV; else return res; }
+    MPC_HD double* up() { if constexpr (UEXT) return Aext + NC * 13; else return u; }   // forces (full layout)
     MPC_HD double* tau() { return adjp(); }
     MPC_HD double* Kp() { if constexpr (AINL) return this->rc + RC_K; else return Aext; }   // Riccati gains: inside the struct or external (global memory)
     // address of the packed factor: a compile-time offset for the shared-memory case, a pointer otherwise
@@ -293,8 +295,10 @@ MPC_HD void horizon_sums(const Tron1Const& P, WK& S, const G& g) {
     for (int c = g.tid(); c < 2; c += g.size()) prefix_scan<N, 2, 1>(S.cs + c, c ? S.ss : S.cc, 1.0, false);
     g.sync();
     for (int j = g.tid(); j < N; j += g.size()) {
-        S.dc[j] = 0.5 * S.cs[2 * j] - S.cc[j + 1];
-        S.ds[j] = 0.5 * S.cs[2 * j + 1] - S.ss[j + 1];
+        if constexpr (!WK::RICCATI) {
+            S.dc[j] = 0.5 * S.cs[2 * j] - S.cc[j + 1];
+            S.ds[j] = 0.5 * S.cs[2 * j + 1] - S.ss[j + 1];
+        }
     }
     if constexpr (WK::RICCATI) { g.sync(); return; }   // the suffix sums below feed build_hessian only
     // per-step terms w_i * {1, cc_i, ss_i, cc_i^2, ss_i^2, cc_i ss_i, i, i^2} (parallel over i = 1..N) ...
@@ -407,7 +411,10 @@ MPC_HD void adjoint(const Tron1Const& P, WK& S, const double* e, double* out, co
         int j = s >> 1;
         const double* a = S.adjp() + 18 * j;
         const double* Wj = S.W + 9 * s;
-        double dc = S.dc[j], ds = S.ds[j], jh = (double)j + 0.5;
+        double dc, ds;
+        if constexpr (WK::RICCATI) { dc = 0.5 * S.cs[2 * j] - S.cc[j + 1]; ds = 0.5 * S.cs[2 * j + 1] - S.ss[j + 1]; }
+        else { dc = S.dc[j]; ds = S.ds[j]; }
+        const double jh = (double)j + 0.5;
         // sum_i S(i,j)' Q e_Theta
         double vt0 = a[0] + dc * a[3] - ds * a[4];
         double vt1 = a[1] + ds * a[3] + dc * a[4];
@@ -1373,15 +1380,15 @@ MPC_HD void gradient(const Tron1Const& P, WK& S, const G& g) {
         // the forward sweep left the full tracking error e0 + B u in S.ee: g = 2 B' Qbar (e0 + B u) + 2 r u in one adjoint pass
         adjoint<WK>(P, S, S.ee, S.gp(), g);
         MPC_TICK(S, g, 11);
-        for (int i = g.tid(); i < 6 * N; i += g.size()) S.gp()[i] += 2.0 * P.r * S.u[i];
+        for (int i = g.tid(); i < 6 * N; i += g.size()) S.gp()[i] += 2.0 * P.r * S.up()[i];
         g.sync();
         return;
     }
-    input_response<WK>(P, S, S.u, g);
+    input_response<WK>(P, S, S.up(), g);
     MPC_TICK(S, g, 10);
     adjoint<WK>(P, S, S.ee, S.gp(), g);
     MPC_TICK(S, g, 11);
-    for (int i = g.tid(); i < 6 * N; i += g.size()) S.gp()[i] += S.f[i] + 2.0 * P.r * S.u[i];
+    for (int i = g.tid(); i < 6 * N; i += g.size()) S.gp()[i] += S.f[i] + 2.0 * P.r * S.up()[i];
     g.sync();
 }
 
@@ -1423,14 +1430,15 @@ struct RicStep {     // uniform per step
     double* Ku;      // this step's forward gains in force space: 6 rows [Ku (12) | ku0] (left foot xyz, right foot xyz), u = ku0 + Ku d
 };
 
-template <class WK>
+template <int MM, class WK>
 MPC_HD RicStep ric_make_step(const Tron1Const& P, WK& S, int k) {
-    RicStep st;
+    RicStep st = {};
     st.k = k; st.sr = 2 * k + 1;
     st.f0 = S.contact[2 * k] ? 2 * k : 2 * k + 1;
     st.cz = S.cs[2 * k]; st.sz = S.cs[2 * k + 1];
     st.wk = step_weight<WK::N>(P, k);
-    for (int a = 0; a < 2; ++a) {
+#pragma unroll
+    for (int a = 0; a < MM / 3; ++a) {
         const int s_ = a == 0 ? st.f0 : st.sr;
         st.Z[a] = face_basis(P.mu, S.ax[s_], S.ay[s_], S.zt[s_]);
         const double fz = S.zt[s_] == 1 ? P.f_max : 0.0;
@@ -1461,7 +1469,7 @@ MPC_HD bool ric_inv3(const double* a, double* inv) {
 template <int MM, class WK, class G>
 MPC_HD bool riccati_backward_step(const Tron1Const& P, WK& S, const G& g, RicLane* LL, int k) {
     static_assert(G::kThreads == 32 || G::kThreads == 1, "the Riccati class maps one warp to an instance");
-    const RicStep st = ric_make_step<WK>(P, S, k);
+    const RicStep st = ric_make_step<MM, WK>(P, S, k);
     const double Ts = P.Ts, hTs = 0.5 * P.Ts, im = P.inv_m;
     double* XM = S.rc + WK::RC_XM;     // rows 0..5 of [X (12) | M (6) | t], stride 20
     double* U6 = S.rc + WK::RC_U6;     // [U6 row i (6) | lt(t)_i], stride 8
@@ -1693,7 +1701,8 @@ MPC_HD void riccati_forward_step(const Tron1Const& P, WK& S, const G& g, int k) 
         ric_fetch_gains<WK>(S, g, k + 3);
     }
     MPC_RTICK(2, S, g, 4);
-    double* uk = S.u + 6 * k;
+    // the forces of this step: read back by the state update below from shared memory (external storage: a copy goes there)
+    double* uk = WK::UEXT ? S.rc + WK::RC_UK : S.up() + 6 * k;
     {
         const double* Kk = WK::AINL ? S.Kp() + 78 * k : S.rc + WK::RC_KF + 78 * (k & 3);
         for (int i = g.tid(); i < 6; i += G::kThreads) {
@@ -1706,6 +1715,7 @@ MPC_HD void riccati_forward_step(const Tron1Const& P, WK& S, const G& g, int k) 
                 v = v0 + (v1 + v2);
             }
             uk[i] = v;
+            if constexpr (WK::UEXT) S.up()[6 * k + i] = v;
         }
         g.sync();
     }
@@ -1816,9 +1826,9 @@ MPC_HD bool face_solve(const Tron1Const& P, WK& S, const G& g) {
     }
     for (int s = g.tid(); s < 2 * N; s += g.size()) {
         double fz = (S.contact[s] && S.zt[s] == 1) ? P.f_max : 0.0;
-        S.u[3 * s] = (double)S.ax[s] * P.mu * fz;
-        S.u[3 * s + 1] = (double)S.ay[s] * P.mu * fz;
-        S.u[3 * s + 2] = fz;
+        S.up()[3 * s] = (double)S.ax[s] * P.mu * fz;
+        S.up()[3 * s + 1] = (double)S.ay[s] * P.mu * fz;
+        S.up()[3 * s + 2] = fz;
     }
     g.sync();
     if (any_fixed) gradient<WK>(P, S, g);   // g0 = f + H u_fix
@@ -1866,9 +1876,9 @@ MPC_HD bool face_solve(const Tron1Const& P, WK& S, const G& g) {
         const double* w = S.w + 3 * S.cidx[s];
         int zt = S.zt[s];
         double fz = zt == 0 ? w[2] : (zt == 1 ? P.f_max : 0.0);
-        S.u[3 * s + 2] = fz;
-        S.u[3 * s] = S.ax[s] != 0 ? (double)S.ax[s] * P.mu * fz : (zt == 2 ? 0.0 : w[0]);
-        S.u[3 * s + 1] = S.ay[s] != 0 ? (double)S.ay[s] * P.mu * fz : (zt == 2 ? 0.0 : w[1]);
+        S.up()[3 * s + 2] = fz;
+        S.up()[3 * s] = S.ax[s] != 0 ? (double)S.ax[s] * P.mu * fz : (zt == 2 ? 0.0 : w[0]);
+        S.up()[3 * s + 1] = S.ay[s] != 0 ? (double)S.ay[s] * P.mu * fz : (zt == 2 ? 0.0 : w[1]);
     }
     g.sync();
     MPC_TICK(S, g, 9);
@@ -1876,7 +1886,7 @@ MPC_HD bool face_solve(const Tron1Const& P, WK& S, const G& g) {
     }
 }
 
-// ---- optimality check of S.u: natural residual |u - P_C(u - gamma g)|_inf, predicts the next face --
+// ---- optimality check of S.up(): natural residual |u - P_C(u - gamma g)|_inf, predicts the next face --
 // returns true if converged; `changed` tells whether the predicted face differs from the current one
 template <class WK, class G>
 MPC_HD bool check_optimality(const Tron1Const& P, WK& S, const G& g, bool& changed, double& resid) {
@@ -1925,12 +1935,12 @@ MPC_HD bool check_optimality(const Tron1Const& P, WK& S, const G& g, bool& chang
         if (s < 2 * N && S.contact[s]) {
             double v[3], o[3];
             int ax, ay, zt;
-            for (int c = 0; c < 3; ++c) v[c] = S.u[3 * s + c] - P.gamma * S.gp()[3 * s + c];
+            for (int c = 0; c < 3; ++c) v[c] = S.up()[3 * s + c] - P.gamma * S.gp()[3 * s + c];
             project_pyramid(P.mu, P.f_max, v, o, ax, ay, zt);
             for (int c = 0; c < 3; ++c) {
-                double d = fabs(S.u[3 * s + c] - o[c]);
+                double d = fabs(S.up()[3 * s + c] - o[c]);
                 r = (!(d <= r) && r == r) ? d : r;   // NaN-propagating max
-                double a = fabs(S.u[3 * s + c]);
+                double a = fabs(S.up()[3 * s + c]);
                 um = a > um ? a : um;
             }
             S.nax[s] = (int8_t)ax; S.nay[s] = (int8_t)ay; S.nzt[s] = (int8_t)zt;
@@ -1956,12 +1966,12 @@ MPC_HD bool check_optimality(const Tron1Const& P, WK& S, const G& g, bool& chang
         if (s < 2 * N && S.contact[s]) {
             double v[3], o[3];
             int ax, ay, zt;
-            for (int c = 0; c < 3; ++c) v[c] = S.u[3 * s + c] - P.gamma * S.gp()[3 * s + c];
+            for (int c = 0; c < 3; ++c) v[c] = S.up()[3 * s + c] - P.gamma * S.gp()[3 * s + c];
             project_pyramid(P.mu, P.f_max, v, o, ax, ay, zt);
             for (int c = 0; c < 3; ++c) {
-                double d = fabs(S.u[3 * s + c] - o[c]);
+                double d = fabs(S.up()[3 * s + c] - o[c]);
                 r = (!(d <= r) && r == r) ? d : r;   // NaN-propagating max
-                double a = fabs(S.u[3 * s + c]);
+                double a = fabs(S.up()[3 * s + c]);
                 um = a > um ? a : um;
             }
             S.nax[s] = (int8_t)ax; S.nay[s] = (int8_t)ay; S.nzt[s] = (int8_t)zt;
@@ -1996,12 +2006,12 @@ MPC_HD bool check_optimality(const Tron1Const& P, WK& S, const G& g, bool& chang
             if (!S.contact[s]) continue;
             double v[3], o[3];
             int ax, ay, zt;
-            for (int c = 0; c < 3; ++c) v[c] = S.u[3 * s + c] - P.gamma * S.gp()[3 * s + c];
+            for (int c = 0; c < 3; ++c) v[c] = S.up()[3 * s + c] - P.gamma * S.gp()[3 * s + c];
             project_pyramid(P.mu, P.f_max, v, o, ax, ay, zt);
             for (int c = 0; c < 3; ++c) {
-                double d = fabs(S.u[3 * s + c] - o[c]);
+                double d = fabs(S.up()[3 * s + c] - o[c]);
                 r = (!(d <= r) && r == r) ? d : r;   // NaN-propagating max
-                double a = fabs(S.u[3 * s + c]);
+                double a = fabs(S.up()[3 * s + c]);
                 um = a > um ? a : um;
             }
             S.nax[s] = (int8_t)ax; S.nay[s] = (int8_t)ay; S.nzt[s] = (int8_t)zt;
@@ -2026,12 +2036,12 @@ MPC_HD bool check_optimality(const Tron1Const& P, WK& S, const G& g, bool& chang
         if (S.contact[s]) {
             double v[3], o[3];
             int ax, ay, zt;
-            for (int c = 0; c < 3; ++c) v[c] = S.u[3 * s + c] - P.gamma * S.gp()[3 * s + c];
+            for (int c = 0; c < 3; ++c) v[c] = S.up()[3 * s + c] - P.gamma * S.gp()[3 * s + c];
             project_pyramid(P.mu, P.f_max, v, o, ax, ay, zt);
             for (int c = 0; c < 3; ++c) {
-                double d = fabs(S.u[3 * s + c] - o[c]);
+                double d = fabs(S.up()[3 * s + c] - o[c]);
                 r = (!(d <= r) && r == r) ? d : r;   // NaN-propagating max
-                double a = fabs(S.u[3 * s + c]);
+                double a = fabs(S.up()[3 * s + c]);
                 um = a > um ? a : um;
             }
             S.nax[s] = (int8_t)ax; S.nay[s] = (int8_t)ay; S.nzt[s] = (int8_t)zt;
@@ -2133,7 +2143,7 @@ MPC_HD void setup_instance(const Tron1Const& P, WK& S, const double* xref, const
     MPC_TICK(S, g, 3);
 }
 
-// ---- full QP solve of one instance.  On exit S.u holds the forces (full layout). -----------------
+// ---- full QP solve of one instance.  On exit S.up() holds the forces (full layout). -----------------
 // iters = face solves + ADMM iterations.
 // `after_setup` runs once the staged inputs (xref, S.x0, S.feet) are dead: everything the iterations need has been
 // condensed into S by then, so a persistent kernel starts fetching its next instance into the same staging area there.
@@ -2174,12 +2184,12 @@ MPC_HD int solve_instance(const Tron1Const& P, WK& S, const double* xref, const 
         g.sync();
     }
     if (bad) {
-        for (int i = g.tid(); i < 6 * N; i += g.size()) S.u[i] = 0.0;
+        for (int i = g.tid(); i < 6 * N; i += g.size()) S.up()[i] = 0.0;
         g.sync();
         return ST_FAILED;
     }
     if (S.nc == 0) {
-        for (int i = g.tid(); i < 6 * N; i += g.size()) S.u[i] = 0.0;
+        for (int i = g.tid(); i < 6 * N; i += g.size()) S.up()[i] = 0.0;
         g.sync();
         return ST_SOLVED;
     }
@@ -2214,7 +2224,7 @@ MPC_HD int solve_instance(const Tron1Const& P, WK& S, const double* xref, const 
         if (!S.contact[s]) continue;
         double o[3];
         int ax, ay, zt;
-        project_pyramid(P.mu, P.f_max, S.u + 3 * s, o, ax, ay, zt);
+        project_pyramid(P.mu, P.f_max, S.up() + 3 * s, o, ax, ay, zt);
         for (int c = 0; c < 3; ++c) { S.z[3 * S.cidx[s] + c] = o[c]; S.y[3 * S.cidx[s] + c] = 0.0; }
     }
     g.sync();
@@ -2293,7 +2303,7 @@ MPC_HD int solve_instance(const Tron1Const& P, WK& S, const double* xref, const 
     }
     // not certified: return the last ADMM iterate (feasible by construction)
     for (int s = g.tid(); s < 2 * N; s += g.size())
-        for (int c = 0; c < 3; ++c) S.u[3 * s + c] = S.contact[s] ? S.z[3 * S.cidx[s] + c] : 0.0;
+        for (int c = 0; c < 3; ++c) S.up()[3 * s + c] = S.contact[s] ? S.z[3 * S.cidx[s] + c] : 0.0;
     g.sync();
     return ST_MAXITER;
     }
@@ -2328,13 +2338,13 @@ MPC_HD void nominal_feet(const double* x, const double* off_l, const double* off
 }
 
 // ---- plant update of the closed loop: x <- Ad x + Bd u0 (reference src/QPSolver.cpp:108-111) with the
-// step-0 model already in S (closed-form ZOH).  u0 = S.u[0..5].  One thread does the 12 updates.
+// step-0 model already in S (closed-form ZOH).  u0 = S.up()[0..5].  One thread does the 12 updates.
 template <class WK, class G>
 MPC_HD void integrate_state(const Tron1Const& P, WK& S, double* x, const G& g) {
     if (g.tid() == 0) {
         const double Ts = P.Ts;
         const double* W0 = S.W;
-        const double* u = S.u;
+        const double* u = S.up();
         double tau[3], phi[3];
         for (int i = 0; i < 3; ++i) {
             tau[i] = W0[i * 3] * u[0] + W0[i * 3 + 1] * u[1] + W0[i * 3 + 2] * u[2]

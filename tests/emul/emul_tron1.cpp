@@ -36,7 +36,7 @@ static int run_solve_nc(const Tron1Const& P, const double* x0, const double* xre
     GrpSerial g;
     int it = 0;
     int st = solve_instance<Work>(P, *S, xref, g, it);
-    std::memcpy(forces, S->u, sizeof(double) * 6 * N);
+    std::memcpy(forces, S->up(), sizeof(double) * 6 * N);
     if (iters) *iters = it;
     delete S;
     return st;
@@ -102,7 +102,7 @@ static int run_rollout(const Tron1Const& P, int steps, double* x, double oy, dou
         }
         int its = 0;
         int code = solve_instance<Work>(P, *S, xr, g, its, s > 0);
-        if (u_traj) std::memcpy(u_traj + 6 * s, S->u, sizeof(double) * 6);
+        if (u_traj) std::memcpy(u_traj + 6 * s, S->up(), sizeof(double) * 6);
         bad += code != 0;
         tot += its;
         integrate_state<Work>(P, *S, x, g);
@@ -129,7 +129,7 @@ static int run_solve_riccati(const Tron1Const& P, const double* x0, const double
     GrpSerial g;
     int it = 0;
     int st = solve_instance<Work>(P, *S, xref, g, it);
-    std::memcpy(forces, S->u, sizeof(double) * 6 * N);
+    std::memcpy(forces, S->up(), sizeof(double) * 6 * N);
     delete S;
     if (deferred) *deferred = (st == ST_DEFER);
     if (st == ST_DEFER) {
