@@ -97,7 +97,7 @@ def structured_flops(N, nc, iters, group_threads):
         # (A: 360 + 372 nf, B: 468 + 108 nf, C: 237 / 690, D: 13 columns x (3x3-block cofactor inverses + solves + force-space
         # rows) = 832 / 3185, E: 12 rows x (26 mm + 5)); forward step 12 lanes x 53 + 81 nf; gradient (one adjoint pass) + check
         # ~ 220 N; setup without f ~ 300 N.  Checked against ncu: 233.6 k computed against 246.5 k executed per trot solve
-        # (profiles/r2d_c4_solve_kernel.json), 413 k against 410 k per double-support solve with the first forward step version.
+        # (profiles/r2e_c4_solve_kernel.json), 413 k against 410 k per double-support solve with the first forward step version.
         nf = m / N                                   # stance feet per step (1 trot, 2 double support)
         back = N * (888.0 + (3373.0 - 888.0) * min(nf, 1.0) + (7595.0 - 3373.0) * max(nf - 1.0, 0.0))
         fwd = N * (636.0 + 81.0 * nf)
@@ -548,11 +548,11 @@ def run_gpu(args, cfg):
     fp64_peak = measure_fp64_peak(local)
     kernel_ms = ms / K / (cfg["steps"] if rollout else 1)       # per batch-solve (rollout: per control step)
     if cfg["standing"]:
-        nc, gthreads, kname = 6 * N, {10: 64, 20: 64, 50: 32}[N], {10: "tron1_solve_kernel<10,60,2,2,3,INDIRECT>", 20: "tron1_solve_kernel<20,120,2,2,1,INDIRECT>", 50: "tron1_solve_kernel<50,300,1,1,7,DIRECT,RICCATI>"}[N]
+        nc, gthreads, kname = 6 * N, {10: 64, 20: 64, 50: 32}[N], {10: "tron1_solve_kernel<10,60,2,2,3,INDIRECT>", 20: "tron1_solve_kernel<20,120,2,2,1,INDIRECT>", 50: "tron1_solve_kernel<50,300,1,1,8,DIRECT,RICCATI>"}[N]
     else:
         nc, gthreads = 3 * N, {10: 32, 20: 64, 50: 32}[N]
         kname = {10: "tron1_solve_kernel<10,30,1,4,4,DIRECT,persistent>", 20: "tron1_solve_kernel<20,60,2,2,2,DIRECT,persistent>",
-                 50: "tron1_solve_kernel<50,300,1,1,7,DIRECT,RICCATI> (one warp per instance, Riccati sweeps)"}[N]
+                 50: "tron1_solve_kernel<50,300,1,1,8,DIRECT,RICCATI> (one warp per instance, Riccati sweeps)"}[N]
         if rollout:
             kname = "tron1_rollout_kernel<10,30,1,4,4>"
     f_exec, f_tensor = structured_flops(N, nc, max(mean_iters, 1.0), gthreads)

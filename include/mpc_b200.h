@@ -81,7 +81,7 @@ int mpc_b200_measure_fp64_peak(int device, double *tflops);
 
 /* engine lifetime.  horizon N must be one of the compiled horizons (10, 20, 50; closed-loop rollout: 10, 20).
  * Device memory per engine: the batch buffers of the host entry points (about 2 KB x max_batch at N = 10), two overflow lists
- * (8 B x 7 x max_batch) and, for horizon 50, 37 MB of gain slabs for the Riccati class (8 x SM count slabs of 31 KB, handed out
+ * (8 B x 7 x max_batch) and, for horizon 50, 40 MB of gain / force slabs for the Riccati class (8 x SM count slabs of 34 KB, handed out
  * through a ring of free slabs, so any number of concurrent launches shares them) plus the factor slabs of the dense class. */
 int mpc_b200_tron1_default_params(mpc_b200_tron1_params *p);
 int mpc_b200_create(const mpc_b200_tron1_params *p, int horizon, int max_batch, int device,
