@@ -1425,6 +1425,7 @@ struct RicLane {
 struct RicStep {     // uniform per step
     int k, f0, sr;   // step, foot-step of the first stance foot (compact columns 0..2), right foot-step (columns 3..5 when both stand)
     double cz, sz, wk;
+    double two;      // 2.0 the compiler cannot see through: 2 x - y stays one fused operation instead of (x + x) - y
     FaceZ Z[2];      // face basis per compact slot
     double cfx[2], cfy[2], cfz[2];   // fixed part c of u = c + Z w per slot (non-zero only with the normal force at its upper bound)
     double* Ku;      // this step's forward gains in force space: 6 rows [Ku (12) | ku0] (left foot xyz, right foot xyz), u = ku0 + Ku d
@@ -1437,6 +1438,7 @@ MPC_HD RicStep ric_make_step(const Tron1Const& P, WK& S, int k) {
     st.f0 = S.contact[2 * k] ? 2 * k : 2 * k + 1;
     st.cz = S.cs[2 * k]; st.sz = S.cs[2 * k + 1];
     st.wk = step_weight<WK::N>(P, k);
+    st.two = 2.0 + 0.0 * P.Ts;
 #pragma unroll
     for (int a = 0; a < MM / 3; ++a) {
         const int s_ = a == 0 ? st.f0 : st.sr;
@@ -1487,7 +1489,7 @@ MPC_HD bool riccati_backward_step(const Tron1Const& P, WK& S, const G& g, RicLan
 #pragma unroll
         for (int j = 3; j < 6; ++j) PT[j] = hTs * L.Pr[j] + L.Pr[6 + j];
 #pragma unroll
-        for (int j = 0; j < 6; ++j) { L.X[j] = L.Pr[j]; L.X[6 + j] = 2.0 * PT[j] - L.Pr[6 + j]; }
+        for (int j = 0; j < 6; ++j) { L.X[j] = L.Pr[j]; L.X[6 + j] = fma(st.two, PT[j], -L.Pr[6 + j]); }
         double t = L.s;
 #pragma unroll
         for (int a = 0; a < MM / 3; ++a) {
@@ -1524,17 +1526,17 @@ MPC_HD bool riccati_backward_step(const Tron1Const& P, WK& S, const G& g, RicLan
 #pragma unroll
         for (int j = 0; j < 12; ++j) {
             const double lt = ca * ra[j] + cb * rb[j] + L.X[j];
-            L.X[j] = 2.0 * lt - L.X[j];
+            L.X[j] = fma(st.two, lt, -L.X[j]);
         }
 #pragma unroll
         for (int b = 0; b < MM; ++b) {
             const double lt = ca * ra[12 + b] + cb * rb[12 + b] + L.M[b];
             urow[b] = lt;
-            L.M[b] = 2.0 * lt - L.M[b];
+            L.M[b] = fma(st.two, lt, -L.M[b]);
         }
         const double lt = ca * ra[18] + cb * rb[18] + L.t;
         urow[6] = lt;
-        L.t = 2.0 * lt - L.t;
+        L.t = fma(st.two, lt, -L.t);
     });
     if constexpr (MM > 0) {
         g.sync();
@@ -1648,7 +1650,12 @@ MPC_HD bool riccati_backward_step(const Tron1Const& P, WK& S, const G& g, RicLan
 #pragma unroll
                     for (int a = 0; a < MM; ++a) v = fma(-L.M[a], KT[6 * j + a], v);
                 }
+#if defined(__CUDA_ARCH__)
+                // one compare and one predicated add (the compiler's select form costs an add and two selects per entry)
+                asm("{\n.reg .pred p;\nsetp.eq.s32 p, %1, %2;\n@p add.f64 %0, %0, %3;\n}" : "+d"(v) : "r"(lane), "r"(j), "d"(wqr));
+#else
                 if (j == lane) v += wqr;
+#endif
                 L.Pr[j] = v;
             }
             double v = L.t;
