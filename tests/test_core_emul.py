@@ -126,6 +126,37 @@ def test_riccati_face_solves_match_dense_path_and_oracle(N, Ts, standing, scale,
         assert np.all(F.reshape(N, 2, 3)[contact == 0] == 0.0)
 
 
+@pytest.mark.parametrize("N,ltv,seed", [(4, 1, 0), (10, 1, 1), (10, 0, 2), (20, 1, 3), (20, 0, 4)])
+def test_riccati_random_contact_patterns_match_dense_path(N, ltv, seed):
+    """Arbitrary contact patterns (flight steps, single and double support mixed, a foot that never lands), the frozen-model
+    and the per-step-model modes, scaled states that leave the interior face: the Riccati sweeps (gains inside the struct and
+    in external storage) reproduce the dense path's faces, iteration counts and forces."""
+    Ts, B = 0.01, 6
+    rng = np.random.default_rng(100 + seed)
+    d = synth.tron1_batch(50 + seed, B, N, Ts, standing=True)
+    pe = E.default_params(Ts=Ts, ltv=ltv, mu=0.35)
+    po = O.tron1_defaults(Ts=Ts, ltv=ltv, mu=0.35)
+    n_deferred = 0
+    for b in range(B):
+        x0 = d["x0"][b].copy(); x0[[0, 1, 6, 7, 8, 9, 10, 11]] *= (1.0 + b)
+        contact = (rng.random((N, 2)) < 0.7).astype(np.uint8)
+        if b == 0: contact[:, 1] = 0                     # the right foot never lands
+        if b == 1: contact[N // 2] = 0                   # a flight step in the middle of the horizon
+        if contact.sum() == 0: contact[0, 0] = 1
+        F2, st2, it2 = E.solve(pe, N, x0, d["x_ref"][b], d["feet"][b], contact)
+        for ext in (False, True):
+            F, st, it, deferred = E.solve_riccati(pe, N, x0, d["x_ref"][b], d["feet"][b], contact, ext_gains=ext)
+            # an instance the active-face iteration does not certify is handed to the dense path (which then pays its own
+            # iterations on top of the max_newton sweeps already spent)
+            assert st == 0 and st2 == 0 and it == it2 + (pe.max_newton if deferred else 0), (b, ext, st, st2, it, it2, deferred)
+            n_deferred += int(bool(deferred))
+            assert np.abs(F - F2).max() / max(1.0, np.abs(F2).max()) < 1e-8
+            assert np.all(F.reshape(N, 2, 3)[contact == 0] == 0.0)
+        c = O.tron1_condense(po, N, x0, d["x_ref"][b], d["feet"][b], want_pred=False)
+        assert O.tron1_natural_residual(po, N, c["H"], c["f"], contact, F) < 1e-6
+    assert n_deferred <= 2 * 2                              # the hand-over is the exception
+
+
 def test_admm_fallback_path():
     """max_newton=1 forces every instance whose first face guess is wrong through ADMM + polish."""
     N, Ts, B = 10, 0.02, 12
