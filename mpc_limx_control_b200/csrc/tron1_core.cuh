@@ -102,7 +102,7 @@ MPC_HD void gait_contact(const Tron1Const& P, int iter, int& left_stance, int& r
 // budget of four CTAs per SM, stays exactly as it was)
 template <bool RIC_, int RC_TOTAL_>
 struct RicStore {
-    alignas(16) double rc[RC_TOTAL_];   // saved free-response error, gains (when inside the struct), exchange buffers of one step
+    alignas(16) double rc[RC_TOTAL_];   // gains (when inside the struct), exchange buffers of one step
     double* adjx;                       // 18 (N + 1) doubles of adjoint scratch provided by the caller
 };
 template <int RC_TOTAL_>
